@@ -1,0 +1,624 @@
+/* TEST INFRASTRUCTURE ONLY -- see cbq_oracle.h for scope and parity status (PINNED against
+ * oracle/_ref, the unmodified reference build).
+ *
+ * Plain-C restatement of:
+ *   findSubDAG / findSubDAGs      src/library/raytracing.cpp:43-97
+ *   findNearestMaterial           src/library/raytracing.cpp:134-162
+ *   findFirstChild                src/library/raytracing.cpp:178-196
+ *   intersectRayNodeESVO          src/library/raytracing.cpp:213-371
+ *   intersectVolume               src/library/raytracing.cpp:407-478
+ *   Camera::rayFromViewportPos    src/application/commands/view/camera.cpp:12-66
+ *   PathtracingDemo bounce loop   src/application/commands/view/pathtracing_demo.cpp:33-229
+ *   fnv1a / bit_mix               src/library/base.cpp:62-77
+ *   GLSL bitMix / hashRay         src/application/commands/view/glsl/pathtracing.frag:287-296,770-780
+ *
+ * Arithmetic contract: FP32 throughout the ray cast, no FMA contraction
+ * (-ffp-contract=off), IEEE division, min/max with the comparison semantics of
+ * std::min/std::max, truncating float->int casts, arithmetic >> on negative ints.
+ */
+#define _POSIX_C_SOURCE 200809L
+#include "cbq_oracle.h"
+
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#define MATERIAL_COUNT 256u   /* storage.h:55 */
+#define ROOT_HEIGHT 32        /* raytracing.cpp:12 */
+
+/* std::min(a,b) returns b only when b < a; std::max(a,b) returns b only when a < b. */
+static inline float min_std(float a, float b) { return (b < a) ? b : a; }
+static inline float max_std(float a, float b) { return (a < b) ? b : a; }
+static inline float least3(const float v[3]) { return min_std(min_std(v[0], v[1]), v[2]); }    /* raytracing.cpp:168-171 */
+static inline float greatest3(const float v[3]) { return max_std(max_std(v[0], v[1]), v[2]); } /* raytracing.cpp:173-176 */
+
+static inline int msb_index(uint32_t v)   /* raytracing.cpp:16-24, findMSB(0) == -1 */
+{
+	int r = -1;
+	while (v) { r++; v >>= 1; }
+	return r;
+}
+
+uint64_t cbqo_iteration_cap(int subdagHeight)
+{
+	uint64_t cap = (subdagHeight >= 20) ? (UINT64_C(1) << 26) : ((UINT64_C(64) << subdagHeight) + 4096);
+	return cap;
+}
+
+/* ---------------------------------------------------------------- sub-DAGs */
+
+static void find_one_subdag(const uint32_t* nodes, uint32_t root, uint32_t octant, cbqo_subdag* out)
+{
+	/* raytracing.cpp:43-87: follow the chain of single-occupied-child nodes below one root octant. */
+	int height = 32;
+	uint32_t lower[3] = { 0x80000000u, 0x80000000u, 0x80000000u }; /* INT_MIN as bits */
+	uint32_t only = octant;
+	uint32_t next = nodes[(uint64_t)root * 8 + only];
+	uint32_t node = 0;
+	uint32_t occupied = 1;
+	while (occupied == 1) {
+		height--;
+		node = next;
+		for (int a = 0; a < 3; a++) {
+			/* childIdAsIVec3 <<= childHeight; lowerBound ^= ... (:62-64) */
+			lower[a] ^= ((only >> a) & 1u) << height;
+		}
+		occupied = 0;
+		for (uint32_t c = 0; c < 8; c++) {
+			uint32_t child = nodes[(uint64_t)node * 8 + c];
+			if (child > 0) { next = child; occupied++; only = c; }
+		}
+	}
+	memset(out, 0, sizeof(*out));
+	for (int a = 0; a < 3; a++) out->lower[a] = (int32_t)lower[a];
+	out->height = height;
+	out->node = node;
+}
+
+void cbqo_find_subdags(const uint32_t* nodes, uint32_t root, cbqo_subdag out[8])
+{
+	for (uint32_t c = 0; c < 8; c++) find_one_subdag(nodes, root, c, &out[c]); /* raytracing.cpp:89-97 */
+}
+
+/* ---------------------------------------------------------------- ray cast */
+
+static uint32_t nearest_material(const uint32_t* nodes, uint32_t node, uint32_t signBits, cbqo_stats* st)
+{
+	/* raytracing.cpp:134-162: fixed near-to-far child order, reflected by the ray's sign bits. */
+	const uint32_t order = (0x76534210u | 0x88888888u) ^ (signBits * 0x11111111u);
+	while (node >= MATERIAL_COUNT) {
+		for (uint32_t ids = order; ids != 0; ids >>= 4) {
+			uint32_t child = nodes[(uint64_t)node * 8 + (ids & 7u)];
+			if (st) st->material_steps++;
+			if (child > 0) { node = child; break; }
+		}
+	}
+	return node;
+}
+
+static void first_child(float tEntry, const float o[3], const float inv[3], const int32_t centre[3], int32_t id[3])
+{
+	/* raytracing.cpp:178-196 */
+	for (int a = 0; a < 3; a++) {
+		float tm = ((float)centre[a] - o[a]) * inv[a];
+		id[a] = (tm < tEntry) ? 1 : 0;
+	}
+	if (tEntry <= 0) {
+		for (int a = 0; a < 3; a++) id[a] |= (o[a] >= (float)centre[a]) ? 1 : 0;
+	}
+}
+
+/* One sub-DAG, reflected ray. Returns 1 on hit. raytracing.cpp:213-371. */
+static int esvo_node(const uint32_t* nodes, uint32_t node, const int32_t nodePos[3], int nodeHeight,
+	const float o[3], const float d[3], const float sign[3], uint32_t signBits,
+	int surf, float maxFootprint, cbqo_hit* hit, cbqo_stats* st)
+{
+	const uint32_t nodeSize = 1u << nodeHeight;
+	float inv[3], t0[3], t1[3];
+	for (int a = 0; a < 3; a++) {
+		inv[a] = 1.0f / d[a];
+		t0[a] = ((float)nodePos[a] - o[a]) * inv[a];
+		t1[a] = (((float)nodePos[a] + (float)nodeSize) - o[a]) * inv[a];
+	}
+	const float nodeEntry = greatest3(t0);
+	const float nodeExit = least3(t1);
+	if (!(nodeEntry < nodeExit)) return 0;
+	if (st) st->subdag_entries++;
+
+	const int startHeight = nodeHeight;
+	int32_t childSize = (int32_t)(nodeSize / 2);
+	int32_t id[3], pos[3], centre[3];
+	for (int a = 0; a < 3; a++) centre[a] = (int32_t)((uint32_t)nodePos[a] + (uint32_t)childSize);
+	first_child(nodeEntry, o, inv, centre, id);
+	for (int a = 0; a < 3; a++) pos[a] = (int32_t)((uint32_t)nodePos[a] + (uint32_t)(id[a] * childSize));
+
+	float lastExit = nodeExit;
+	uint32_t stack[ROOT_HEIGHT + 1];
+	memset(stack, 0, sizeof(stack)); /* the reference leaves it uninitialised; slot 32 is read-then-discarded */
+	int found = 0;
+
+	/* QUIRK Q5 (ours to handle, not in the reference): with a zero direction component and the
+	 * reflected origin exactly on a cell boundary, (pos - o) * inf is NaN, no sibling flip is ever
+	 * taken and the reference's loop never ends. A legitimate traversal of a height-h sub-DAG takes
+	 * fewer than 8 * 2^h trips, so give up after cbqo_iteration_cap(h) and report
+	 * "no hit, pad = 1". The GPU kernel applies the identical rule. */
+	const uint64_t cap = cbqo_iteration_cap(startHeight);
+	uint64_t trips = 0;
+
+	do {
+		if (++trips > cap) { hit->pad = 1; return 0; }
+		if (st) st->iterations++;
+		float c1[3];
+		for (int a = 0; a < 3; a++) {
+			c1[a] = ((float)(int32_t)((uint32_t)pos[a] + (uint32_t)childSize) - o[a]) * inv[a];
+		}
+		const float tExit = least3(c1);
+
+		const uint32_t slot = (uint32_t)((id[0] & 1) | ((id[1] & 1) << 1) | ((id[2] & 1) << 2));
+		const uint32_t child = nodes[(uint64_t)node * 8 + (slot ^ signBits)];
+
+		if (child > 0) {
+			float c0[3];
+			for (int a = 0; a < 3; a++) c0[a] = ((float)pos[a] - o[a]) * inv[a];
+			const float tEntry = greatest3(c0);
+			const int internal = child >= MATERIAL_COUNT;
+			const int bigEnough = ((float)childSize / tExit) > maxFootprint;
+			if (internal && bigEnough) {
+				if (st) st->descents++;
+				if (tExit < lastExit) stack[nodeHeight] = node;
+				lastExit = tExit;
+				nodeHeight--;
+				node = child;
+				childSize /= 2;
+				for (int a = 0; a < 3; a++) centre[a] = (int32_t)((uint32_t)pos[a] + (uint32_t)childSize);
+				first_child(tEntry, o, inv, centre, id);
+				for (int a = 0; a < 3; a++) pos[a] = (int32_t)((uint32_t)pos[a] + (uint32_t)(id[a] * childSize));
+			} else {
+				found = 1;
+				hit->hit = 1;
+				hit->distance = tEntry;
+				if (surf) {
+					hit->material = nearest_material(nodes, child, signBits, st);
+					for (int a = 0; a < 3; a++) {
+						float n = (tEntry == c0[a]) ? 1.0f : 0.0f;
+						hit->normal[a] = n * (-sign[a]);
+					}
+				}
+			}
+		} else {
+			int32_t flips[3], old[3];
+			int wrapped = 0;
+			for (int a = 0; a < 3; a++) {
+				flips[a] = (c1[a] <= tExit) ? 1 : 0;
+				id[a] ^= flips[a];
+				old[a] = pos[a];
+				pos[a] = (int32_t)((uint32_t)pos[a] + (uint32_t)(flips[a] * childSize));
+				if ((id[a] & flips[a]) != flips[a]) wrapped = 1;
+			}
+			if (wrapped) {
+				if (st) st->pops++;
+				uint32_t diff = 0;
+				for (int a = 0; a < 3; a++) diff |= (uint32_t)(old[a] ^ pos[a]);
+				const int msb = msb_index(diff);
+				nodeHeight = msb + 1;
+				node = stack[nodeHeight <= ROOT_HEIGHT ? nodeHeight : ROOT_HEIGHT];
+				if (nodeHeight <= startHeight) {
+					/* Only reachable with nodeHeight <= 31, so the shifts below are defined.
+					 * (When nodeHeight reaches 32 the reference evaluates x >> 32 and then leaves
+					 * the loop because 32 > startHeight; nothing computed there is used.) */
+					childSize = (int32_t)(1u << msb);
+					for (int a = 0; a < 3; a++) {
+						id[a] = (pos[a] >> msb) & 1;
+						pos[a] = (int32_t)(((uint32_t)(pos[a] >> nodeHeight)) << nodeHeight);
+						pos[a] = (int32_t)((uint32_t)pos[a] + (uint32_t)(id[a] * childSize));
+					}
+				}
+				lastExit = 0.0f;
+			}
+		}
+	} while (!found && nodeHeight <= startHeight);
+	return found;
+}
+
+void cbqo_intersect(const uint32_t* nodes, const cbqo_subdag sd[8], const cbqo_ray* ray,
+	int surf, float maxFootprint, cbqo_hit* out, cbqo_stats* st)
+{
+	/* raytracing.cpp:407-478 */
+	memset(out, 0, sizeof(*out));
+	if (st) st->rays++;
+
+	int32_t neg[3];
+	float sign[3], ro[3], rd[3], dist[3];
+	uint32_t signBits = 0;
+	for (int a = 0; a < 3; a++) {
+		neg[a] = (ray->d[a] < 0.0f) ? 1 : 0;              /* -0.0 counts as positive (:416) */
+		signBits |= (uint32_t)neg[a] << a;
+		sign[a] = (float)(neg[a] * (-2) + 1);
+		ro[a] = (ray->o[a] + 0.5f) * sign[a];
+		rd[a] = fabsf(ray->d[a]);
+		dist[a] = (-ro[a]) / rd[a];
+	}
+	int octant = 0;
+	for (int a = 0; a < 3; a++) {
+		if (dist[a] < 0.0) { octant += 1 << a; dist[a] += FLT_MAX; }
+	}
+
+	int octantTrips = 0;
+	do {
+		/* Q5 again: -0/0 = NaN in dist[] means the octant id below never advances. A legitimate
+		 * ray visits at most 8 octants. */
+		if (++octantTrips > 8) { memset(out, 0, sizeof(*out)); out->pad = 1; break; }
+		const cbqo_subdag* s = &sd[(uint32_t)octant ^ signBits];
+		if (s->node > 0) {
+			const int32_t size = (int32_t)(1u << s->height);
+			int32_t lb[3];
+			for (int a = 0; a < 3; a++) {
+				/* lowerBound * ivec3(rayDirSign) - signBit * nodeSize, all with int wrap-around (:454-456) */
+				uint32_t v = (uint32_t)s->lower[a] * (uint32_t)(int32_t)sign[a];
+				v -= (uint32_t)neg[a] * (uint32_t)size;
+				lb[a] = (int32_t)v;
+			}
+			if (esvo_node(nodes, s->node, lb, s->height, ro, rd, sign, signBits, surf, maxFootprint, out, st)) {
+				for (int a = 0; a < 3; a++) out->position[a] = ray->o[a] + (ray->d[a] * out->distance);
+				if (st) st->hits++;
+				break;
+			}
+			if (out->pad) break; /* Q5: traversal abandoned */
+		}
+		const float nearest = least3(dist);
+		for (int a = 0; a < 3; a++) {
+			if (dist[a] <= nearest) { octant += 1 << a; dist[a] += FLT_MAX; }
+		}
+	} while (octant <= 7);
+}
+
+/* ---------------------------------------------------------------- threading helper */
+
+typedef struct {
+	const uint32_t* nodes; const cbqo_subdag* sd; const cbqo_ray* rays; uint64_t n;
+	int surf; float maxFootprint; cbqo_hit* hits; cbqo_stats stats; int wantStats;
+	uint64_t* cursor; pthread_mutex_t* lock;
+} trace_job;
+
+static double now_s(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static void* trace_worker(void* arg)
+{
+	trace_job* j = (trace_job*)arg;
+	const uint64_t chunk = 4096;
+	for (;;) {
+		pthread_mutex_lock(j->lock);
+		uint64_t b = *j->cursor;
+		*j->cursor = b + chunk;
+		pthread_mutex_unlock(j->lock);
+		if (b >= j->n) break;
+		uint64_t e = b + chunk < j->n ? b + chunk : j->n;
+		cbqo_hit scratch;
+		for (uint64_t i = b; i < e; i++) {
+			cbqo_intersect(j->nodes, j->sd, &j->rays[i], j->surf, j->maxFootprint,
+				j->hits ? &j->hits[i] : &scratch, j->wantStats ? &j->stats : NULL);
+		}
+	}
+	return NULL;
+}
+
+double cbqo_trace(const uint32_t* nodes, const cbqo_subdag sd[8], const cbqo_ray* rays, uint64_t n,
+	int surf, float maxFootprint, cbqo_hit* hits, int threads, cbqo_stats* stats)
+{
+	if (threads < 1) threads = 1;
+	if (threads > 256) threads = 256;
+	pthread_mutex_t lock = PTHREAD_MUTEX_INITIALIZER;
+	uint64_t cursor = 0;
+	trace_job* jobs = (trace_job*)calloc((size_t)threads, sizeof(trace_job));
+	pthread_t* tids = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+	for (int t = 0; t < threads; t++) {
+		trace_job j = { nodes, sd, rays, n, surf, maxFootprint, hits, {0,0,0,0,0,0,0}, stats != NULL, &cursor, &lock };
+		jobs[t] = j;
+	}
+	double t0 = now_s();
+	if (threads == 1) {
+		trace_worker(&jobs[0]);
+	} else {
+		for (int t = 0; t < threads; t++) pthread_create(&tids[t], NULL, trace_worker, &jobs[t]);
+		for (int t = 0; t < threads; t++) pthread_join(tids[t], NULL);
+	}
+	double t1 = now_s();
+	if (stats) {
+		memset(stats, 0, sizeof(*stats));
+		for (int t = 0; t < threads; t++) {
+			stats->rays += jobs[t].stats.rays; stats->hits += jobs[t].stats.hits;
+			stats->subdag_entries += jobs[t].stats.subdag_entries;
+			stats->iterations += jobs[t].stats.iterations; stats->descents += jobs[t].stats.descents;
+			stats->pops += jobs[t].stats.pops; stats->material_steps += jobs[t].stats.material_steps;
+		}
+	}
+	free(jobs); free(tids);
+	return t1 - t0;
+}
+
+/* ---------------------------------------------------------------- hashes */
+
+uint64_t cbqo_bit_mix64(uint64_t b)  /* base.cpp:72-77 ('xmxmx') */
+{
+	b = ((b >> 32) ^ b) * UINT64_C(0x0e9846af9b1a615d);
+	b = ((b >> 32) ^ b) * UINT64_C(0x0e9846af9b1a615d);
+	return (b >> 28) ^ b;
+}
+
+uint64_t cbqo_fnv1a(const void* data, int64_t len)  /* base.cpp:62-69, default seed base.h:51 */
+{
+	uint64_t h = UINT64_C(0xcbf29ce484222325);
+	const uint8_t* p = (const uint8_t*)data;
+	for (int64_t i = 0; i < len; i++) { h ^= p[i]; h *= UINT64_C(0x00000100000001B3); }
+	return h;
+}
+
+uint32_t cbqo_fmix32(uint32_t h)  /* glsl/pathtracing.frag:287-296 */
+{
+	h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+	return h;
+}
+
+/* ---------------------------------------------------------------- camera */
+
+void cbqo_camera_from_pose(const double position[3], double pitch, double yaw, double fovDegrees, cbqo_camera* c)
+{
+	/* camera.cpp:40-66. Pi is the FLOAT constant of camera.h:6. */
+	const float Pi = 3.14159265358979f;
+	memset(c, 0, sizeof(*c));
+	for (int a = 0; a < 3; a++) c->position[a] = position[a];
+	c->forward[0] = cos(pitch) * sin(yaw);
+	c->forward[1] = cos(pitch) * cos(yaw);
+	c->forward[2] = sin(pitch);
+	c->right[0] = sin(yaw + (Pi / 2));
+	c->right[1] = cos(yaw + (Pi / 2));
+	c->right[2] = 0;
+	/* up = cross(right, forward), linalg.h cross */
+	c->up[0] = c->right[1] * c->forward[2] - c->right[2] * c->forward[1];
+	c->up[1] = c->right[2] * c->forward[0] - c->right[0] * c->forward[2];
+	c->up[2] = c->right[0] * c->forward[1] - c->right[1] * c->forward[0];
+	c->scale = (float)(tan(fovDegrees * 0.0174533f * 0.5f) * 2.0f);  /* camera.cpp:24 */
+}
+
+void cbqo_camera_ray(const cbqo_camera* c, int x, int y, int width, int height, cbqo_ray* out)
+{
+	/* camera.cpp:19-35, mixed float/double exactly as written there. */
+	const double invWidth = 1.0f / width;
+	const double invHeight = 1.0f / height;
+	const float aspect = (float)width / (float)height;
+	const float xOff = x - (width / 2.0f) + 0.5f;
+	const float yOff = y - (height / 2.0f) + 0.5f;
+	const double kx = invWidth * xOff * aspect * c->scale;
+	const double ky = invHeight * yOff * c->scale;
+	double target[3], dir[3];
+	for (int a = 0; a < 3; a++) {
+		target[a] = c->position[a] + c->forward[a];
+		target[a] += c->right[a] * kx;
+		target[a] -= c->up[a] * ky;
+		dir[a] = target[a] - c->position[a];
+	}
+	/* linalg normalize: a / sqrt(sum(a*a)), sum folds left from 0 (linalg.h:401,501-504) */
+	const double len = sqrt(((0.0 + dir[0] * dir[0]) + dir[1] * dir[1]) + dir[2] * dir[2]);
+	for (int a = 0; a < 3; a++) {
+		out->o[a] = (float)c->position[a];
+		out->d[a] = (float)(dir[a] / len);
+	}
+}
+
+void cbqo_camera_rays(const cbqo_camera* c, int width, int height, cbqo_ray* out)
+{
+	for (int y = 0; y < height; y++)
+		for (int x = 0; x < width; x++)
+			cbqo_camera_ray(c, x, y, width, height, &out[(size_t)y * (size_t)width + (size_t)x]);
+}
+
+/* ---------------------------------------------------------------- path tracer */
+
+typedef struct {
+	const uint32_t* nodes; const cbqo_subdag* sd; const float* colours;
+	const cbqo_pt_params* p;
+	uint32_t rng;        /* per-sample stream; the reference's is one process-global (pathtracing_demo.cpp:33) */
+	uint64_t rays;
+} pt_state;
+
+static inline float dot3(const float a[3], const float b[3])
+{
+	return ((0.0f + a[0] * b[0]) + a[1] * b[1]) + a[2] * b[2];   /* linalg sum(a*b) */
+}
+
+static inline void normalize3(const float v[3], float out[3])
+{
+	const float len = sqrtf(dot3(v, v));
+	for (int a = 0; a < 3; a++) out[a] = v[a] / len;
+}
+
+static void unit_ball_point(pt_state* s, float out[3])
+{
+	/* pathtracing_demo.cpp:62-79 */
+	do {
+		s->rng = (uint32_t)cbqo_bit_mix64(s->rng);
+		out[0] = (float)(s->rng & 0x3FFu);
+		out[1] = (float)((s->rng >> 10) & 0x3FFu);
+		out[2] = (float)((s->rng >> 20) & 0x3FFu);
+		for (int a = 0; a < 3; a++) { out[a] = out[a] - 511.5f; out[a] = out[a] / 511.5f; }
+	} while (dot3(out, out) >= 1.0f);
+}
+
+static void cast(pt_state* s, const float o[3], const float d[3], int surf, cbqo_hit* h)
+{
+	cbqo_ray r;
+	for (int a = 0; a < 3; a++) { r.o[a] = o[a]; r.d[a] = d[a]; }
+	cbqo_intersect(s->nodes, s->sd, &r, surf, s->p->max_footprint, h, NULL);
+	s->rays++;
+}
+
+static void surface_colour(const pt_state* s, const cbqo_hit* h, float out[3])
+{
+	/* pathtracing_demo.cpp:36-60 */
+	for (int a = 0; a < 3; a++) out[a] = s->colours[3 * h->material + a];
+	if (s->p->add_noise) {
+		int32_t cell[3];
+		for (int a = 0; a < 3; a++) cell[a] = (int32_t)(h->position[a] + 0.499f);
+		const uint32_t hash = (uint32_t)cbqo_fnv1a(cell, sizeof(cell));
+		float noise = (float)(hash & 0xffu) / 255.0f;
+		noise = (float)(((double)noise * 0.1) + 0.9);
+		for (int a = 0; a < 3; a++) out[a] *= noise;
+	}
+}
+
+static void gather_lighting(pt_state* s, const float pos[3], const float nrm[3], float out[3])
+{
+	/* pathtracing_demo.cpp:81-118 */
+	float start[3];
+	for (int a = 0; a < 3; a++) { start[a] = pos[a] + nrm[a] * 0.001f; out[a] = 0.0f; }
+	cbqo_hit h;
+	if (s->p->include_sun) {
+		const float sunRaw[3] = { 1.0f, -2.0f, 10.0f };
+		float sunDir[3];
+		normalize3(sunRaw, sunDir);
+		cast(s, start, sunDir, 0, &h);
+		if (!h.hit) {
+			const float k = max_std(dot3(sunDir, nrm), 0.0f);
+			for (int a = 0; a < 3; a++) out[a] += 0.1f * k;
+		}
+	}
+	if (s->p->include_sky) {
+		float rnd[3], raw[3], skyDir[3];
+		unit_ball_point(s, rnd);
+		for (int a = 0; a < 3; a++) raw[a] = nrm[a] + rnd[a];
+		normalize3(raw, skyDir);
+		cast(s, start, skyDir, 0, &h);
+		if (!h.hit) for (int a = 0; a < 3; a++) out[a] += 1.5f;
+	}
+}
+
+static void bounce_ray(pt_state* s, const cbqo_hit* h, float o[3], float d[3])
+{
+	float rnd[3], raw[3];
+	unit_ball_point(s, rnd);
+	for (int a = 0; a < 3; a++) raw[a] = h->normal[a] + rnd[a];
+	normalize3(raw, d);
+	for (int a = 0; a < 3; a++) o[a] = h->position[a] + (h->normal[a] * 0.01f);
+}
+
+static void trace_recursive(pt_state* s, const float o[3], const float d[3], uint32_t depth, float out[3])
+{
+	/* pathtracing_demo.cpp:120-148 */
+	if (depth > s->p->bounces) { out[0] = out[1] = out[2] = 0.0f; return; }
+	out[0] = 0.8f; out[1] = 0.8f; out[2] = 1.0f;
+	cbqo_hit h;
+	cast(s, o, d, 1, &h);
+	if (h.hit) {
+		float direct[3], indirect[3], no[3], nd[3];
+		surface_colour(s, &h, out);
+		gather_lighting(s, h.position, h.normal, direct);
+		bounce_ray(s, &h, no, nd);
+		trace_recursive(s, no, nd, depth + 1, indirect);
+		for (int a = 0; a < 3; a++) out[a] *= (direct[a] + indirect[a]);
+	}
+}
+
+static void trace_one_bounce(pt_state* s, const float o[3], const float d[3], float out[3])
+{
+	/* pathtracing_demo.cpp:150-190 -- ignores `bounces`, applies gamma per sample. */
+	out[0] = 0.8f; out[1] = 0.8f; out[2] = 1.0f;
+	cbqo_hit h0;
+	cast(s, o, d, 1, &h0);
+	if (h0.hit) {
+		float c0[3], direct0[3], no[3], nd[3], indirect[3] = { 0.0f, 0.0f, 0.0f };
+		surface_colour(s, &h0, c0);
+		gather_lighting(s, h0.position, h0.normal, direct0);
+		bounce_ray(s, &h0, no, nd);
+		cbqo_hit h1;
+		cast(s, no, nd, 1, &h1);
+		if (h1.hit) {
+			float c1[3], direct1[3];
+			surface_colour(s, &h1, c1);
+			gather_lighting(s, h1.position, h1.normal, direct1);
+			for (int a = 0; a < 3; a++) indirect[a] = c1[a] * direct1[a];
+		}
+		const float gamma = (float)(1.0 / 2.2);
+		for (int a = 0; a < 3; a++) {
+			out[a] = c0[a] * (direct0[a] + indirect[a]);
+			out[a] = powf(out[a], gamma);
+		}
+	}
+}
+
+uint32_t cbqo_pixel_seed(const cbqo_ray* r, uint32_t sampleIndex)
+{
+	/* The per-fragment seeding rule of the GLSL tracer (pathtracing.frag:770-780,786,816):
+	 * XOR of fmix32 over the six float bit patterns, XOR fmix32(frameId). */
+	uint32_t bits[6], h = 0;
+	memcpy(bits, r, sizeof(bits));
+	for (int i = 0; i < 6; i++) h ^= cbqo_fmix32(bits[i]);
+	return h ^ cbqo_fmix32(sampleIndex);
+}
+
+typedef struct {
+	pt_state st; const cbqo_camera* cam; float* accum;
+	uint32_t* cursor; pthread_mutex_t* lock;
+} render_job;
+
+static void* render_worker(void* arg)
+{
+	render_job* j = (render_job*)arg;
+	const cbqo_pt_params* p = j->st.p;
+	for (;;) {
+		pthread_mutex_lock(j->lock);
+		uint32_t y = *j->cursor;
+		*j->cursor = y + 1;
+		pthread_mutex_unlock(j->lock);
+		if (y >= p->y1) break;
+		for (uint32_t x = p->x0; x < p->x1; x++) {
+			cbqo_ray r;
+			cbqo_camera_ray(j->cam, (int)x, (int)y, (int)p->width, (int)p->height, &r);
+			float* px = &j->accum[3 * ((size_t)y * p->width + x)];
+			for (uint32_t s = 0; s < p->spp; s++) {
+				float c[3];
+				j->st.rng = cbqo_pixel_seed(&r, p->frame_id + s);
+				if (p->variant == 0) trace_one_bounce(&j->st, r.o, r.d, c);
+				else trace_recursive(&j->st, r.o, r.d, 0, c);
+				for (int a = 0; a < 3; a++) px[a] += c[a];
+			}
+		}
+	}
+	return NULL;
+}
+
+double cbqo_render(const uint32_t* nodes, const cbqo_subdag sd[8], const float* colours,
+	const cbqo_camera* cam, const cbqo_pt_params* p, float* accum, int threads, uint64_t* raysOut)
+{
+	if (threads < 1) threads = 1;
+	if (threads > 256) threads = 256;
+	pthread_mutex_t lock = PTHREAD_MUTEX_INITIALIZER;
+	uint32_t cursor = p->y0;
+	render_job* jobs = (render_job*)calloc((size_t)threads, sizeof(render_job));
+	pthread_t* tids = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+	for (int t = 0; t < threads; t++) {
+		jobs[t].st.nodes = nodes; jobs[t].st.sd = sd; jobs[t].st.colours = colours; jobs[t].st.p = p;
+		jobs[t].st.rng = 17; jobs[t].st.rays = 0;
+		jobs[t].cam = cam; jobs[t].accum = accum; jobs[t].cursor = &cursor; jobs[t].lock = &lock;
+	}
+	double t0 = now_s();
+	if (threads == 1) render_worker(&jobs[0]);
+	else {
+		for (int t = 0; t < threads; t++) pthread_create(&tids[t], NULL, render_worker, &jobs[t]);
+		for (int t = 0; t < threads; t++) pthread_join(tids[t], NULL);
+	}
+	double t1 = now_s();
+	uint64_t rays = 0;
+	for (int t = 0; t < threads; t++) rays += jobs[t].st.rays;
+	if (raysOut) *raysOut = rays;
+	free(jobs); free(tids);
+	return t1 - t0;
+}
