@@ -1,0 +1,341 @@
+"""ctypes binding of include/cubiquity_b200.h -- the host-side mirror used by tests and bench.py.
+
+Names follow the reference (reference src/library/raytracing.h:69-81): `Context.intersect_volume`
+is a batch of `Cubiquity::intersectVolume`, `find_subdags` is `findSubDAGs`, `Context.render` is
+`PathtracingDemo::raytrace`. Everything here goes through the C ABI; there is no Python or CPU
+implementation of the ray cast in this package and the import FAILS if the CUDA library is absent.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+RAY_DTYPE = np.dtype([("o", "<f4", 3), ("d", "<f4", 3)])
+HIT_DTYPE = np.dtype([("hit", "<u4"), ("distance", "<f4"), ("material", "<u4"),
+                      ("position", "<f4", 3), ("normal", "<f4", 3), ("status", "<u4")])
+SUBDAG_DTYPE = np.dtype([("lower", "<i4", 3), ("height", "<i4"), ("pad0", "<u4"),
+                         ("node", "<u4"), ("pad1", "<u4"), ("pad2", "<u4")])
+assert RAY_DTYPE.itemsize == 24 and HIT_DTYPE.itemsize == 40 and SUBDAG_DTYPE.itemsize == 32
+
+TRACE_SURFACE = 1
+MAX_FOOTPRINT_DISABLED = -1.0
+VARIANT_ONE_BOUNCE = 0
+VARIANT_RECURSIVE = 1
+
+OK, ERROR_INVALID_ARGUMENT, ERROR_NO_DEVICE, ERROR_CUDA, ERROR_OUT_OF_MEMORY, ERROR_NO_VOLUME, ERROR_CORRUPT_VOLUME = range(7)
+
+
+class CubiquityError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("cubiquity_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+class Camera(C.Structure):
+    _fields_ = [("position", C.c_double * 3), ("forward", C.c_double * 3), ("up", C.c_double * 3),
+                ("right", C.c_double * 3), ("scale", C.c_float), ("pad", C.c_float)]
+
+
+class PtParams(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("spp", C.c_uint32), ("bounces", C.c_uint32),
+                ("variant", C.c_uint32), ("include_sun", C.c_uint32), ("include_sky", C.c_uint32),
+                ("add_noise", C.c_uint32), ("max_footprint", C.c_float), ("frame_id", C.c_uint32),
+                ("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32), ("y1", C.c_uint32), ("pad", C.c_uint32)]
+
+
+def pt_params(width, height, spp=1, bounces=1, variant=VARIANT_ONE_BOUNCE, include_sun=True, include_sky=True,
+              add_noise=True, max_footprint=0.0035, frame_id=0, rect=None):
+    """Defaults are PathtracingDemo's (reference pathtracing_demo.h:80-84)."""
+    x0, y0, x1, y1 = rect if rect is not None else (0, 0, width, height)
+    return PtParams(width, height, spp, bounces, variant, int(include_sun), int(include_sky), int(add_noise),
+                    max_footprint, frame_id, x0, y0, x1, y1, 0)
+
+
+EXPORTS = [
+    "cbq_create", "cbq_destroy", "cbq_last_error", "cbq_device_count", "cbq_synchronize",
+    "cbq_upload", "cbq_update", "cbq_set_colours", "cbq_get_subdags", "cbq_find_subdags",
+    "cbq_download_nodes", "cbq_node_count",
+    "cbq_trace", "cbq_trace_device", "cbq_camera_from_pose", "cbq_primary_rays_device", "cbq_raycast_frame_device",
+    "cbq_render", "cbq_render_device",
+    "cbq_host_alloc", "cbq_host_free", "cbq_set_option", "cbq_get_option", "cbq_get_counter", "cbq_reset_counters",
+    "cbq_scene_build", "cbq_scene_nodes", "cbq_scene_root", "cbq_scene_bounds", "cbq_scene_colours",
+    "cbq_scene_voxels", "cbq_scene_free",
+]
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB
+
+
+def load_library():
+    """Loads the CUDA library, building it in-tree if needed. Raises if it cannot -- never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_build.LIB):
+        _build.build_library()
+    L = C.CDLL(_build.LIB)
+    vp, u64, u32, i32, f32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_float
+    L.cbq_last_error.restype = C.c_char_p
+    L.cbq_create.argtypes = [i32, C.POINTER(vp)]
+    L.cbq_destroy.argtypes = [vp]
+    L.cbq_destroy.restype = None
+    L.cbq_synchronize.argtypes = [vp]
+    L.cbq_upload.argtypes = [vp, vp, u64, u32, vp]
+    L.cbq_update.argtypes = [vp, vp, u64, u64, u32]
+    L.cbq_set_colours.argtypes = [vp, vp]
+    L.cbq_get_subdags.argtypes = [vp, vp]
+    L.cbq_find_subdags.argtypes = [vp, u64, u32, vp]
+    L.cbq_download_nodes.argtypes = [vp, u64, u64, vp]
+    L.cbq_node_count.argtypes = [vp, C.POINTER(u64)]
+    L.cbq_trace.argtypes = [vp, vp, u64, u32, f32, vp]
+    L.cbq_trace_device.argtypes = [vp, vp, u64, u32, f32, vp, vp]
+    L.cbq_camera_from_pose.argtypes = [C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double, C.POINTER(Camera)]
+    L.cbq_primary_rays_device.argtypes = [vp, C.POINTER(Camera), u32, u32, vp, vp]
+    L.cbq_raycast_frame_device.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, f32, vp, vp]
+    L.cbq_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(PtParams), vp]
+    L.cbq_render_device.argtypes = [vp, C.POINTER(Camera), C.POINTER(PtParams), vp, vp]
+    L.cbq_host_alloc.argtypes = [C.POINTER(vp), u64]
+    L.cbq_host_free.argtypes = [vp]
+    L.cbq_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.cbq_get_option.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
+    L.cbq_get_counter.argtypes = [vp, C.c_char_p, C.POINTER(u64)]
+    L.cbq_reset_counters.argtypes = [vp]
+    L.cbq_scene_build.argtypes = [C.c_char_p, u32, u64, C.POINTER(vp)]
+    L.cbq_scene_nodes.restype = C.POINTER(u32)
+    L.cbq_scene_nodes.argtypes = [vp, C.POINTER(u64)]
+    L.cbq_scene_root.restype = u32
+    L.cbq_scene_root.argtypes = [vp]
+    L.cbq_scene_bounds.restype = None
+    L.cbq_scene_bounds.argtypes = [vp, vp, vp]
+    L.cbq_scene_colours.restype = None
+    L.cbq_scene_colours.argtypes = [vp, vp]
+    L.cbq_scene_voxels.restype = None
+    L.cbq_scene_voxels.argtypes = [vp, vp, u64, vp]
+    L.cbq_scene_free.restype = None
+    L.cbq_scene_free.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != OK:
+        raise CubiquityError(rc, load_library().cbq_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def device_count():
+    return int(load_library().cbq_device_count())
+
+
+def find_subdags(nodes, root):
+    """findSubDAGs (reference raytracing.cpp:89-97) on the host; needs no device."""
+    nodes = np.ascontiguousarray(nodes, dtype=np.uint32).reshape(-1, 8)
+    out = np.zeros(8, dtype=SUBDAG_DTYPE)
+    _check(load_library().cbq_find_subdags(_ptr(nodes), len(nodes), int(root), _ptr(out)))
+    return out
+
+
+def camera_from_pose(position, pitch, yaw, fov_degrees=60.0):
+    """Camera::forward/right/up + fov scale (reference camera.cpp:24,40-66). Host only."""
+    cam = Camera()
+    pos = (C.c_double * 3)(*[float(v) for v in position])
+    _check(load_library().cbq_camera_from_pose(pos, float(pitch), float(yaw), float(fov_degrees), C.byref(cam)))
+    return cam
+
+
+def default_camera(lower, upper):
+    """The viewer's start pose for a solid object (reference viewer.cpp:71-79): centred in x, back and
+    up by half the bounding-box diagonal, looking down 45 degrees."""
+    lower = np.asarray(lower, dtype=np.float64)
+    upper = np.asarray(upper, dtype=np.float64)
+    centre = (lower + upper) * 0.5
+    half_diag = float(np.sqrt(((upper - lower) ** 2).sum())) * 0.5
+    pi_f = float(np.float32(3.14159265358979))
+    return camera_from_pose([centre[0], centre[1] - half_diag, centre[2] + half_diag], -(pi_f / 4.0), 0.0)
+
+
+class PinnedArray:
+    """A numpy view over cudaHostAlloc memory (cbq_host_alloc)."""
+
+    def __init__(self, count, dtype):
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(count) * self.dtype.itemsize
+        p = C.c_void_p()
+        _check(load_library().cbq_host_alloc(C.byref(p), self.nbytes))
+        self.ptr = p
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(count))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            load_library().cbq_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Scene:
+    """A procedural volume (csrc/scene_builder.cpp). Host only."""
+
+    def __init__(self, kind, size_log2, seed=1):
+        L = load_library()
+        self.kind, self.size_log2, self.seed = kind, int(size_log2), int(seed)
+        h = C.c_void_p()
+        _check(L.cbq_scene_build(kind.encode(), int(size_log2), int(seed), C.byref(h)))
+        self._h = h
+        n = C.c_uint64()
+        p = L.cbq_scene_nodes(h, C.byref(n))
+        self.nodes = np.ctypeslib.as_array(p, shape=(int(n.value), 8))   # view into the scene's memory
+        self.root = int(L.cbq_scene_root(h))
+        lo = np.zeros(3, dtype=np.int32)
+        hi = np.zeros(3, dtype=np.int32)
+        L.cbq_scene_bounds(h, _ptr(lo), _ptr(hi))
+        self.lower, self.upper = lo, hi
+        self.colours = np.zeros((256, 3), dtype=np.float32)
+        L.cbq_scene_colours(h, _ptr(self.colours))
+
+    def voxels(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.int32).reshape(-1, 3)
+        out = np.zeros(len(xyz), dtype=np.uint8)
+        load_library().cbq_scene_voxels(self._h, _ptr(xyz), len(xyz), _ptr(out))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.nodes = None
+            load_library().cbq_scene_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU. Mirrors the reference call sites: upload the Volume's node array, then intersect_volume."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        _check(self.L.cbq_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.cbq_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- volume ------------------------------------------------------------------------------
+    def upload(self, nodes, root, colours=None):
+        nodes = np.ascontiguousarray(nodes, dtype=np.uint32).reshape(-1, 8)
+        if colours is not None:
+            colours = np.ascontiguousarray(colours, dtype=np.float32).reshape(256, 3)
+        _check(self.L.cbq_upload(self._h, _ptr(nodes), len(nodes), int(root), _ptr(colours)))
+
+    def update(self, nodes, dirty_begin, root):
+        nodes = np.ascontiguousarray(nodes, dtype=np.uint32).reshape(-1, 8)
+        _check(self.L.cbq_update(self._h, _ptr(nodes), int(dirty_begin), len(nodes), int(root)))
+
+    def subdags(self):
+        out = np.zeros(8, dtype=SUBDAG_DTYPE)
+        _check(self.L.cbq_get_subdags(self._h, _ptr(out)))
+        return out
+
+    def node_count(self):
+        n = C.c_uint64()
+        _check(self.L.cbq_node_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    def download_nodes(self, begin=0, count=None):
+        if count is None:
+            count = self.node_count() - begin
+        out = np.zeros((count, 8), dtype=np.uint32)
+        _check(self.L.cbq_download_nodes(self._h, int(begin), int(count), _ptr(out)))
+        return out
+
+    # -- ray cast ----------------------------------------------------------------------------
+    def intersect_volume(self, rays, compute_surface_properties=True, max_footprint=MAX_FOOTPRINT_DISABLED, out=None):
+        """Batch of Cubiquity::intersectVolume (reference raytracing.h:72-75). Host arrays in and out."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = out if out is not None else np.zeros(len(rays), dtype=HIT_DTYPE)
+        flags = TRACE_SURFACE if compute_surface_properties else 0
+        _check(self.L.cbq_trace(self._h, _ptr(rays), len(rays), flags, float(max_footprint), _ptr(hits)))
+        return hits
+
+    def trace_device(self, d_rays, n, d_hits, compute_surface_properties=True,
+                     max_footprint=MAX_FOOTPRINT_DISABLED, stream=None):
+        flags = TRACE_SURFACE if compute_surface_properties else 0
+        _check(self.L.cbq_trace_device(self._h, C.c_void_p(int(d_rays)), int(n), flags, float(max_footprint),
+                                       C.c_void_p(int(d_hits)), C.c_void_p(int(stream)) if stream else None))
+
+    def primary_rays_device(self, cam, width, height, d_rays, stream=None):
+        _check(self.L.cbq_primary_rays_device(self._h, C.byref(cam), int(width), int(height), C.c_void_p(int(d_rays)),
+                                              C.c_void_p(int(stream)) if stream else None))
+
+    def raycast_frame_device(self, cam, width, height, d_hits, compute_surface_properties=True,
+                             max_footprint=MAX_FOOTPRINT_DISABLED, stream=None):
+        flags = TRACE_SURFACE if compute_surface_properties else 0
+        _check(self.L.cbq_raycast_frame_device(self._h, C.byref(cam), int(width), int(height), flags,
+                                               float(max_footprint), C.c_void_p(int(d_hits)),
+                                               C.c_void_p(int(stream)) if stream else None))
+
+    # -- path tracer -------------------------------------------------------------------------
+    def render(self, cam, params, accum=None):
+        """PathtracingDemo::raytrace (reference pathtracing_demo.cpp:214-229): adds params.spp samples."""
+        if accum is None:
+            accum = np.zeros((params.height, params.width, 3), dtype=np.float32)
+        assert accum.dtype == np.float32 and accum.flags["C_CONTIGUOUS"]
+        _check(self.L.cbq_render(self._h, C.byref(cam), C.byref(params), _ptr(accum)))
+        return accum
+
+    def render_device(self, cam, params, d_accum, stream=None):
+        _check(self.L.cbq_render_device(self._h, C.byref(cam), C.byref(params), C.c_void_p(int(d_accum)),
+                                        C.c_void_p(int(stream)) if stream else None))
+
+    # -- misc --------------------------------------------------------------------------------
+    def synchronize(self):
+        _check(self.L.cbq_synchronize(self._h))
+
+    def set_option(self, key, value):
+        _check(self.L.cbq_set_option(self._h, key.encode(), int(value)))
+
+    def get_option(self, key):
+        v = C.c_int64()
+        _check(self.L.cbq_get_option(self._h, key.encode(), C.byref(v)))
+        return int(v.value)
+
+    def counter(self, key):
+        v = C.c_uint64()
+        _check(self.L.cbq_get_counter(self._h, key.encode(), C.byref(v)))
+        return int(v.value)
+
+    def reset_counters(self):
+        _check(self.L.cbq_reset_counters(self._h))

@@ -1,0 +1,621 @@
+// extern "C" layer of cubiquity_b200 (include/cubiquity_b200.h): context, DAG -> GPU serialisation
+// with delta re-upload, batched ray cast, frame ray cast, path-traced render.
+//
+// Reference interfaces replaced (all under /root/reference):
+//   upload      src/application/commands/view/gpu_pathtracing_viewer.cpp:43-67 (glBufferData of
+//               NodeStore::rawBytesPtr(), the 8 SubDAGs and the colour table)
+//   update      Viewer::onMouseButtonDown -> onVolumeModified (viewer.cpp:152-172,
+//               pathtracing_demo.cpp:335-341); COW rules storage.cpp:152-167,298-303
+//   trace       Cubiquity::intersectVolume, src/library/raytracing.cpp:397-478
+//   render      PathtracingDemo::raytrace, src/application/commands/view/pathtracing_demo.cpp:214-229
+#include "cbq_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(int code, const char* fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_lastError = buf;
+	return code;
+}
+
+#define CBQ_CUDA(expr)                                                                            \
+	do {                                                                                          \
+		cudaError_t e_ = (expr);                                                                  \
+		if (e_ != cudaSuccess) {                                                                  \
+			return fail(e_ == cudaErrorMemoryAllocation ? CBQ_ERROR_OUT_OF_MEMORY : CBQ_ERROR_CUDA, \
+				"%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);      \
+		}                                                                                         \
+	} while (0)
+
+constexpr int kQueueSlots = 4096;      // ring of zeroed ticket counters, one per launch
+constexpr uint64_t kPipelineChunk = 1u << 18;  // rays per host<->device pipeline stage
+
+// findSubDAG (reference src/library/raytracing.cpp:43-87), host side, bounds-checked because the
+// node array comes from outside.
+bool findOneSubDag(const uint32_t* nodes, uint64_t nodeCount, uint32_t root, uint32_t octant, cbq::SubDag& out)
+{
+	int height = 32;
+	uint32_t lower[3] = { 0x80000000u, 0x80000000u, 0x80000000u };
+	uint32_t only = octant;
+	if (root >= nodeCount) return false;
+	uint32_t next = nodes[(uint64_t)root * 8 + only];
+	uint32_t node = 0;
+	uint32_t occupied = 1;
+	while (occupied == 1) {
+		height--;
+		if (height < 0) return false;   // a chain of single children deeper than the tree: corrupt
+		node = next;
+		if (node >= nodeCount) return false;
+		for (int a = 0; a < 3; a++) lower[a] ^= ((only >> a) & 1u) << height;
+		occupied = 0;
+		for (uint32_t c = 0; c < 8; c++) {
+			const uint32_t child = nodes[(uint64_t)node * 8 + c];
+			if (child > 0) { next = child; occupied++; only = c; }
+		}
+	}
+	std::memset(&out, 0, sizeof(out));
+	for (int a = 0; a < 3; a++) out.lower[a] = (int32_t)lower[a];
+	out.height = height;
+	out.node = node;
+	return true;
+}
+
+bool findSubDags(const uint32_t* nodes, uint64_t nodeCount, uint32_t root, cbq::SubDag out[8])
+{
+	for (uint32_t c = 0; c < 8; c++) if (!findOneSubDag(nodes, nodeCount, root, c, out[c])) return false;
+	return true;
+}
+
+} // namespace
+
+struct cbq_context {
+	int device = 0;
+	cudaDeviceProp prop{};
+	cudaStream_t stream = nullptr;       // compute + default
+	cudaStream_t copyIn = nullptr, copyOut = nullptr;
+	cudaEvent_t evIn[2]{}, evKernel[2]{}, evOut[2]{};
+
+	// The volume: one linear device buffer.
+	uint8_t* volume = nullptr;
+	size_t volumeBytes = 0;
+	uint64_t nodeCount = 0, nodeCapacity = 0;
+	uint32_t root = 0;
+	uint64_t generation = 0;
+	cbq::SubDag subdags[8]{};
+	int maxSubDagHeight = 0;
+
+	// Launch bookkeeping.
+	unsigned long long* queues = nullptr; // kQueueSlots counters + 1 abandoned counter at the end
+	int queueCursor = 0;
+	cbq::LaunchConfig cfg{};
+	int l2Persist = 1;
+	cudaStream_t windowStream = nullptr;  // stream the access-policy window was last applied to
+	uint64_t windowGeneration = ~0ull;
+
+	// cbq_trace staging (device side), double buffered.
+	cbq::Ray* stageRays[2]{};
+	cbq::Hit* stageHits[2]{};
+
+	// cbq_render staging
+	float* stageAccum = nullptr;
+	size_t stageAccumBytes = 0;
+
+	// Counters
+	uint64_t launches = 0, raysTraced = 0, bytesH2D = 0, bytesD2H = 0;
+
+	const uint32_t* nodesPtr() const { return reinterpret_cast<const uint32_t*>(volume + cbq::kNodeOffset); }
+	const cbq::SubDag* subdagsPtr() const { return reinterpret_cast<const cbq::SubDag*>(volume + cbq::kSubDagOffset); }
+	const float4* coloursPtr() const { return reinterpret_cast<const float4*>(volume + cbq::kColourOffset); }
+	unsigned long long* abandonedPtr() const { return queues + kQueueSlots; }
+};
+
+namespace {
+
+int bind(cbq_context* ctx)
+{
+	if (!ctx) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null context");
+	CBQ_CUDA(cudaSetDevice(ctx->device));
+	return CBQ_OK;
+}
+
+// Hand out a zeroed ticket counter. The ring is re-zeroed (stream ordered) each time it wraps.
+int nextQueue(cbq_context* ctx, cudaStream_t stream, unsigned long long** out)
+{
+	if (ctx->queueCursor == kQueueSlots) {
+		// All users of earlier slots were enqueued on streams we synchronise with here.
+		CBQ_CUDA(cudaDeviceSynchronize());
+		CBQ_CUDA(cudaMemsetAsync(ctx->queues, 0, sizeof(unsigned long long) * kQueueSlots, stream));
+		ctx->queueCursor = 0;
+	}
+	*out = ctx->queues + ctx->queueCursor++;
+	return CBQ_OK;
+}
+
+int writeHeaderAndSubdags(cbq_context* ctx)
+{
+	cbq::VolumeHeader h;
+	std::memset(&h, 0, sizeof(h));
+	h.magic = 0x31514243u; h.version = CBQ_VERSION;
+	h.nodeCount = ctx->nodeCount; h.nodeCapacity = ctx->nodeCapacity;
+	h.rootIndex = ctx->root; h.maxSubDagHeight = (uint32_t)ctx->maxSubDagHeight; h.generation = ctx->generation;
+	CBQ_CUDA(cudaMemcpyAsync(ctx->volume + cbq::kHeaderOffset, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+	CBQ_CUDA(cudaMemcpyAsync(ctx->volume + cbq::kSubDagOffset, ctx->subdags, sizeof(ctx->subdags), cudaMemcpyHostToDevice, ctx->stream));
+	CBQ_CUDA(cudaStreamSynchronize(ctx->stream)); // h is on our stack
+	ctx->bytesH2D += sizeof(h) + sizeof(ctx->subdags);
+	return CBQ_OK;
+}
+
+int refreshSubdags(cbq_context* ctx, const uint32_t* nodes, uint64_t nodeCount, uint32_t root)
+{
+	cbq::SubDag sd[8];
+	if (!findSubDags(nodes, nodeCount, root, sd))
+		return fail(CBQ_ERROR_CORRUPT_VOLUME, "node array is not a valid DAG below root %u (child index out of range or runaway chain)", root);
+	int maxH = 0;
+	for (int i = 0; i < 8; i++) if (sd[i].node > 0) maxH = std::max(maxH, sd[i].height);
+	std::memcpy(ctx->subdags, sd, sizeof(sd));
+	ctx->maxSubDagHeight = maxH;
+	ctx->cfg.stackLevels = maxH + 1;
+	return CBQ_OK;
+}
+
+// Pin the node array in L2 (persisting access-policy window) for kernels on `stream`.
+void applyL2Window(cbq_context* ctx, cudaStream_t stream)
+{
+	if (ctx->windowStream == stream && ctx->windowGeneration == ctx->generation) return;
+	cudaStreamAttrValue attr;
+	std::memset(&attr, 0, sizeof(attr));
+	if (ctx->l2Persist && ctx->volume && ctx->prop.persistingL2CacheMaxSize > 0) {
+		const size_t nodeBytes = (size_t)ctx->nodeCount * 32;
+		const size_t window = std::min(nodeBytes + cbq::kNodeOffset, (size_t)ctx->prop.accessPolicyMaxWindowSize);
+		const size_t carve = std::min((size_t)ctx->prop.persistingL2CacheMaxSize, window);
+		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+		attr.accessPolicyWindow.base_ptr = ctx->volume;
+		attr.accessPolicyWindow.num_bytes = window;
+		attr.accessPolicyWindow.hitRatio = window ? (float)std::min(1.0, (double)carve / (double)window) : 0.0f;
+		attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+	} else {
+		attr.accessPolicyWindow.num_bytes = 0;
+	}
+	if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+	ctx->windowStream = stream;
+	ctx->windowGeneration = ctx->generation;
+}
+
+int ensureStaging(cbq_context* ctx)
+{
+	for (int i = 0; i < 2; i++) {
+		if (!ctx->stageRays[i]) CBQ_CUDA(cudaMalloc(&ctx->stageRays[i], kPipelineChunk * sizeof(cbq::Ray)));
+		if (!ctx->stageHits[i]) CBQ_CUDA(cudaMalloc(&ctx->stageHits[i], kPipelineChunk * sizeof(cbq::Hit)));
+	}
+	return CBQ_OK;
+}
+
+int traceDevice(cbq_context* ctx, const cbq::Ray* dRays, uint64_t n, uint32_t flags, float maxFootprint,
+	cbq::Hit* dHits, cudaStream_t stream, const cbq_camera* cam, uint32_t width, uint32_t height)
+{
+	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "no volume uploaded");
+	if (n == 0) return CBQ_OK;
+	cbq::TraceArgs a;
+	std::memset(&a, 0, sizeof(a));
+	a.nodes = ctx->nodesPtr(); a.subdags = ctx->subdagsPtr();
+	a.rays = dRays; a.hits = dHits; a.count = n; a.maxFootprint = maxFootprint;
+	a.abandoned = ctx->abandonedPtr();
+	if (cam) { a.camera = *cam; a.width = width; a.height = height; }
+	int rc = nextQueue(ctx, stream, &a.queue);
+	if (rc != CBQ_OK) return rc;
+	applyL2Window(ctx, stream);
+	CBQ_CUDA(cbq::launchTrace(a, (flags & CBQ_TRACE_SURFACE) != 0, ctx->cfg, stream));
+	ctx->launches++;
+	ctx->raysTraced += n;
+	return CBQ_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* cbq_last_error(void) { return g_lastError.c_str(); }
+
+int cbq_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+int cbq_create(int device, cbq_context** out)
+{
+	if (!out) return fail(CBQ_ERROR_INVALID_ARGUMENT, "out is null");
+	*out = nullptr;
+	const int n = cbq_device_count();
+	if (n <= 0) return fail(CBQ_ERROR_NO_DEVICE, "no CUDA device is visible; cubiquity_b200 has no CPU fallback");
+	if (device < 0 || device >= n) return fail(CBQ_ERROR_INVALID_ARGUMENT, "device %d out of range (0..%d)", device, n - 1);
+	CBQ_CUDA(cudaSetDevice(device));
+	cbq_context* ctx = new cbq_context();
+	ctx->device = device;
+	CBQ_CUDA(cudaGetDeviceProperties(&ctx->prop, device));
+	if (ctx->prop.major < 10)
+		{ const int maj = ctx->prop.major, mnr = ctx->prop.minor; delete ctx; return fail(CBQ_ERROR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, maj, mnr); }
+	CBQ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	CBQ_CUDA(cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking));
+	CBQ_CUDA(cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; i++) {
+		CBQ_CUDA(cudaEventCreateWithFlags(&ctx->evIn[i], cudaEventDisableTiming));
+		CBQ_CUDA(cudaEventCreateWithFlags(&ctx->evKernel[i], cudaEventDisableTiming));
+		CBQ_CUDA(cudaEventCreateWithFlags(&ctx->evOut[i], cudaEventDisableTiming));
+	}
+	CBQ_CUDA(cudaMalloc(&ctx->queues, sizeof(unsigned long long) * (kQueueSlots + 1)));
+	CBQ_CUDA(cudaMemset(ctx->queues, 0, sizeof(unsigned long long) * (kQueueSlots + 1)));
+	ctx->cfg.blockThreads = 256;
+	ctx->cfg.blocksPerSm = 4;
+	ctx->cfg.smCount = ctx->prop.multiProcessorCount;
+	ctx->cfg.refillThreshold = 8;
+	ctx->cfg.kernel = 0;
+	ctx->cfg.stackLevels = 33;
+	*out = ctx;
+	return CBQ_OK;
+}
+
+void cbq_destroy(cbq_context* ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaDeviceSynchronize();
+	for (int i = 0; i < 2; i++) {
+		cudaFree(ctx->stageRays[i]); cudaFree(ctx->stageHits[i]);
+		if (ctx->evIn[i]) cudaEventDestroy(ctx->evIn[i]);
+		if (ctx->evKernel[i]) cudaEventDestroy(ctx->evKernel[i]);
+		if (ctx->evOut[i]) cudaEventDestroy(ctx->evOut[i]);
+	}
+	cudaFree(ctx->stageAccum);
+	cudaFree(ctx->queues);
+	cudaFree(ctx->volume);
+	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
+	if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
+	delete ctx;
+}
+
+int cbq_synchronize(cbq_context* ctx)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	return CBQ_OK;
+}
+
+int cbq_find_subdags(const uint32_t* nodes, uint64_t node_count, uint32_t root_index, cbq_subdag out[8])
+{
+	if (!nodes || !out || node_count < cbq::kMaterialCount) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad node array");
+	static_assert(sizeof(cbq_subdag) == sizeof(cbq::SubDag), "subdag layout");
+	if (!findSubDags(nodes, node_count, root_index, reinterpret_cast<cbq::SubDag*>(out)))
+		return fail(CBQ_ERROR_CORRUPT_VOLUME, "node array is not a valid DAG below root %u", root_index);
+	return CBQ_OK;
+}
+
+int cbq_upload(cbq_context* ctx, const uint32_t* nodes, uint64_t node_count, uint32_t root_index, const float* colours_rgb)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!nodes || node_count < cbq::kMaterialCount) return fail(CBQ_ERROR_INVALID_ARGUMENT, "node array must include the 256 material nodes");
+	if (node_count > 0xffffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "node indices are 32-bit");
+	rc = refreshSubdags(ctx, nodes, node_count, root_index); if (rc) return rc;
+
+	// Head-room for copy-on-write growth so that edits rarely force a reallocation.
+	const uint64_t capacity = node_count + std::max<uint64_t>(node_count / 4, 1u << 16);
+	const size_t bytes = cbq::kNodeOffset + (size_t)capacity * 32;
+	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (bytes > ctx->volumeBytes) {
+		if (ctx->volume) { CBQ_CUDA(cudaDeviceSynchronize()); CBQ_CUDA(cudaFree(ctx->volume)); ctx->volume = nullptr; ctx->volumeBytes = 0; }
+		CBQ_CUDA(cudaMalloc(&ctx->volume, bytes));
+		ctx->volumeBytes = bytes;
+	}
+	ctx->nodeCapacity = (ctx->volumeBytes - cbq::kNodeOffset) / 32;
+	ctx->nodeCount = node_count;
+	ctx->root = root_index;
+	ctx->generation++;
+	CBQ_CUDA(cudaMemcpyAsync(ctx->volume + cbq::kNodeOffset, nodes, (size_t)node_count * 32, cudaMemcpyHostToDevice, ctx->stream));
+	ctx->bytesH2D += node_count * 32;
+	rc = cbq_set_colours(ctx, colours_rgb); if (rc) return rc;
+	return writeHeaderAndSubdags(ctx);
+}
+
+int cbq_update(cbq_context* ctx, const uint32_t* nodes, uint64_t dirty_begin, uint64_t node_count, uint32_t root_index)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "cbq_update before cbq_upload");
+	if (!nodes || node_count < cbq::kMaterialCount || dirty_begin > node_count) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad dirty range");
+	if (dirty_begin > ctx->nodeCount) return fail(CBQ_ERROR_INVALID_ARGUMENT, "dirty_begin %llu is past the %llu nodes on the device", (unsigned long long)dirty_begin, (unsigned long long)ctx->nodeCount);
+	if (node_count > 0xffffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "node indices are 32-bit");
+	rc = refreshSubdags(ctx, nodes, node_count, root_index); if (rc) return rc;
+	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (node_count > ctx->nodeCapacity) {
+		// Out of head-room: grow, keeping the clean prefix that is already on the device.
+		const uint64_t capacity = node_count + std::max<uint64_t>(node_count / 4, 1u << 16);
+		const size_t bytes = cbq::kNodeOffset + (size_t)capacity * 32;
+		uint8_t* bigger = nullptr;
+		CBQ_CUDA(cudaDeviceSynchronize());
+		CBQ_CUDA(cudaMalloc(&bigger, bytes));
+		CBQ_CUDA(cudaMemcpy(bigger, ctx->volume, cbq::kNodeOffset + (size_t)dirty_begin * 32, cudaMemcpyDeviceToDevice));
+		CBQ_CUDA(cudaFree(ctx->volume));
+		ctx->volume = bigger; ctx->volumeBytes = bytes; ctx->nodeCapacity = capacity;
+	}
+	const uint64_t tail = node_count - dirty_begin;
+	if (tail) {
+		CBQ_CUDA(cudaMemcpyAsync(ctx->volume + cbq::kNodeOffset + (size_t)dirty_begin * 32, nodes + dirty_begin * 8, (size_t)tail * 32,
+			cudaMemcpyHostToDevice, ctx->stream));
+		ctx->bytesH2D += tail * 32;
+	}
+	ctx->nodeCount = node_count;
+	ctx->root = root_index;
+	ctx->generation++;
+	return writeHeaderAndSubdags(ctx);
+}
+
+int cbq_set_colours(cbq_context* ctx, const float* colours_rgb)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "no volume uploaded");
+	std::vector<float> c4(256 * 4);
+	for (int i = 0; i < 256; i++) {
+		// Purple default, like Viewer (reference viewer.cpp:50-55).
+		c4[4 * i + 0] = colours_rgb ? colours_rgb[3 * i + 0] : 1.0f;
+		c4[4 * i + 1] = colours_rgb ? colours_rgb[3 * i + 1] : 0.0f;
+		c4[4 * i + 2] = colours_rgb ? colours_rgb[3 * i + 2] : 1.0f;
+		c4[4 * i + 3] = 0.0f;
+	}
+	CBQ_CUDA(cudaMemcpyAsync(ctx->volume + cbq::kColourOffset, c4.data(), c4.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->bytesH2D += c4.size() * sizeof(float);
+	return CBQ_OK;
+}
+
+int cbq_get_subdags(cbq_context* ctx, cbq_subdag out[8])
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "no volume uploaded");
+	// Read back what the kernels see, not the host copy.
+	CBQ_CUDA(cudaMemcpyAsync(out, ctx->volume + cbq::kSubDagOffset, 256, cudaMemcpyDeviceToHost, ctx->stream));
+	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	return CBQ_OK;
+}
+
+int cbq_download_nodes(cbq_context* ctx, uint64_t begin, uint64_t count, uint32_t* out)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "no volume uploaded");
+	if (begin + count > ctx->nodeCount) return fail(CBQ_ERROR_INVALID_ARGUMENT, "range past end");
+	CBQ_CUDA(cudaMemcpyAsync(out, ctx->volume + cbq::kNodeOffset + (size_t)begin * 32, (size_t)count * 32, cudaMemcpyDeviceToHost, ctx->stream));
+	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	return CBQ_OK;
+}
+
+int cbq_node_count(cbq_context* ctx, uint64_t* out)
+{
+	if (!ctx || !out) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");
+	*out = ctx->nodeCount;
+	return CBQ_OK;
+}
+
+int cbq_trace_device(cbq_context* ctx, const cbq_ray* d_rays, uint64_t n, uint32_t flags, float max_footprint, cbq_hit* d_hits, void* stream)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (n && (!d_rays || !d_hits)) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null ray or hit buffer");
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	return traceDevice(ctx, reinterpret_cast<const cbq::Ray*>(d_rays), n, flags, max_footprint, reinterpret_cast<cbq::Hit*>(d_hits), s, nullptr, 0, 0);
+}
+
+int cbq_trace(cbq_context* ctx, const cbq_ray* rays, uint64_t n, uint32_t flags, float max_footprint, cbq_hit* hits)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "no volume uploaded");
+	if (n == 0) return CBQ_OK;
+	if (!rays || !hits) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null ray or hit buffer");
+	rc = ensureStaging(ctx); if (rc) return rc;
+	// Three-stage pipeline over chunks: H2D on copyIn, kernel on stream, D2H on copyOut, two
+	// staging buffers in flight. With pinned host memory the three overlap; with pageable memory
+	// the copies degrade to synchronous but the result is the same.
+	const uint64_t chunks = (n + kPipelineChunk - 1) / kPipelineChunk;
+	for (uint64_t c = 0; c < chunks; c++) {
+		const int b = (int)(c & 1);
+		const uint64_t begin = c * kPipelineChunk;
+		const uint64_t len = std::min(kPipelineChunk, n - begin);
+		if (c >= 2) CBQ_CUDA(cudaStreamWaitEvent(ctx->copyIn, ctx->evOut[b], 0));   // buffer b free again
+		CBQ_CUDA(cudaMemcpyAsync(ctx->stageRays[b], rays + begin, len * sizeof(cbq_ray), cudaMemcpyHostToDevice, ctx->copyIn));
+		CBQ_CUDA(cudaEventRecord(ctx->evIn[b], ctx->copyIn));
+		CBQ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evIn[b], 0));
+		if (c >= 2) CBQ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evOut[b], 0));
+		rc = traceDevice(ctx, ctx->stageRays[b], len, flags, max_footprint, ctx->stageHits[b], ctx->stream, nullptr, 0, 0);
+		if (rc) return rc;
+		CBQ_CUDA(cudaEventRecord(ctx->evKernel[b], ctx->stream));
+		CBQ_CUDA(cudaStreamWaitEvent(ctx->copyOut, ctx->evKernel[b], 0));
+		CBQ_CUDA(cudaMemcpyAsync(hits + begin, ctx->stageHits[b], len * sizeof(cbq_hit), cudaMemcpyDeviceToHost, ctx->copyOut));
+		CBQ_CUDA(cudaEventRecord(ctx->evOut[b], ctx->copyOut));
+	}
+	CBQ_CUDA(cudaStreamSynchronize(ctx->copyOut));
+	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->bytesH2D += n * sizeof(cbq_ray);
+	ctx->bytesD2H += n * sizeof(cbq_hit);
+	return CBQ_OK;
+}
+
+int cbq_camera_from_pose(const double position[3], double pitch, double yaw, double fov_degrees, cbq_camera* c)
+{
+	if (!position || !c) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");
+	// Camera::forward / right / up and the fov scale (reference camera.cpp:24,40-66), evaluated with
+	// the host libm exactly as the reference does; Pi is the FLOAT constant of camera.h:6.
+	const float Pi = 3.14159265358979f;
+	std::memset(c, 0, sizeof(*c));
+	for (int a = 0; a < 3; a++) c->position[a] = position[a];
+	c->forward[0] = std::cos(pitch) * std::sin(yaw);
+	c->forward[1] = std::cos(pitch) * std::cos(yaw);
+	c->forward[2] = std::sin(pitch);
+	c->right[0] = std::sin(yaw + (Pi / 2));
+	c->right[1] = std::cos(yaw + (Pi / 2));
+	c->right[2] = 0;
+	c->up[0] = c->right[1] * c->forward[2] - c->right[2] * c->forward[1];
+	c->up[1] = c->right[2] * c->forward[0] - c->right[0] * c->forward[2];
+	c->up[2] = c->right[0] * c->forward[1] - c->right[1] * c->forward[0];
+	c->scale = (float)(std::tan(fov_degrees * 0.0174533f * 0.5f) * 2.0f);
+	return CBQ_OK;
+}
+
+int cbq_primary_rays_device(cbq_context* ctx, const cbq_camera* cam, uint32_t width, uint32_t height, cbq_ray* d_rays, void* stream)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!cam || !d_rays || !width || !height) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad argument");
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	CBQ_CUDA(cbq::launchPrimaryRays(*cam, width, height, reinterpret_cast<cbq::Ray*>(d_rays), s));
+	ctx->launches++;
+	return CBQ_OK;
+}
+
+int cbq_raycast_frame_device(cbq_context* ctx, const cbq_camera* cam, uint32_t width, uint32_t height, uint32_t flags,
+	float max_footprint, cbq_hit* d_hits, void* stream)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!cam || !d_hits || !width || !height) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad argument");
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	return traceDevice(ctx, nullptr, (uint64_t)width * height, flags, max_footprint, reinterpret_cast<cbq::Hit*>(d_hits), s, cam, width, height);
+}
+
+int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_params* p, float* d_accum, void* stream)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "no volume uploaded");
+	if (!cam || !p || !d_accum) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");
+	if (!p->width || !p->height || p->x1 > p->width || p->y1 > p->height || p->x0 > p->x1 || p->y0 > p->y1)
+		return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad image rectangle");
+	if (p->variant > 1 || p->bounces > 5) return fail(CBQ_ERROR_INVALID_ARGUMENT, "variant must be 0/1 and bounces <= 5 (the viewer's F2 limit, pathtracing_demo.cpp:280)");
+	if (p->x0 == p->x1 || p->y0 == p->y1 || p->spp == 0) return CBQ_OK;
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	cbq::RenderArgs a;
+	std::memset(&a, 0, sizeof(a));
+	a.nodes = ctx->nodesPtr(); a.subdags = ctx->subdagsPtr(); a.colours = ctx->coloursPtr();
+	a.camera = *cam; a.params = *p; a.accum = d_accum; a.abandoned = ctx->abandonedPtr();
+	rc = nextQueue(ctx, s, &a.queue); if (rc) return rc;
+	applyL2Window(ctx, s);
+	CBQ_CUDA(cbq::launchRender(a, ctx->cfg, s));
+	ctx->launches++;
+	return CBQ_OK;
+}
+
+int cbq_render(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_params* p, float* accum)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!cam || !p || !accum) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");
+	const size_t bytes = (size_t)p->width * p->height * 3 * sizeof(float);
+	if (bytes > ctx->stageAccumBytes) {
+		CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->stageAccum); ctx->stageAccum = nullptr; ctx->stageAccumBytes = 0;
+		CBQ_CUDA(cudaMalloc(&ctx->stageAccum, bytes));
+		ctx->stageAccumBytes = bytes;
+	}
+	// accum is added to, so the caller's running image goes up first (mImage += pixel).
+	CBQ_CUDA(cudaMemcpyAsync(ctx->stageAccum, accum, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	rc = cbq_render_device(ctx, cam, p, ctx->stageAccum, ctx->stream); if (rc) return rc;
+	CBQ_CUDA(cudaMemcpyAsync(accum, ctx->stageAccum, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->bytesH2D += bytes; ctx->bytesD2H += bytes;
+	return CBQ_OK;
+}
+
+int cbq_host_alloc(void** out, uint64_t bytes)
+{
+	if (!out) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");
+	if (cbq_device_count() <= 0) return fail(CBQ_ERROR_NO_DEVICE, "no CUDA device is visible");
+	CBQ_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+	return CBQ_OK;
+}
+
+int cbq_host_free(void* p)
+{
+	if (p) CBQ_CUDA(cudaFreeHost(p));
+	return CBQ_OK;
+}
+
+int cbq_set_option(cbq_context* ctx, const char* key, int64_t value)
+{
+	if (!ctx || !key) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");
+	const std::string k(key);
+	if (k == "block_threads") {
+		if (value < 32 || value > 256 || (value % 32) != 0) return fail(CBQ_ERROR_INVALID_ARGUMENT, "block_threads must be a multiple of 32 in [32, 256]");
+		ctx->cfg.blockThreads = (int)value;
+	} else if (k == "blocks_per_sm") {
+		if (value < 1 || value > 32) return fail(CBQ_ERROR_INVALID_ARGUMENT, "blocks_per_sm must be in [1, 32]");
+		ctx->cfg.blocksPerSm = (int)value;
+	} else if (k == "refill_threshold") {
+		if (value < 1 || value > 32) return fail(CBQ_ERROR_INVALID_ARGUMENT, "refill_threshold must be in [1, 32]");
+		ctx->cfg.refillThreshold = (int)value;
+	} else if (k == "kernel") {
+		if (value < 0 || value > 1) return fail(CBQ_ERROR_INVALID_ARGUMENT, "kernel must be 0 or 1");
+		ctx->cfg.kernel = (int)value;
+	} else if (k == "l2_persist") {
+		ctx->l2Persist = value ? 1 : 0;
+		ctx->windowGeneration = ~0ull; // re-apply on next launch
+	} else {
+		return fail(CBQ_ERROR_INVALID_ARGUMENT, "unknown option '%s'", key);
+	}
+	return CBQ_OK;
+}
+
+int cbq_get_option(cbq_context* ctx, const char* key, int64_t* value)
+{
+	if (!ctx || !key || !value) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");
+	const std::string k(key);
+	if (k == "block_threads") *value = ctx->cfg.blockThreads;
+	else if (k == "blocks_per_sm") *value = ctx->cfg.blocksPerSm;
+	else if (k == "refill_threshold") *value = ctx->cfg.refillThreshold;
+	else if (k == "kernel") *value = ctx->cfg.kernel;
+	else if (k == "l2_persist") *value = ctx->l2Persist;
+	else if (k == "sm_count") *value = ctx->cfg.smCount;
+	else if (k == "stack_levels") *value = ctx->cfg.stackLevels;
+	else if (k == "l2_bytes") *value = ctx->prop.l2CacheSize;
+	else if (k == "l2_persist_max_bytes") *value = ctx->prop.persistingL2CacheMaxSize;
+	else return fail(CBQ_ERROR_INVALID_ARGUMENT, "unknown option '%s'", key);
+	return CBQ_OK;
+}
+
+int cbq_get_counter(cbq_context* ctx, const char* key, uint64_t* value)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!key || !value) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");
+	const std::string k(key);
+	if (k == "kernel_launches") *value = ctx->launches;
+	else if (k == "rays_traced") *value = ctx->raysTraced;
+	else if (k == "bytes_h2d") *value = ctx->bytesH2D;
+	else if (k == "bytes_d2h") *value = ctx->bytesD2H;
+	else if (k == "abandoned_rays") {
+		unsigned long long v = 0;
+		CBQ_CUDA(cudaDeviceSynchronize());
+		CBQ_CUDA(cudaMemcpy(&v, ctx->abandonedPtr(), sizeof(v), cudaMemcpyDeviceToHost));
+		*value = v;
+	} else return fail(CBQ_ERROR_INVALID_ARGUMENT, "unknown counter '%s'", key);
+	return CBQ_OK;
+}
+
+int cbq_reset_counters(cbq_context* ctx)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	ctx->launches = ctx->raysTraced = ctx->bytesH2D = ctx->bytesD2H = 0;
+	CBQ_CUDA(cudaDeviceSynchronize());
+	CBQ_CUDA(cudaMemset(ctx->abandonedPtr(), 0, sizeof(unsigned long long)));
+	return CBQ_OK;
+}
+
+} // extern "C"

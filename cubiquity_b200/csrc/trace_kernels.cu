@@ -1,0 +1,290 @@
+// sm_100a ray-cast kernels: batches of intersectVolume (reference src/library/raytracing.cpp:397-478).
+//
+// COMPILE WITH -fmad=false (see traverse.cuh for the arithmetic contract).
+//
+// tracePersistent -- the production kernel.
+//   * Persistent threads: the grid is (SM count x resident CTAs per SM); every warp loops, taking
+//     tickets from ONE global atomic counter (the ray queue). A warp claims kChunk consecutive rays
+//     per atomic and deals them to its lanes, so the counter sees 1/kChunk of the traffic.
+//   * Dynamic refill: the per-ray work is a flat sequence of `steps` (traverse.cuh). After every
+//     kStepsPerRound steps the warp votes (__ballot_sync); if at least `refillThreshold` lanes have
+//     retired their ray, those lanes are compacted onto the next tickets (rank = popc of the lower
+//     idle lanes) and start new rays while their neighbours keep walking. That is the
+//     warp-vote/ballot compaction of the north star, applied continuously instead of per bounce.
+//   * Per-ray short stack in SHARED memory, one column per thread ([level][thread]: conflict-free),
+//     sized to the deepest sub-DAG of the uploaded volume (13 entries for 4096^3) instead of the
+//     reference's 33-entry local array (raytracing.cpp:251).
+//   * Node words are fetched through the read-only path (ld.global.nc). A sibling step re-reads a
+//     different word of the SAME 32-byte node, i.e. the same L1 sector.
+//   * Rays come either from a buffer (24-byte records) or straight from the camera in 8x4-pixel
+//     tiles per warp (Morton-like locality for primary rays) -- cbq_raycast_frame_device.
+//
+// traceSimple -- one thread per ray, stack in local memory; kept as the A/B baseline.
+#include "cbq_internal.h"
+
+namespace cbq {
+
+namespace {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kChunk = 128;           // rays claimed per atomic ticket
+constexpr int kStepsPerRound = 8;     // traversal steps between two refill votes
+
+struct GlobalNodes {
+	const uint32_t* __restrict__ base;
+	__device__ __forceinline__ uint32_t child(uint32_t node, uint32_t slot) const
+	{
+		return __ldg(base + ((size_t)node * 8u + slot));
+	}
+};
+
+struct SharedStack {          // one column of a [levels][blockDim.x] array
+	uint32_t* column;
+	uint32_t stride;
+	__device__ __forceinline__ void store(int h, uint32_t n) { column[(uint32_t)h * stride] = n; }
+	__device__ __forceinline__ uint32_t load(int h) const { return column[(uint32_t)h * stride]; }
+};
+
+struct LocalStack {
+	uint32_t v[33];
+	__device__ __forceinline__ void store(int h, uint32_t n) { v[h] = n; }
+	__device__ __forceinline__ uint32_t load(int h) const { return v[h]; }
+};
+
+__device__ __forceinline__ void loadRay(const Ray* __restrict__ rays, uint64_t i, Ray& r)
+{
+	// 24-byte records are 8-byte aligned: three 64-bit read-only loads.
+	const float2* p = reinterpret_cast<const float2*>(rays + i);
+	const float2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+	r.o[0] = a.x; r.o[1] = a.y; r.o[2] = b.x; r.d[0] = b.y; r.d[1] = c.x; r.d[2] = c.y;
+}
+
+__device__ __forceinline__ void storeHit(Hit* __restrict__ hits, uint64_t i, const Hit& h)
+{
+	// 40-byte records are 8-byte aligned: five 64-bit stores.
+	uint2* p = reinterpret_cast<uint2*>(hits + i);
+	p[0] = make_uint2(h.hit, __float_as_uint(h.distance));
+	p[1] = make_uint2(h.material, __float_as_uint(h.position[0]));
+	p[2] = make_uint2(__float_as_uint(h.position[1]), __float_as_uint(h.position[2]));
+	p[3] = make_uint2(__float_as_uint(h.normal[0]), __float_as_uint(h.normal[1]));
+	p[4] = make_uint2(__float_as_uint(h.normal[2]), h.status);
+}
+
+// Camera::rayFromViewportPos (reference src/application/commands/view/camera.cpp:19-35) followed by
+// static_cast<Ray3f> (pathtracing_demo.cpp:220). Mixed float/double exactly as written there.
+__device__ __forceinline__ void cameraRay(const cbq_camera& c, int x, int y, int width, int height, Ray& out)
+{
+	const double invWidth = (double)(1.0f / (float)width);
+	const double invHeight = (double)(1.0f / (float)height);
+	const float aspect = (float)width / (float)height;
+	const float xOff = ((float)x - ((float)width / 2.0f)) + 0.5f;
+	const float yOff = ((float)y - ((float)height / 2.0f)) + 0.5f;
+	const double kx = ((invWidth * (double)xOff) * (double)aspect) * (double)c.scale;
+	const double ky = (invHeight * (double)yOff) * (double)c.scale;
+	double dir[3];
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		double t = c.position[a] + c.forward[a];
+		t += c.right[a] * kx;
+		t -= c.up[a] * ky;
+		dir[a] = t - c.position[a];
+	}
+	const double len = sqrt(((0.0 + dir[0] * dir[0]) + dir[1] * dir[1]) + dir[2] * dir[2]);
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		out.o[a] = (float)c.position[a];
+		out.d[a] = (float)(dir[a] / len);
+	}
+}
+
+// Ray sources. `ticket` is the position in the queue; `slot` is where the result goes.
+struct BufferSource {
+	const Ray* __restrict__ rays;
+	__device__ __forceinline__ void fetch(uint64_t ticket, Ray& r, uint64_t& slot) const { loadRay(rays, ticket, r); slot = ticket; }
+};
+
+struct CameraSource {
+	cbq_camera cam;
+	uint32_t width, height, tilesX;
+	// Tickets enumerate 8x4-pixel tiles row by row, 32 tickets per tile, so the 32 lanes of a warp
+	// start on one compact tile. Tiles overhanging the image produce slot = ~0 (skipped).
+	__device__ __forceinline__ void fetch(uint64_t ticket, Ray& r, uint64_t& slot) const
+	{
+		const uint32_t tile = (uint32_t)(ticket >> 5), within = (uint32_t)ticket & 31u;
+		const uint32_t tx = tile % tilesX, ty = tile / tilesX;
+		const uint32_t x = tx * 8u + (within & 7u), y = ty * 4u + (within >> 3);
+		if (x < width && y < height) {
+			cameraRay(cam, (int)x, (int)y, (int)width, (int)height, r);
+			slot = (uint64_t)y * width + x;
+		} else {
+			slot = ~0ull;
+		}
+	}
+};
+
+template <bool kSurface, typename Source>
+__global__ void __launch_bounds__(256, 4)
+tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict__ subdagsGlobal, Source source,
+	Hit* __restrict__ hits, uint64_t count, float maxFootprint, int refillThreshold,
+	unsigned long long* __restrict__ queue, unsigned long long* __restrict__ abandoned)
+{
+	extern __shared__ uint32_t stackMem[];
+	__shared__ SubDag subdags[8];
+	if (threadIdx.x < 64) reinterpret_cast<uint32_t*>(subdags)[threadIdx.x] = reinterpret_cast<const uint32_t*>(subdagsGlobal)[threadIdx.x];
+	__syncthreads();
+
+	const GlobalNodes nodes{ nodeBase };
+	SharedStack stack{ stackMem + threadIdx.x, blockDim.x };
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lowerLanes = (1u << lane) - 1u;
+
+	RayState s;
+	s.phase = kPhaseIdle;
+	uint64_t slot = 0, ticketOfRay = 0;
+	// Warp-uniform window of claimed tickets.
+	uint64_t chunkNext = 0, chunkEnd = 0;
+	bool drained = false;
+
+	for (;;) {
+		const unsigned idle = __ballot_sync(kFullMask, s.phase == kPhaseIdle);
+		if (idle != 0u && !drained && (__popc(idle) >= refillThreshold || idle == kFullMask)) {
+			int want = __popc(idle);
+			int myRank = __popc(idle & lowerLanes);
+			// Deal from the current chunk, claiming a new one when it runs dry.
+			while (want > 0) {
+				if (chunkNext == chunkEnd) {
+					unsigned long long base = 0;
+					if (lane == 0) base = atomicAdd(queue, (unsigned long long)kChunk);
+					base = __shfl_sync(kFullMask, base, 0);
+					if (base >= count) { drained = true; break; }
+					chunkNext = base;
+					chunkEnd = (base + kChunk < count) ? base + kChunk : count;
+				}
+				const int avail = (int)(chunkEnd - chunkNext);
+				const int take = want < avail ? want : avail;
+				if (s.phase == kPhaseIdle && myRank >= 0 && myRank < take) {
+					Ray r;
+					ticketOfRay = chunkNext + (uint64_t)myRank;
+					source.fetch(ticketOfRay, r, slot);
+					if (slot != ~0ull) beginRay(s, r);
+					myRank = -1;    // served
+				} else if (myRank >= take) {
+					myRank -= take;
+				}
+				chunkNext += (uint64_t)take;
+				want -= take;
+			}
+		}
+		if (__ballot_sync(kFullMask, s.phase != kPhaseIdle) == 0u) {
+			if (drained) break;
+			continue;
+		}
+
+#pragma unroll 1
+		for (int k = 0; k < kStepsPerRound; k++) {
+			if (s.phase == kPhaseIdle) continue;
+			Hit out;
+			StepResult res;
+			if (s.phase == kPhaseOctant) res = stepOctant(s, subdags);
+			else res = stepEsvo(s, nodes, stack, maxFootprint, kSurface, out);
+			if (res != kStepContinue) {
+				if (res == kStepHit) {
+					if (!kSurface) { out.material = 0; out.normal[0] = out.normal[1] = out.normal[2] = 0.0f; }
+					out.status = 0;
+					Ray r; uint64_t again;
+					source.fetch(ticketOfRay, r, again);   // the un-reflected ray, for position = o + d * t
+					finishHit(out, r);
+				} else {
+					clearHit(out);
+					if (res == kStepAbandoned) { out.status = CBQ_HIT_ABANDONED; atomicAdd(abandoned, 1ull); }
+				}
+				storeHit(hits, slot, out);
+				s.phase = kPhaseIdle;
+			}
+		}
+	}
+}
+
+template <bool kSurface>
+__global__ void __launch_bounds__(128)
+traceSimple(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict__ subdagsGlobal, const Ray* __restrict__ rays,
+	Hit* __restrict__ hits, uint64_t count, float maxFootprint, unsigned long long* __restrict__ abandoned)
+{
+	__shared__ SubDag subdags[8];
+	if (threadIdx.x < 64) reinterpret_cast<uint32_t*>(subdags)[threadIdx.x] = reinterpret_cast<const uint32_t*>(subdagsGlobal)[threadIdx.x];
+	__syncthreads();
+	const GlobalNodes nodes{ nodeBase };
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+		Ray r;
+		loadRay(rays, i, r);
+		LocalStack stack;
+		Hit out;
+		traceRay<kSurface>(r, nodes, subdags, stack, maxFootprint, out);
+		if (out.status) atomicAdd(abandoned, 1ull);
+		storeHit(hits, i, out);
+	}
+}
+
+__global__ void __launch_bounds__(256)
+primaryRays(cbq_camera cam, uint32_t width, uint32_t height, Ray* __restrict__ rays)
+{
+	const uint64_t total = (uint64_t)width * height;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint32_t x = (uint32_t)(i % width), y = (uint32_t)(i / width);
+		Ray r;
+		cameraRay(cam, (int)x, (int)y, (int)width, (int)height, r);
+		float2* p = reinterpret_cast<float2*>(rays + i);
+		p[0] = make_float2(r.o[0], r.o[1]); p[1] = make_float2(r.o[2], r.d[0]); p[2] = make_float2(r.d[1], r.d[2]);
+	}
+}
+
+template <bool kSurface, typename Source>
+cudaError_t launchPersistent(const TraceArgs& a, const Source& src, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
+{
+	auto kernel = tracePersistent<kSurface, Source>;
+	const size_t smem = (size_t)cfg.stackLevels * (size_t)cfg.blockThreads * sizeof(uint32_t);
+	cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	int grid = cfg.smCount * cfg.blocksPerSm;
+	const uint64_t needed = (tickets + (uint64_t)cfg.blockThreads - 1) / (uint64_t)cfg.blockThreads;
+	if ((uint64_t)grid > needed) grid = (int)(needed ? needed : 1);
+	kernel<<<grid, cfg.blockThreads, smem, stream>>>(a.nodes, a.subdags, src, a.hits, tickets, a.maxFootprint,
+		cfg.refillThreshold, a.queue, a.abandoned);
+	return cudaGetLastError();
+}
+
+} // namespace
+
+cudaError_t launchTrace(const TraceArgs& a, bool surface, const LaunchConfig& cfg, cudaStream_t stream)
+{
+	if (a.rays == nullptr) {
+		CameraSource src;
+		src.cam = a.camera; src.width = a.width; src.height = a.height; src.tilesX = (a.width + 7u) / 8u;
+		const uint64_t tickets = (uint64_t)src.tilesX * ((a.height + 3u) / 4u) * 32u;
+		return surface ? launchPersistent<true>(a, src, tickets, cfg, stream) : launchPersistent<false>(a, src, tickets, cfg, stream);
+	}
+	if (cfg.kernel == 1) {
+		const int block = 128;
+		uint64_t blocks = (a.count + block - 1) / block;
+		const uint64_t cap = (uint64_t)cfg.smCount * 64u;
+		if (blocks > cap) blocks = cap;
+		if (blocks == 0) blocks = 1;
+		if (surface) traceSimple<true><<<(int)blocks, block, 0, stream>>>(a.nodes, a.subdags, a.rays, a.hits, a.count, a.maxFootprint, a.abandoned);
+		else traceSimple<false><<<(int)blocks, block, 0, stream>>>(a.nodes, a.subdags, a.rays, a.hits, a.count, a.maxFootprint, a.abandoned);
+		return cudaGetLastError();
+	}
+	BufferSource src{ a.rays };
+	return surface ? launchPersistent<true>(a, src, a.count, cfg, stream) : launchPersistent<false>(a, src, a.count, cfg, stream);
+}
+
+cudaError_t launchPrimaryRays(const cbq_camera& cam, uint32_t width, uint32_t height, Ray* rays, cudaStream_t stream)
+{
+	const uint64_t total = (uint64_t)width * height;
+	uint64_t blocks = (total + 255) / 256;
+	if (blocks > 148u * 8u) blocks = 148u * 8u;
+	if (blocks == 0) blocks = 1;
+	primaryRays<<<(int)blocks, 256, 0, stream>>>(cam, width, height, rays);
+	return cudaGetLastError();
+}
+
+} // namespace cbq

@@ -1,0 +1,203 @@
+/* cubiquity_b200 -- C ABI of the Blackwell-native SVDAG ray cast and path tracer.
+ *
+ * This is the drop-in boundary for ONE path of Cubiquity (reference tree under
+ * /root/reference, citations are relative to it): ray traversal of the Sparse Voxel DAG
+ * and the path-tracer bounce loop built on it. The reference has no FFI of its own
+ * ("there is no C API at present", README.md:136-137); each entry point below names the
+ * C++ interface it stands in for. Plain pointers and sizes only, no exceptions cross the
+ * boundary, every function returns a status code (CBQ_OK == 0) and cbq_last_error() gives
+ * the message, in the manner of the existing C-style wrappers (src/library/cubiquity.h:22-26).
+ *
+ * One cbq_context per GPU. Calls on one context are serialised (stream ordered); different
+ * contexts may be driven from different host threads.
+ *
+ * There is NO CPU fallback anywhere behind this header: without a CUDA device every compute
+ * entry point fails with CBQ_ERROR_NO_DEVICE.
+ */
+#ifndef CUBIQUITY_B200_H
+#define CUBIQUITY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CBQ_VERSION 100
+
+enum {
+	CBQ_OK = 0,
+	CBQ_ERROR_INVALID_ARGUMENT = 1,
+	CBQ_ERROR_NO_DEVICE = 2,
+	CBQ_ERROR_CUDA = 3,
+	CBQ_ERROR_OUT_OF_MEMORY = 4,
+	CBQ_ERROR_NO_VOLUME = 5,
+	CBQ_ERROR_CORRUPT_VOLUME = 6
+};
+
+/* ---- records ------------------------------------------------------------------------- */
+
+/* A ray: the six floats every caller of intersectVolume passes (src/library/raytracing.h:72-75). */
+typedef struct cbq_ray { float origin[3]; float dir[3]; } cbq_ray;                  /* 24 bytes */
+
+/* Every field of struct RayVolumeIntersection (src/library/raytracing.h:48-55). `distance` is
+ * the float the reference computes and then widens to double (raytracing.cpp:305); the C++
+ * shim in cubiquity_b200/host/cubiquity_gpu.h widens it back. */
+typedef struct cbq_hit {
+	uint32_t hit;
+	float    distance;
+	uint32_t material;
+	float    position[3];
+	float    normal[3];
+	uint32_t status;      /* 0, or CBQ_HIT_ABANDONED: see "degenerate rays" in DESIGN.md */
+} cbq_hit;                                                                          /* 40 bytes */
+#define CBQ_HIT_ABANDONED 1u
+
+/* struct SubDAG verbatim (src/library/raytracing.h:57-65; GLSL mirror glsl/pathtracing.frag:118-126). */
+typedef struct cbq_subdag {
+	int32_t  lower[3];
+	int32_t  height;
+	uint32_t pad0;
+	uint32_t node;
+	uint32_t pad1, pad2;
+} cbq_subdag;                                                                       /* 32 bytes */
+
+/* class Camera (src/application/commands/view/camera.h:8-27) after forward()/right()/up() and
+ * the fov scale have been evaluated on the host (camera.cpp:24,40-66: libm sin/cos/tan are not
+ * bit-portable to the device; everything per-pixel in camera.cpp:19-35 is, and runs on the GPU). */
+typedef struct cbq_camera {
+	double position[3];
+	double forward[3];
+	double up[3];
+	double right[3];
+	float  scale;
+	float  pad;
+} cbq_camera;
+
+/* The knobs of PathtracingDemo (src/application/commands/view/pathtracing_demo.h:80-84). */
+typedef struct cbq_pt_params {
+	uint32_t width, height;
+	uint32_t spp;              /* samples accumulated per pixel by this call */
+	uint32_t bounces;          /* pathtracing_demo.h:80 (used by variant 1 only, like the reference) */
+	uint32_t variant;          /* 0: traceSingleRay (pathtracing_demo.cpp:150-190); 1: traceSingleRayRecurse (:120-148) */
+	uint32_t include_sun, include_sky, add_noise;
+	float    max_footprint;    /* 0.0035 in the reference; -1 disables LOD */
+	uint32_t frame_id;         /* index of the first sample: sample s is seeded with frame_id + s */
+	uint32_t x0, y0, x1, y1;   /* pixel rectangle [x0,x1) x [y0,y1) this call renders (tile sharding) */
+	uint32_t pad;
+} cbq_pt_params;
+
+#define CBQ_VARIANT_ONE_BOUNCE 0u
+#define CBQ_VARIANT_RECURSIVE  1u
+
+/* cbq_trace flags */
+#define CBQ_TRACE_SURFACE 1u   /* computeSurfaceProperties = true (raytracing.h:75) */
+
+#define CBQ_MAX_FOOTPRINT_DISABLED (-1.0f)   /* MAX_FOOTPRINT_DISABLED, raytracing.h:71 */
+
+typedef struct cbq_context cbq_context;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+
+int  cbq_create(int device, cbq_context** out);
+void cbq_destroy(cbq_context* ctx);
+const char* cbq_last_error(void);              /* thread-local, never NULL */
+int  cbq_device_count(void);                   /* 0 when no CUDA device / driver is present */
+int  cbq_synchronize(cbq_context* ctx);
+
+/* ---- DAG -> GPU serialisation ------------------------------------------- */
+
+/* Replaces the one-off glBufferData upload of gpu_pathtracing_viewer.cpp:43-67.
+ * nodes      : NodeStore::rawBytesPtr() (storage.h:101) -- node_count x 8 u32 INCLUDING the 256
+ *              material nodes.
+ * root_index : Internals::getRootNodeIndex(volume) (storage.cpp:573-576).
+ * colours_rgb: 256 x 3 floats (Viewer::colours(), viewer.cpp:50-55) or NULL for all-purple.
+ * The eight sub-DAGs (findSubDAGs, raytracing.cpp:89-97) are computed here and the whole lot is
+ * flattened into ONE linear device buffer: [header | subDAG[8] | colours | nodes...]. */
+int cbq_upload(cbq_context* ctx, const uint32_t* nodes, uint64_t node_count, uint32_t root_index,
+               const float* colours_rgb);
+
+/* Delta re-upload after a runtime edit (Viewer::onMouseButtonDown, viewer.cpp:152-172:
+ * checkpoint -> fillBrush -> onVolumeModified). Copy-on-write (NodeStore::setNodeChild,
+ * storage.cpp:152-167) only ever touches nodes at or above sharedNodesEnd(), so the device copy
+ * is stale exactly on the tail [dirty_begin, node_count): pass dirty_begin = the
+ * sharedNodesEnd() seen at the previous sync (or anything lower), the CURRENT base pointer and
+ * node count, and the new root. Sub-DAGs are recomputed (pathtracing_demo.cpp:335-341).
+ * After Volume::bake() everything moved: call cbq_upload again. */
+int cbq_update(cbq_context* ctx, const uint32_t* nodes, uint64_t dirty_begin, uint64_t node_count,
+               uint32_t root_index);
+
+int cbq_set_colours(cbq_context* ctx, const float* colours_rgb);
+int cbq_get_subdags(cbq_context* ctx, cbq_subdag out[8]);
+
+/* Host-only restatement of findSubDAGs for callers that want it without a device. */
+int cbq_find_subdags(const uint32_t* nodes, uint64_t node_count, uint32_t root_index, cbq_subdag out[8]);
+
+/* Read nodes [begin, begin + count) back from the device copy (testing / verification). */
+int cbq_download_nodes(cbq_context* ctx, uint64_t begin, uint64_t count, uint32_t* out);
+int cbq_node_count(cbq_context* ctx, uint64_t* out);
+
+/* ---- ray cast: intersectVolume over a batch -------------------------------------------- */
+
+/* hits[i] = intersectVolume(volume, subDAGs, rays[i]..., flags & CBQ_TRACE_SURFACE, max_footprint)
+ * (raytracing.cpp:397-478) for every i. Host buffers; pinned memory (cbq_host_alloc) makes the
+ * copies asynchronous and overlapped with the kernel. */
+int cbq_trace(cbq_context* ctx, const cbq_ray* rays, uint64_t n, uint32_t flags, float max_footprint,
+              cbq_hit* hits);
+
+/* Same with device pointers, enqueued on `stream` (a cudaStream_t; NULL = the context's stream). */
+int cbq_trace_device(cbq_context* ctx, const cbq_ray* d_rays, uint64_t n, uint32_t flags,
+                     float max_footprint, cbq_hit* d_hits, void* stream);
+
+/* Camera::rayFromViewportPos (camera.cpp:12-38) for every pixel, row-major, cast to float like
+ * static_cast<Ray3f> in PathtracingDemo::raytrace (pathtracing_demo.cpp:220). */
+int cbq_camera_from_pose(const double position[3], double pitch, double yaw, double fov_degrees,
+                         cbq_camera* out);
+int cbq_primary_rays_device(cbq_context* ctx, const cbq_camera* cam, uint32_t width, uint32_t height,
+                            cbq_ray* d_rays, void* stream);
+
+/* Fused: generate the primary ray of every pixel (8x4-pixel tiles per warp for coherence) and
+ * trace it; d_hits is row-major width x height. */
+int cbq_raycast_frame_device(cbq_context* ctx, const cbq_camera* cam, uint32_t width, uint32_t height,
+                             uint32_t flags, float max_footprint, cbq_hit* d_hits, void* stream);
+
+/* ---- path tracer: PathtracingDemo::raytrace -------------------------------------------- */
+
+/* accum (width x height x 3 floats, row-major) has p->spp samples ADDED to every pixel of the
+ * rectangle, like `mImage[...] += pixel` (pathtracing_demo.cpp:224). Per-pixel RNG stream:
+ * seed = hashRay(primary ray) ^ fmix32(frame_id + s) (the GLSL tracer's rule,
+ * glsl/pathtracing.frag:770-780,816), advanced by (u32)bit_mix (pathtracing_demo.cpp:67). */
+int cbq_render(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_params* p, float* accum);
+int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_params* p, float* d_accum,
+                      void* stream);
+
+/* ---- pinned host memory, tuning, counters ---------------------------------------------- */
+
+int cbq_host_alloc(void** out, uint64_t bytes);
+int cbq_host_free(void* p);
+
+/* Options: "block_threads", "blocks_per_sm", "refill_threshold", "l2_persist" (0/1),
+ * "kernel" (0 = persistent queue kernel, 1 = plain one-thread-per-ray), "sort_rays" (0/1). */
+int cbq_set_option(cbq_context* ctx, const char* key, int64_t value);
+int cbq_get_option(cbq_context* ctx, const char* key, int64_t* value);
+
+/* Counters: "kernel_launches", "rays_traced", "bytes_h2d", "bytes_d2h", "abandoned_rays". */
+int cbq_get_counter(cbq_context* ctx, const char* key, uint64_t* value);
+int cbq_reset_counters(cbq_context* ctx);
+
+/* ---- procedural scenes (inputs for tests and benchmarks; host only) --------------------- */
+
+typedef struct cbq_scene cbq_scene;
+/* kind: "sphere_noise" | "terrain" | "soup" | "city". The volume is 2^size_log2 voxels a side. */
+int cbq_scene_build(const char* kind, uint32_t size_log2, uint64_t seed, cbq_scene** out);
+const uint32_t* cbq_scene_nodes(const cbq_scene* s, uint64_t* node_count);
+uint32_t cbq_scene_root(const cbq_scene* s);
+void cbq_scene_bounds(const cbq_scene* s, int32_t lower[3], int32_t upper[3]);
+void cbq_scene_colours(const cbq_scene* s, float* rgb768);
+void cbq_scene_voxels(const cbq_scene* s, const int32_t* xyz, uint64_t n, uint8_t* out);
+void cbq_scene_free(cbq_scene* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUBIQUITY_B200_H */

@@ -29,6 +29,7 @@
 
 #define MATERIAL_COUNT 256u   /* storage.h:55 */
 #define ROOT_HEIGHT 32        /* raytracing.cpp:12 */
+#define NO_MATERIAL 0xffffffffu
 
 /* std::min(a,b) returns b only when b < a; std::max(a,b) returns b only when a < b. */
 static inline float min_std(float a, float b) { return (b < a) ? b : a; }
@@ -90,12 +91,19 @@ static uint32_t nearest_material(const uint32_t* nodes, uint32_t node, uint32_t 
 {
 	/* raytracing.cpp:134-162: fixed near-to-far child order, reflected by the ray's sign bits. */
 	const uint32_t order = (0x76534210u | 0x88888888u) ^ (signBits * 0x11111111u);
+	int levels = 0;
 	while (node >= MATERIAL_COUNT) {
+		int found = 0;
 		for (uint32_t ids = order; ids != 0; ids >>= 4) {
 			uint32_t child = nodes[(uint64_t)node * 8 + (ids & 7u)];
 			if (st) st->material_steps++;
-			if (child > 0) { node = child; break; }
+			if (child > 0) { node = child; found = 1; break; }
 		}
+		/* QUIRK Q6 (ours to handle): an internal node whose eight children are all empty -- legal in
+		 * an edited, un-baked volume because fillBrush/setNodeChild never collapse nodes
+		 * (voxelization.cpp:825-915, storage.cpp:152-167) -- makes the reference spin here for ever.
+		 * Report "no material" and let the caller abandon the ray. Same rule in the GPU kernel. */
+		if (!found || ++levels > ROOT_HEIGHT) return NO_MATERIAL;
 	}
 	return node;
 }
@@ -183,6 +191,7 @@ static int esvo_node(const uint32_t* nodes, uint32_t node, const int32_t nodePos
 				hit->distance = tEntry;
 				if (surf) {
 					hit->material = nearest_material(nodes, child, signBits, st);
+					if (hit->material == NO_MATERIAL) { hit->pad = 1; return 0; }
 					for (int a = 0; a < 3; a++) {
 						float n = (tEntry == c0[a]) ? 1.0f : 0.0f;
 						hit->normal[a] = n * (-sign[a]);
@@ -267,7 +276,7 @@ void cbqo_intersect(const uint32_t* nodes, const cbqo_subdag sd[8], const cbqo_r
 				if (st) st->hits++;
 				break;
 			}
-			if (out->pad) break; /* Q5: traversal abandoned */
+			if (out->pad) { memset(out, 0, sizeof(*out)); out->pad = 1; break; } /* Q5/Q6: traversal abandoned */
 		}
 		const float nearest = least3(dist);
 		for (int a = 0; a < 3; a++) {
