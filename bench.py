@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the SVDAG ray-cast hot path (BASELINE.json metric: Grays/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload primary|random|pathtrace]
+
+Default workload = BASELINE.json configs[1]: primary-ray ray cast, 1920x1080, against the procedural
+4096^3 multi-material terrain, LOD off, surface properties on. One "step" = one pass of
+cbq_trace_device over one frame of rays (2 073 600 rays) that already sit in HBM.
+
+  value      whole-job Grays/s, device-timed (CUDA events on the launching stream, one pair per step,
+             L2 flushed between steps), max over ranks.
+  e2e        the same metric through the public host-buffer call cbq_trace(): pinned host rays in,
+             pinned host hits out, both copies inside the timed region.
+  roofline   algorithmic bytes per ray (32 B x node visits V + 24 B ray + 40 B hit; V counted by the
+             instrumented oracle on a sample of the same rays) x rays / kernel time, against the
+             measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the reference's own intersectVolume (oracle/_ref, compiled from /root/reference) on the
+             GPU box's host cores, same rays. oracle/ is used ONLY here and in --impl reference.
+
+N > 1 (torchrun): the DAG is built on rank 0 and replicated with one NCCL broadcast; every rank then
+traces its own frame (its own camera on an orbit) -- weak scaling, no collective in the data path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT = 1920, 1080
+SCENE_KIND, SCENE_LOG2, SCENE_SEED = "terrain", 12, 1
+PI_F = float(np.float32(3.14159265358979))
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="primary", choices=["primary", "random", "pathtrace"])
+    ap.add_argument("--scene-log2", type=int, default=SCENE_LOG2)
+    ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (reported as such)")
+    ap.add_argument("--option", action="append", default=[], help="key=value passed to cbq_set_option")
+    ap.add_argument("--spp", type=int, default=4)
+    ap.add_argument("--bounces", type=int, default=4)
+    ap.add_argument("--random-rays", type=int, default=8_000_000)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def orbit_camera(api, scene, rank):
+    """Rank 0 = the viewer's default pose (reference viewer.cpp:71-79); other ranks orbit the scene."""
+    lower = np.asarray(scene.lower, dtype=np.float64)
+    upper = np.asarray(scene.upper, dtype=np.float64)
+    centre = (lower + upper) * 0.5
+    half_diag = float(np.sqrt(((upper - lower) ** 2).sum())) * 0.5
+    yaw = rank * (2.0 * np.pi / 8.0)
+    pos = [centre[0] - half_diag * np.sin(yaw), centre[1] - half_diag * np.cos(yaw), centre[2] + half_diag]
+    return api.camera_from_pose(pos, -(PI_F / 4.0), yaw), pos, yaw
+
+
+def reference_arm(args):
+    """bench.py --impl reference: the reference's own CPU intersectVolume, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from cubiquity_b200 import api
+    from oracle import pyoracle
+    scene = api.Scene(SCENE_KIND, args.scene_log2, SCENE_SEED)
+    port = pyoracle.Port()
+    cam, pos, yaw = orbit_camera(api, scene, 0)
+    ocam = port.camera(pos, -(PI_F / 4.0), yaw)
+    rays = port.camera_rays(ocam, WIDTH, HEIGHT)
+    threads = os.cpu_count() or 1
+    kind = "reference"
+    try:
+        vol = pyoracle.Ref().volume().load_arrays(scene.nodes, scene.root)
+        run = lambda r: vol.intersect(r, True, -1.0, threads=threads, want_hits=True)[1]
+    except Exception:
+        kind = "port"
+        sd = port.find_subdags(scene.nodes, scene.root)
+        run = lambda r: port.trace(scene.nodes, sd, r, True, -1.0, threads=threads)[1]
+    # Bounded sample per step: every 4th 8-row band of the frame (about half a million rays).
+    rows = np.arange(HEIGHT).reshape(-1, 8)[::4].reshape(-1)
+    sample = np.ascontiguousarray(rays.reshape(HEIGHT, WIDTH)[rows].reshape(-1))
+    for _ in range(args.warmup):
+        run(sample)
+    secs = [run(sample) for _ in range(args.steps)]
+    total = float(np.sum(secs))
+    value = len(sample) * args.steps / total / 1e9
+    line = {
+        "impl": "reference", "metric": "Grays/s SVDAG traversal (primary rays)", "value": value, "unit": "Grays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
+        "config": {"workload": "primary rays 1920x1080 vs procedural 4096^3 terrain SVDAG (BASELINE configs[1]), LOD off, surface properties on",
+                   "scene": "%s 2^%d seed %d" % (SCENE_KIND, args.scene_log2, SCENE_SEED), "nodes": int(len(scene.nodes))},
+        "cpu_baseline": {"value": value, "unit": "Grays/s", "cores": threads, "kind": kind,
+                         "sample": "%d rays per step: every 4th 8-row band of the 1080p frame" % len(sample)},
+        "e2e": {"value": value, "unit": "Grays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from cubiquity_b200 import api, sharding
+    from cubiquity_b200 import rays as R
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: cubiquity_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- scene: built on rank 0, replicated by broadcast -------------------------------------
+    t0 = time.time()
+    scene = None
+    if rank == 0:
+        scene = api.Scene(SCENE_KIND, args.scene_log2, SCENE_SEED)
+        nodes, root, colours = scene.nodes, scene.root, scene.colours
+        lower, upper = scene.lower.copy(), scene.upper.copy()
+    build_s = time.time() - t0
+    if world > 1:
+        nodes, root = sharding.broadcast_volume(dist, nodes if rank == 0 else None, root if rank == 0 else None, device=dev)
+        meta = torch.zeros(6, dtype=torch.int64, device=dev)
+        if rank == 0:
+            meta[:3] = torch.from_numpy(lower.astype(np.int64))
+            meta[3:] = torch.from_numpy(upper.astype(np.int64))
+        dist.broadcast(meta, src=0)
+        lower, upper = meta[:3].cpu().numpy(), meta[3:].cpu().numpy()
+        col = torch.from_numpy(colours.copy()).to(dev) if rank == 0 else torch.empty(256, 3, device=dev)
+        dist.broadcast(col, src=0)
+        colours = col.cpu().numpy()
+
+    class Bounds:
+        pass
+    b = Bounds()
+    b.lower, b.upper = lower, upper
+
+    ctx = api.Context(local)
+    for kv in args.option:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
+    ctx.upload(nodes, root, colours)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- inputs resident in HBM --------------------------------------------------------------
+    cam, pos, yaw = orbit_camera(api, b, rank)
+    if args.workload == "random":
+        n_rays = args.random_rays
+        host_rays = R.random_rays(n_rays, lower, upper, seed=100 + rank)
+        d_rays = torch.from_numpy(host_rays.view(np.float32).reshape(-1)).to(dev)
+        workload = "incoherent batch of %d random rays (origin U(bounds+10%%), random direction) vs procedural 4096^3 terrain SVDAG (BASELINE configs[2], reduced count)" % n_rays
+    else:
+        n_rays = WIDTH * HEIGHT
+        d_rays = torch.empty(n_rays * 6, dtype=torch.float32, device=dev)
+        ctx.primary_rays_device(cam, WIDTH, HEIGHT, d_rays.data_ptr(), stream)
+        workload = "primary rays 1920x1080 vs procedural 4096^3 terrain SVDAG (BASELINE configs[1]), LOD off, surface properties on"
+    d_hits = torch.zeros(n_rays * 10, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # 2x the 126 MB L2
+    torch.cuda.synchronize()
+
+    def step():
+        ctx.trace_device(d_rays.data_ptr(), n_rays, d_hits.data_ptr(), True, -1.0, stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps, one CUDA-event pair per step on the launching stream ----
+    ctx.reset_counters()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        wall0 = time.time()
+        for i in range(args.steps):
+            if not args.no_flush:
+                flush.zero_()                      # evict the DAG, rays and hits from L2 (untimed)
+            starts[i].record()
+            step()
+            stops[i].record()
+        torch.cuda.synchronize()
+        wall = time.time() - wall0
+    launches = ctx.counter("kernel_launches")
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    total_ms = float(np.sum(step_ms))
+    if world > 1:
+        dist.barrier()
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n_rays / (ms_per_step * 1e-3) / 1e9
+
+    # warm-L2 figure for context (same kernel, no flush)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    warm_ms = e0.elapsed_time(e1) / args.steps
+
+    # ---- end to end through the public host-buffer call ------------------------------------------
+    pin_rays = api.PinnedArray(n_rays, api.RAY_DTYPE)
+    pin_hits = api.PinnedArray(n_rays, api.HIT_DTYPE)
+    pin_rays.array[:] = d_rays.cpu().numpy().view(api.RAY_DTYPE).reshape(-1)
+    for _ in range(2):
+        ctx.intersect_volume(pin_rays.array, True, -1.0, out=pin_hits.array)
+    e2e_steps = max(3, min(args.steps, 10))
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.intersect_volume(pin_rays.array, True, -1.0, out=pin_hits.array)   # returns after the D2H copy
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * n_rays / e2e_s / 1e9
+    hit_fraction = float((pin_hits.array["hit"] == 1).mean())
+    device_hits = d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)
+    same = device_hits.tobytes() == pin_hits.array.tobytes()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rank 0: oracle-derived roofline and CPU baseline (the only use of oracle/ in this file) ---
+    from oracle import pyoracle
+    port = pyoracle.Port()
+    host_rays = pin_rays.array.copy()
+    sd = port.find_subdags(nodes, root)
+    pick = np.arange(0, n_rays, max(1, n_rays // 200000))
+    _, _, st = port.trace(nodes, sd, host_rays[pick], True, -1.0, threads=os.cpu_count() or 1, want_hits=False, want_stats=True)
+    visits = st.node_visits() / len(pick)
+    bytes_per_ray = 32.0 * visits + 24.0 + 40.0
+    peak, peak_src = peaks()
+    achieved = n_rays * bytes_per_ray / (ms_per_step * 1e-3) / 1e9
+    # parity spot check of what was just timed
+    want, _, _ = port.trace(nodes, sd, host_rays[pick], True, -1.0, threads=os.cpu_count() or 1)
+    parity = float((want.view(np.uint32).reshape(-1, 10) == device_hits[pick].view(np.uint32).reshape(-1, 10)).all(axis=1).mean())
+
+    threads = os.cpu_count() or 1
+    kind = "reference"
+    try:
+        vol = pyoracle.Ref().volume().load_arrays(nodes, root)
+        run = lambda r, t: vol.intersect(r, True, -1.0, threads=t, want_hits=True)[1]
+    except Exception:
+        kind = "port"
+        run = lambda r, t: port.trace(nodes, sd, r, True, -1.0, threads=t)[1]
+    cpu_sample = host_rays[: min(n_rays, 1 << 20)]
+    run(cpu_sample[:50000], threads)
+    cpu_all = len(cpu_sample) / run(cpu_sample, threads) / 1e9
+    cpu_one_sample = cpu_sample[:: 8]
+    cpu_one = len(cpu_one_sample) / run(cpu_one_sample, 1) / 1e9
+
+    line = {
+        "metric": "Grays/s SVDAG traversal (primary rays)", "value": value, "unit": "Grays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
+        "config": {"workload": workload, "scene": "%s 2^%d seed %d" % (SCENE_KIND, args.scene_log2, SCENE_SEED),
+                   "nodes": int(len(nodes)), "dag_mb": round(len(nodes) * 32 / 1e6, 1), "rays_per_step_per_gpu": n_rays,
+                   "l2": "warm (no flush)" if args.no_flush else "flushed between steps (256 MB memset, untimed)",
+                   "hit_fraction": round(hit_fraction, 4), "options": args.option,
+                   "parallelism": "replicated DAG, one frame per GPU" if world > 1 else "single GPU"},
+        "e2e": {"value": e2e_value, "unit": "Grays/s", "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * 40,
+                "ms_per_step": 1e3 * e2e_s, "call": "cbq_trace (pinned host rays -> pinned host hits, 3-stage copy/compute pipeline)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "node_visits_per_ray": visits,
+                     "kernel": "tracePersistent<surface, BufferSource>", "note": "algorithmic bytes = 32 B x V + 24 B ray + 40 B hit; the DAG working set is L2-resident so HBM is not the binding limit (see DESIGN.md)"},
+        "cpu_baseline": {"value": cpu_all, "unit": "Grays/s", "cores": threads, "kind": kind,
+                         "sample": "first %d rays of the same frame, all host threads" % len(cpu_sample),
+                         "single_thread_value": cpu_one, "single_thread_sample": "%d rays (every 8th of the sample)" % len(cpu_one_sample)},
+        "clocks": clocks.summary(),
+        "extra": {"warm_l2_ms_per_step": warm_ms, "warm_l2_value": world * n_rays / (warm_ms * 1e-3) / 1e9,
+                  "step_ms_min": float(np.min(step_ms)), "step_ms_max": float(np.max(step_ms)), "timed_wall_s": wall,
+                  "scene_build_s": build_s, "parity_vs_oracle_sample": parity, "e2e_equals_device_path": bool(same)},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

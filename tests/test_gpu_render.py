@@ -1,0 +1,74 @@
+"""GPU parity of the path tracer (cbq_render) against the oracle's restatement of the bounce loop."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PI_F = float(np.float32(3.14159265358979))
+
+
+def both_cameras(api, port, sc):
+    cam = api.default_camera(sc.lower, sc.upper)
+    ocam = port.camera(list(cam.position), -(PI_F / 4.0), 0.0)
+    assert bytes(cam) == bytes(ocam)
+    return cam, ocam
+
+
+def oracle_params(pyoracle, p):
+    return pyoracle.PtParams(*[getattr(p, f) for f, _ in p._fields_])
+
+
+@pytest.mark.parametrize("kind,size_log2", [("sphere_noise", 8), ("soup", 8)])
+@pytest.mark.parametrize("bounces,spp", [(0, 1), (1, 2), (4, 3)])
+def test_recursive_variant_is_bit_exact(gpu, port, api, scenes, kind, size_log2, bounces, spp):
+    from oracle import pyoracle
+    sc = scenes(kind, size_log2)
+    gpu.upload(sc.nodes, sc.root, sc.colours)
+    cam, ocam = both_cameras(api, port, sc)
+    p = api.pt_params(160, 120, spp=spp, bounces=bounces, variant=api.VARIANT_RECURSIVE, frame_id=7)
+    sd = port.find_subdags(sc.nodes, sc.root)
+    want, _, nrays = port.render(sc.nodes, sd, sc.colours, ocam, oracle_params(pyoracle, p), threads=8)
+    got = gpu.render(cam, p)
+    assert nrays > 160 * 120 * spp
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "max abs diff %g" % np.abs(got - want).max()
+    assert got.std() > 0.05
+
+
+def test_one_bounce_variant_within_gamma_tolerance(gpu, port, api, scenes):
+    """BASELINE config 1: traceSingleRay as used by the reference (pathtracing_demo.cpp:222). Its
+    per-sample powf gamma is not bit-portable; everything before the powf is."""
+    from oracle import pyoracle
+    sc = scenes("sphere_noise", 8)
+    gpu.upload(sc.nodes, sc.root, sc.colours)
+    cam, ocam = both_cameras(api, port, sc)
+    p = api.pt_params(256, 256, spp=2, variant=api.VARIANT_ONE_BOUNCE)
+    sd = port.find_subdags(sc.nodes, sc.root)
+    want, _, _ = port.render(sc.nodes, sd, sc.colours, ocam, oracle_params(pyoracle, p), threads=8)
+    got = gpu.render(cam, p)
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-6)
+    mse = float(((got - want) ** 2).mean())
+    psnr = 10 * np.log10((want.max() ** 2) / max(mse, 1e-30))
+    assert psnr > 100.0
+
+
+def test_flags_tiles_and_accumulation(gpu, port, api, scenes):
+    from oracle import pyoracle
+    sc = scenes("sphere_noise", 7)
+    gpu.upload(sc.nodes, sc.root, sc.colours)
+    cam, ocam = both_cameras(api, port, sc)
+    sd = port.find_subdags(sc.nodes, sc.root)
+    for sun, sky, noise in [(0, 1, 1), (1, 0, 0), (0, 0, 1)]:
+        p = api.pt_params(96, 64, spp=1, bounces=2, variant=1, include_sun=sun, include_sky=sky, add_noise=noise, max_footprint=-1.0)
+        want, _, _ = port.render(sc.nodes, sd, sc.colours, ocam, oracle_params(pyoracle, p), threads=4)
+        assert np.array_equal(gpu.render(cam, p), want)
+    # Tiles: four rectangles rendered separately into one image == the whole frame (tile sharding is exact).
+    w, h = 100, 70
+    whole = gpu.render(cam, api.pt_params(w, h, spp=2, bounces=1, variant=1))
+    pieces = np.zeros_like(whole)
+    for rect in [(0, 0, 37, 41), (37, 0, 100, 41), (0, 41, 64, 70), (64, 41, 100, 70)]:
+        gpu.render(cam, api.pt_params(w, h, spp=2, bounces=1, variant=1, rect=rect), pieces)
+    assert np.array_equal(whole, pieces)
+    # Accumulation: 1 + 1 samples with consecutive frame ids == 2 samples in one call (mImage += pixel).
+    acc = gpu.render(cam, api.pt_params(w, h, spp=1, bounces=1, variant=1, frame_id=0))
+    gpu.render(cam, api.pt_params(w, h, spp=1, bounces=1, variant=1, frame_id=1), acc)
+    assert np.array_equal(acc, whole)

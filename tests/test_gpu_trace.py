@@ -1,0 +1,193 @@
+"""GPU parity: cbq_trace & friends (through the C ABI) against the oracle, bit for bit."""
+import numpy as np
+import pytest
+
+from conftest import assert_hits_identical, mixed_rays
+from cubiquity_b200 import rays as R
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_hits(port, sc, rays, surface, mf, threads=8):
+    sd = port.find_subdags(sc.nodes, sc.root)
+    want, _, _ = port.trace(sc.nodes, sd, rays, surface, mf, threads=threads)
+    return want
+
+
+@pytest.mark.parametrize("kind,size_log2", [("sphere_noise", 8), ("terrain", 9), ("soup", 8), ("city", 11)])
+@pytest.mark.parametrize("surface,mf", [(True, -1.0), (False, -1.0), (True, 0.0035), (False, 0.05)])
+def test_trace_bit_exact(gpu, port, scenes, kind, size_log2, surface, mf):
+    sc = scenes(kind, size_log2)
+    gpu.upload(sc.nodes, sc.root, sc.colours)
+    rays = mixed_rays(sc.lower, sc.upper, 300000, seed=21)
+    got = gpu.intersect_volume(rays, surface, mf)
+    want = oracle_hits(port, sc, rays, surface, mf)
+    assert want["hit"].sum() > 10000
+    assert_hits_identical(got, want, "%s/%d" % (kind, size_log2))
+    # the north-star metric spelled out: voxel + material agreement and relative distance
+    h = want["hit"] == 1
+    assert (R.hit_voxels(got)[h] == R.hit_voxels(want)[h]).all()
+    assert (got["material"][h] == want["material"][h]).all()
+
+
+def test_subdags_on_device_match_oracle(gpu, port, scenes):
+    sc = scenes("terrain", 9)
+    gpu.upload(sc.nodes, sc.root)
+    assert gpu.subdags().tobytes() == port.find_subdags(sc.nodes, sc.root).tobytes()
+    assert np.array_equal(gpu.download_nodes(), sc.nodes)
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 127, 129, (1 << 18) - 1, (1 << 18) + 1, 3 * (1 << 18) + 17])
+def test_ragged_batch_sizes(gpu, port, scenes, n):
+    sc = scenes("sphere_noise", 7)
+    gpu.upload(sc.nodes, sc.root)
+    rays = R.random_rays(n, sc.lower, sc.upper, seed=n, dilate=0.2)
+    got = gpu.intersect_volume(rays, True, -1.0)
+    assert len(got) == n
+    if n:
+        assert_hits_identical(got, oracle_hits(port, sc, rays, True, -1.0), "n=%d" % n)
+
+
+@pytest.mark.parametrize("option,value", [("kernel", 1), ("refill_threshold", 1), ("refill_threshold", 32),
+                                          ("block_threads", 128), ("blocks_per_sm", 2), ("l2_persist", 0)])
+def test_every_kernel_configuration_agrees(gpu, port, scenes, option, value):
+    sc = scenes("terrain", 9)
+    gpu.upload(sc.nodes, sc.root)
+    rays = mixed_rays(sc.lower, sc.upper, 200000, seed=5)
+    want = oracle_hits(port, sc, rays, True, 0.0035)
+    old = gpu.get_option(option)
+    try:
+        gpu.set_option(option, value)
+        assert_hits_identical(gpu.intersect_volume(rays, True, 0.0035), want, "%s=%d" % (option, value))
+    finally:
+        gpu.set_option(option, old)
+
+
+def test_degenerate_rays_are_abandoned_not_hung(gpu, port, scenes):
+    sc = scenes("sphere_noise", 7)
+    gpu.upload(sc.nodes, sc.root)
+    rng = np.random.default_rng(9)
+    rays = R.random_rays(4096, sc.lower, sc.upper, seed=1)
+    rays["o"][:512] = rng.integers(-60, 60, (512, 3)) + 0.5
+    rays["d"][:512] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 512)]
+    rays["d"][512:520] = 0.0                                 # null directions
+    rays["o"][520:528] = np.nan
+    gpu.reset_counters()
+    got = gpu.intersect_volume(rays, True, -1.0)
+    want = oracle_hits(port, sc, rays, True, -1.0, threads=1)
+    assert want["pad"].sum() > 0
+    assert_hits_identical(got, want, "degenerate")
+    assert gpu.counter("abandoned_rays") == int(want["pad"].sum())
+
+
+def test_empty_and_tiny_volumes(gpu, port, api):
+    from cubiquity_b200.dagfile import material_nodes
+    # Empty volume: root is material 0 (Volume::fill, reference storage.cpp:339-342).
+    nodes = material_nodes()
+    gpu.upload(nodes, 0)
+    rays = R.random_rays(1000, [-10] * 3, [10] * 3, seed=2)
+    got = gpu.intersect_volume(rays)
+    assert not got["hit"].any() and not got["status"].any()
+    # One voxel at the origin, built by hand: a chain of 32 nodes.
+    chain = [nodes]
+    child, idx = 7, 256
+    extra = []
+    for h in range(32):
+        n = np.zeros(8, dtype=np.uint32)
+        n[7 if h == 31 else 0] = child       # x,y,z >= 0 at the root; the low corner below it
+        extra.append(n)
+        child = idx
+        idx += 1
+    tiny = np.concatenate([nodes, np.array(extra, dtype=np.uint32)])
+    root = len(tiny) - 1
+    gpu.upload(tiny, root)
+    rays = R.random_rays(20000, [-3] * 3, [3] * 3, seed=3, dilate=0.0)
+    rays["d"] = -rays["o"] / np.linalg.norm(rays["o"], axis=1, keepdims=True)   # aim at the voxel
+    sd = port.find_subdags(tiny, root)
+    want, _, _ = port.trace(tiny, sd, rays, True, -1.0)
+    got = gpu.intersect_volume(rays)
+    assert want["hit"].sum() > 5000 and (want["material"][want["hit"] == 1] == 7).all()
+    assert_hits_identical(got, want, "single voxel")
+
+
+def test_device_pointer_api_and_primary_rays(gpu, port, scenes, api):
+    torch = pytest.importorskip("torch")
+    sc = scenes("terrain", 9)
+    gpu.upload(sc.nodes, sc.root)
+    w, h = 640, 360
+    cam = api.default_camera(sc.lower, sc.upper)
+    ocam = port.camera([cam.position[0], cam.position[1], cam.position[2]], -(float(np.float32(3.14159265358979)) / 4.0), 0.0)
+    assert bytes(cam) == bytes(ocam)
+    want_rays = port.camera_rays(ocam, w, h)
+    d_rays = torch.empty(w * h * 6, dtype=torch.float32, device="cuda")
+    d_hits = torch.empty(w * h * 10, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    gpu.primary_rays_device(cam, w, h, d_rays.data_ptr(), stream)
+    torch.cuda.synchronize()
+    got_rays = d_rays.cpu().numpy().view(api.RAY_DTYPE).reshape(-1)
+    assert got_rays.tobytes() == want_rays.tobytes()           # Camera::rayFromViewportPos, bit for bit
+
+    want = oracle_hits(port, sc, want_rays, True, -1.0)
+    gpu.trace_device(d_rays.data_ptr(), w * h, d_hits.data_ptr(), True, -1.0, stream)
+    torch.cuda.synchronize()
+    got = d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)
+    assert_hits_identical(got, want, "trace_device")
+
+    d_hits.zero_()
+    gpu.raycast_frame_device(cam, w, h, d_hits.data_ptr(), True, -1.0, stream)
+    torch.cuda.synchronize()
+    got = d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)
+    assert_hits_identical(got, want, "raycast_frame_device")
+    assert 0.2 < want["hit"].mean() < 1.0
+
+    # odd image sizes exercise the overhanging 8x4 tiles
+    w2, h2 = 131, 67
+    want2 = oracle_hits(port, sc, port.camera_rays(ocam, w2, h2), False, 0.0035)
+    d2 = torch.zeros(w2 * h2 * 10, dtype=torch.int32, device="cuda")
+    gpu.raycast_frame_device(cam, w2, h2, d2.data_ptr(), False, 0.0035, stream)
+    torch.cuda.synchronize()
+    assert_hits_identical(d2.cpu().numpy().view(api.HIT_DTYPE).reshape(-1), want2, "odd frame")
+
+
+def test_full_size_terrain_4096(gpu, port, api):
+    """BASELINE config 2 at full size: 1080p primary rays against the 4096^3 terrain. The oracle checks a
+    200k-ray sample bit for bit; the whole frame is checked through properties that need no oracle."""
+    torch = pytest.importorskip("torch")
+    sc = api.Scene("terrain", 12, seed=1)
+    gpu.upload(sc.nodes, sc.root, sc.colours)
+    w, h = 1920, 1080
+    cam = api.default_camera(sc.lower, sc.upper)
+    d_hits = torch.zeros(w * h * 10, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    gpu.raycast_frame_device(cam, w, h, d_hits.data_ptr(), True, -1.0, stream)
+    torch.cuda.synchronize()
+    frame = d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)
+
+    ocam = port.camera(list(cam.position), -(float(np.float32(3.14159265358979)) / 4.0), 0.0)
+    rays = port.camera_rays(ocam, w, h)
+    pick = np.random.default_rng(0).choice(w * h, 200000, replace=False)
+    want = oracle_hits(port, sc, rays[pick], True, -1.0)
+    assert_hits_identical(frame[pick], want, "1080p sample")
+
+    # properties over the full frame
+    assert not frame["status"].any()
+    hit = frame["hit"] == 1
+    assert 0.3 < hit.mean() < 1.0
+    # the hit point lies on the ray at the reported distance ...
+    p = rays["o"] + rays["d"] * frame["distance"][:, None]
+    assert np.array_equal(p[hit].astype(np.float32), frame["position"][hit])
+    # ... on a face of an occupied voxel of the scene, whose material is what the closed form says
+    vox = R.hit_voxels(frame[hit])
+    assert (sc.voxels(vox) == frame["material"][hit]).all()
+    # ... entered from empty space (the voxel in front of the face is empty) for rays that start outside
+    front = np.floor(frame["position"][hit].astype(np.float64) + 0.5 * frame["normal"][hit] + 0.5).astype(np.int64)
+    one_axis = (np.abs(frame["normal"][hit]).sum(axis=1) == 1)
+    assert (sc.voxels(front[one_axis]) == 0).all()
+    # the same rays through the buffer path give the same frame
+    host = gpu.intersect_volume(rays, True, -1.0)
+    assert_hits_identical(host, frame, "buffer path vs fused frame path")
+
+    # BASELINE config 3 in miniature: incoherent random rays, also with LOD
+    rnd = R.random_rays(400000, sc.lower, sc.upper, seed=3)
+    for mf in (-1.0, 0.0035):
+        assert_hits_identical(gpu.intersect_volume(rnd, True, mf), oracle_hits(port, sc, rnd, True, mf), "random rays mf=%g" % mf)

@@ -1,0 +1,70 @@
+"""Delta re-upload after runtime edits: cbq_update with the dirty tail only."""
+import numpy as np
+import pytest
+
+from conftest import assert_hits_identical, mixed_rays
+
+pytestmark = pytest.mark.gpu
+
+
+def test_edit_protocol_with_reference_edits(gpu, port, ref, scenes):
+    """The reference's own edit path (viewer.cpp:152-172): checkpoint -> fillBrush -> re-sync."""
+    sc = scenes("sphere_noise", 7)
+    v = ref.volume().load_arrays(sc.nodes, sc.root)
+    gpu.upload(v.nodes(), v.root())
+    rays = mixed_rays(sc.lower, sc.upper, 100000, seed=2)
+    synced = v.shared_end()
+    rng = np.random.default_rng(1)
+    for step in range(4):
+        v.checkpoint()
+        c = rng.uniform(-40, 40, 3)
+        v.fill_sphere(c[0], c[1], c[2], 12.0, 0 if step % 2 == 0 else 5)
+        nodes, root = v.nodes(), v.root()
+        before = gpu.counter("bytes_h2d")
+        gpu.update(nodes, synced, root)
+        sent = gpu.counter("bytes_h2d") - before
+        assert sent == (len(nodes) - synced) * 32 + 512            # the tail + header + 8 sub-DAGs, nothing else
+        assert sent < 0.2 * nodes.nbytes
+        synced = v.shared_end()
+        assert np.array_equal(gpu.download_nodes(), nodes)
+        assert gpu.subdags().tobytes() == port.find_subdags(nodes, root).tobytes()
+        want, _, _ = port.trace(nodes, port.find_subdags(nodes, root), rays, True, -1.0, threads=8)
+        assert_hits_identical(gpu.intersect_volume(rays, True, -1.0), want, "after edit %d" % step)
+    # undo = just a different root over the same array
+    v.undo()
+    gpu.update(v.nodes(), len(v.nodes()), v.root())
+    want, _, _ = port.trace(v.nodes(), port.find_subdags(v.nodes(), v.root()), rays, True, -1.0, threads=8)
+    assert_hits_identical(gpu.intersect_volume(rays, True, -1.0), want, "after undo")
+    # bake relocates everything: full upload
+    v.bake()
+    gpu.upload(v.nodes(), v.root())
+    want, _, _ = port.trace(v.nodes(), port.find_subdags(v.nodes(), v.root()), rays, True, -1.0, threads=8)
+    assert_hits_identical(gpu.intersect_volume(rays, True, -1.0), want, "after bake")
+
+
+def test_update_grows_past_capacity(gpu, port, scenes):
+    sc = scenes("sphere_noise", 6)
+    nodes = sc.nodes.copy()
+    gpu.upload(nodes, sc.root)
+    # Append > capacity worth of (unreachable) nodes plus a new root that is a copy of the old one.
+    extra = np.zeros((200000, 8), dtype=np.uint32)
+    extra[-1] = nodes[sc.root]
+    grown = np.concatenate([nodes, extra])
+    gpu.update(grown, len(nodes), len(grown) - 1)
+    assert gpu.node_count() == len(grown)
+    assert np.array_equal(gpu.download_nodes(0, len(nodes)), nodes)
+    rays = mixed_rays(sc.lower, sc.upper, 50000, seed=4)
+    want, _, _ = port.trace(nodes, port.find_subdags(nodes, sc.root), rays, True, -1.0)
+    assert_hits_identical(gpu.intersect_volume(rays, True, -1.0), want, "grown")
+
+
+def test_update_argument_checks(gpu, api, scenes):
+    sc = scenes("sphere_noise", 6)
+    gpu.upload(sc.nodes, sc.root)
+    with pytest.raises(api.CubiquityError):
+        gpu.update(sc.nodes, len(sc.nodes) + 5, sc.root)
+    bad = sc.nodes.copy()
+    bad[sc.root] = 0xfffffff0
+    with pytest.raises(api.CubiquityError) as e:
+        gpu.update(bad, 256, sc.root)
+    assert e.value.code == api.ERROR_CORRUPT_VOLUME
