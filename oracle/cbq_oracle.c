@@ -631,3 +631,18 @@ double cbqo_render(const uint32_t* nodes, const cbqo_subdag sd[8], const float* 
 	free(jobs); free(tids);
 	return t1 - t0;
 }
+
+
+/* Per-ray trip counts (iterations of the ESVO loop summed over the ray's sub-DAGs): workload-shape
+ * diagnostics for DESIGN.md / the roofline, not used by any parity check. */
+void cbqo_trace_iterations(const uint32_t* nodes, const cbqo_subdag sd[8], const cbqo_ray* rays, uint64_t n,
+	int surf, float maxFootprint, uint32_t* iterations)
+{
+	for (uint64_t i = 0; i < n; i++) {
+		cbqo_stats st;
+		cbqo_hit h;
+		memset(&st, 0, sizeof(st));
+		cbqo_intersect(nodes, sd, &rays[i], surf, maxFootprint, &h, &st);
+		iterations[i] = (uint32_t)st.iterations;
+	}
+}

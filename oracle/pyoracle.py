@@ -161,6 +161,10 @@ class Ref:
         L.ref_intersect_volume.restype = C.c_double
         L.ref_intersect_volume.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_float, C.c_void_p, C.c_int]
         L.ref_trace_ray_ref.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.ref_pt_render.restype = C.c_double
+        L.ref_pt_render.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_float,
+                                    C.c_int, C.c_void_p]
+        L.ref_camera_rays.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p]
         L.ref_bit_mix.restype = C.c_uint64
         L.ref_bit_mix.argtypes = [C.c_uint64]
         L.ref_fnv1a.restype = C.c_uint64
@@ -168,6 +172,34 @@ class Ref:
 
     def volume(self):
         return RefVolume(self)
+
+    def camera_rays(self, position, pitch, yaw, width, height):
+        """Camera::rayFromViewportPos (reference camera.cpp:12-38) for every pixel, cast to float."""
+        pos = np.asarray(position, dtype=np.float64)
+        rays = np.zeros(width * height, dtype=RAY_DTYPE)
+        self.lib.ref_camera_rays(_ptr(pos), float(pitch), float(yaw), int(width), int(height), _ptr(rays))
+        return rays
+
+    def pt_render(self, nodes, root, colours, position, pitch, yaw, params, reseed=True, accum=None):
+        """The reference's own PathtracingDemo::traceSingleRay / traceSingleRayRecurse over a pixel rectangle
+        (oracle/ref_pt_shim.cpp). `params` is a PtParams. Single threaded: the reference's RNG is a global."""
+        from cubiquity_b200.dagfile import write_dag
+        colours = np.ascontiguousarray(colours, dtype=np.float32)
+        pos = np.asarray(position, dtype=np.float64)
+        if accum is None:
+            accum = np.zeros((params.height, params.width, 3), dtype=np.float32)
+        pv = np.array([params.width, params.height, params.spp, params.bounces, params.variant, params.include_sun,
+                       params.include_sky, params.add_noise, params.frame_id, params.x0, params.y0, params.x1, params.y1],
+                      dtype=np.uint32)
+        with tempfile.NamedTemporaryFile(suffix=".dag", delete=False) as f:
+            path = f.name
+        try:
+            write_dag(path, nodes, root)
+            secs = self.lib.ref_pt_render(os.fsencode(path), _ptr(colours), _ptr(pos), float(pitch), float(yaw), _ptr(pv),
+                                          float(params.max_footprint), int(bool(reseed)), _ptr(accum))
+        finally:
+            os.unlink(path)
+        return accum, secs
 
 
 class RefVolume:
