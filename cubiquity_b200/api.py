@@ -131,6 +131,17 @@ def _ptr(a):
     return C.c_void_p(a.ctypes.data) if a is not None else None
 
 
+CUDA_STREAM_LEGACY = 1   # cudaStreamLegacy: the handle that names the default stream explicitly
+
+
+def _stream(stream):
+    """None -> NULL (the context's own stream). 0 is torch's default stream: pass cudaStreamLegacy so the
+    work is really ordered on it (a NULL would select the context's private non-blocking stream)."""
+    if stream is None:
+        return None
+    return C.c_void_p(int(stream) if int(stream) != 0 else CUDA_STREAM_LEGACY)
+
+
 def device_count():
     return int(load_library().cbq_device_count())
 
@@ -294,18 +305,18 @@ class Context:
                      max_footprint=MAX_FOOTPRINT_DISABLED, stream=None):
         flags = TRACE_SURFACE if compute_surface_properties else 0
         _check(self.L.cbq_trace_device(self._h, C.c_void_p(int(d_rays)), int(n), flags, float(max_footprint),
-                                       C.c_void_p(int(d_hits)), C.c_void_p(int(stream)) if stream else None))
+                                       C.c_void_p(int(d_hits)), _stream(stream)))
 
     def primary_rays_device(self, cam, width, height, d_rays, stream=None):
         _check(self.L.cbq_primary_rays_device(self._h, C.byref(cam), int(width), int(height), C.c_void_p(int(d_rays)),
-                                              C.c_void_p(int(stream)) if stream else None))
+                                              _stream(stream)))
 
     def raycast_frame_device(self, cam, width, height, d_hits, compute_surface_properties=True,
                              max_footprint=MAX_FOOTPRINT_DISABLED, stream=None):
         flags = TRACE_SURFACE if compute_surface_properties else 0
         _check(self.L.cbq_raycast_frame_device(self._h, C.byref(cam), int(width), int(height), flags,
                                                float(max_footprint), C.c_void_p(int(d_hits)),
-                                               C.c_void_p(int(stream)) if stream else None))
+                                               _stream(stream)))
 
     # -- path tracer -------------------------------------------------------------------------
     def render(self, cam, params, accum=None):
@@ -318,7 +329,7 @@ class Context:
 
     def render_device(self, cam, params, d_accum, stream=None):
         _check(self.L.cbq_render_device(self._h, C.byref(cam), C.byref(params), C.c_void_p(int(d_accum)),
-                                        C.c_void_p(int(stream)) if stream else None))
+                                        _stream(stream)))
 
     # -- misc --------------------------------------------------------------------------------
     def synchronize(self):

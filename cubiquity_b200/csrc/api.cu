@@ -76,6 +76,17 @@ bool findOneSubDag(const uint32_t* nodes, uint64_t nodeCount, uint32_t root, uin
 	return true;
 }
 
+// Every child index must address a node that exists: the kernels follow them unchecked.
+bool childrenInRange(const uint32_t* nodes, uint64_t begin, uint64_t end, uint64_t nodeCount)
+{
+	const uint32_t limit = (uint32_t)std::min<uint64_t>(nodeCount, 0xffffffffull);
+	uint32_t worst = 0;
+	const uint32_t* p = nodes + begin * 8;
+	const uint64_t words = (end - begin) * 8;
+	for (uint64_t i = 0; i < words; i++) worst = std::max(worst, p[i]);
+	return worst < limit || nodeCount > 0xffffffffull;
+}
+
 bool findSubDags(const uint32_t* nodes, uint64_t nodeCount, uint32_t root, cbq::SubDag out[8])
 {
 	for (uint32_t c = 0; c < 8; c++) if (!findOneSubDag(nodes, nodeCount, root, c, out[c])) return false;
@@ -314,6 +325,8 @@ int cbq_upload(cbq_context* ctx, const uint32_t* nodes, uint64_t node_count, uin
 	int rc = bind(ctx); if (rc) return rc;
 	if (!nodes || node_count < cbq::kMaterialCount) return fail(CBQ_ERROR_INVALID_ARGUMENT, "node array must include the 256 material nodes");
 	if (node_count > 0xffffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "node indices are 32-bit");
+	if (!childrenInRange(nodes, 0, node_count, node_count))
+		return fail(CBQ_ERROR_CORRUPT_VOLUME, "a child index is >= the node count %llu", (unsigned long long)node_count);
 	rc = refreshSubdags(ctx, nodes, node_count, root_index); if (rc) return rc;
 
 	// Head-room for copy-on-write growth so that edits rarely force a reallocation.
@@ -342,6 +355,8 @@ int cbq_update(cbq_context* ctx, const uint32_t* nodes, uint64_t dirty_begin, ui
 	if (!nodes || node_count < cbq::kMaterialCount || dirty_begin > node_count) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad dirty range");
 	if (dirty_begin > ctx->nodeCount) return fail(CBQ_ERROR_INVALID_ARGUMENT, "dirty_begin %llu is past the %llu nodes on the device", (unsigned long long)dirty_begin, (unsigned long long)ctx->nodeCount);
 	if (node_count > 0xffffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "node indices are 32-bit");
+	if (!childrenInRange(nodes, dirty_begin, node_count, node_count))
+		return fail(CBQ_ERROR_CORRUPT_VOLUME, "a child index in the dirty tail is >= the node count %llu", (unsigned long long)node_count);
 	rc = refreshSubdags(ctx, nodes, node_count, root_index); if (rc) return rc;
 	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
 	if (node_count > ctx->nodeCapacity) {

@@ -274,8 +274,8 @@ renderPersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict
 			if (s.phase == kPhaseIdle) continue;
 			Hit out;
 			StepResult res;
-			if (s.phase == kPhaseOctant) res = stepOctant(s, subdags);
-			else res = stepEsvo(s, nodes, stack, p.max_footprint, t.kind == kKindSurface, out);
+			if (s.phase == kPhaseOctant) res = stepOctant2(s, subdags);
+			else res = stepEsvo2<false>(s, nodes, stack, p.max_footprint, t.kind == kKindSurface, out);
 			if (res == kStepContinue) continue;
 
 			const bool hit = (res == kStepHit);

@@ -27,7 +27,7 @@ namespace cbq {
 namespace {
 
 constexpr unsigned kFullMask = 0xffffffffu;
-constexpr int kChunk = 128;           // rays claimed per atomic ticket
+constexpr int kChunk = 32;            // rays claimed per atomic ticket (small: ~14 claims per warp per frame keeps the tail short)
 constexpr int kStepsPerRound = 8;     // traversal steps between two refill votes
 
 struct GlobalNodes {
@@ -122,7 +122,7 @@ struct CameraSource {
 	}
 };
 
-template <bool kSurface, typename Source>
+template <bool kSurface, bool kLodOff, typename Source>
 __global__ void __launch_bounds__(256, 4)
 tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict__ subdagsGlobal, Source source,
 	Hit* __restrict__ hits, uint64_t count, float maxFootprint, int refillThreshold,
@@ -185,8 +185,8 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 			if (s.phase == kPhaseIdle) continue;
 			Hit out;
 			StepResult res;
-			if (s.phase == kPhaseOctant) res = stepOctant(s, subdags);
-			else res = stepEsvo(s, nodes, stack, maxFootprint, kSurface, out);
+			if (s.phase == kPhaseOctant) res = stepOctant2(s, subdags);
+			else res = stepEsvo2<kLodOff>(s, nodes, stack, maxFootprint, kSurface, out);
 			if (res != kStepContinue) {
 				if (res == kStepHit) {
 					if (!kSurface) { out.material = 0; out.normal[0] = out.normal[1] = out.normal[2] = 0.0f; }
@@ -238,10 +238,10 @@ primaryRays(cbq_camera cam, uint32_t width, uint32_t height, Ray* __restrict__ r
 	}
 }
 
-template <bool kSurface, typename Source>
-cudaError_t launchPersistent(const TraceArgs& a, const Source& src, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
+template <bool kSurface, bool kLodOff, typename Source>
+cudaError_t launchPersistentImpl(const TraceArgs& a, const Source& src, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
 {
-	auto kernel = tracePersistent<kSurface, Source>;
+	auto kernel = tracePersistent<kSurface, kLodOff, Source>;
 	const size_t smem = (size_t)cfg.stackLevels * (size_t)cfg.blockThreads * sizeof(uint32_t);
 	cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
@@ -251,6 +251,14 @@ cudaError_t launchPersistent(const TraceArgs& a, const Source& src, uint64_t tic
 	kernel<<<grid, cfg.blockThreads, smem, stream>>>(a.nodes, a.subdags, src, a.hits, tickets, a.maxFootprint,
 		cfg.refillThreshold, a.queue, a.abandoned);
 	return cudaGetLastError();
+}
+
+template <bool kSurface, typename Source>
+cudaError_t launchPersistent(const TraceArgs& a, const Source& src, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
+{
+	// maxFootprint == -1 exactly (MAX_FOOTPRINT_DISABLED) selects the division-free LOD test.
+	if (a.maxFootprint == CBQ_MAX_FOOTPRINT_DISABLED) return launchPersistentImpl<kSurface, true>(a, src, tickets, cfg, stream);
+	return launchPersistentImpl<kSurface, false>(a, src, tickets, cfg, stream);
 }
 
 } // namespace

@@ -23,6 +23,7 @@
 
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define CBQ_HD __host__ __device__ __forceinline__
@@ -105,6 +106,10 @@ struct RayState {
 	float lastExit;
 	uint32_t trips;
 	int phase;
+	// V2 only: t-values of the current child's lower (L) and upper (U) planes, i.e. exactly the
+	// childT0 / childT1 of raytracing.cpp:259,270 for the current childPos, carried between steps.
+	float Lx, Ly, Lz;
+	float Ux, Uy, Uz;
 };
 
 template <typename Nodes>
@@ -301,6 +306,184 @@ CBQ_HD StepResult stepEsvo(RayState& s, const Nodes& nodes, Stack& stack, float 
 	return kStepContinue;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// V2 of the step functions: the same traversal, bit for bit, with far fewer instructions per step.
+//
+// The reference recomputes childT1 = (float(childPos + size) - o) * inv on every trip and childT0,
+// plus the mid-plane times of findFirstChild, whenever a child is occupied (raytracing.cpp:259,270,181).
+// Every one of those is a pure function of ONE integer plane coordinate, so a value computed once
+// for a plane is bit-identical to any later recomputation for the same plane. V2 therefore carries
+// the current child's lower/upper plane times (L, U) in registers and derives the next child's by
+// SELECTION:
+//   descend into sub-child bit b:  (L', U') = b ? (M, U) : (L, M)     (M = centre-plane times)
+//   advance across a flipped axis: L' = U, U' = time of the next plane  (one new plane per flip)
+//   pop:                           recompute both from the integers
+// An advance costs no multiplies for un-flipped axes and a descend three plane evaluations instead
+// of nine. The LOD test `float(size) / tExit > maxFootprint` keeps its IEEE division except when
+// maxFootprint is exactly -1 (MAX_FOOTPRINT_DISABLED, raytracing.h:71), where the quotient's
+// comparison with -1 is decided exactly by comparing |tExit| with size (see lodOffTest).
+// tests/test_host_core.py checks V2 against the oracle on the host; the GPU tests do so on device.
+
+CBQ_HD uint32_t floatBits(float f)
+{
+#if defined(__CUDA_ARCH__)
+	return __float_as_uint(f);
+#else
+	uint32_t u; memcpy(&u, &f, sizeof(u)); return u;
+#endif
+}
+
+CBQ_HD float planeT(int plane, float o, float inv) { return ((float)plane - o) * inv; }
+
+// Exact value of `((float)size / t) > -1.0f` for size = 2^k > 0 without dividing:
+//   t > 0 or t == +0  -> quotient >= +0 or +inf          -> true
+//   t == -0           -> -inf                            -> false
+//   t < 0             -> RN(size / t) > -1  <=>  |t| > size   (size is a power of two, so the only
+//                        float quotients that round to <= -1 are those with |t| <= size)
+//   NaN               -> false
+CBQ_HD bool lodOffTest(float t, int size)
+{
+	return (t > 0.0f) || (floatBits(t) == 0u) || ((-t) > (float)size);
+}
+
+// stepOctant for V2: identical control flow, additionally leaves L/U of the first child in `s`.
+CBQ_HD StepResult stepOctant2(RayState& s, const SubDag* subdags)
+{
+	if (++s.octantTrips > 8) return kStepAbandoned;
+	const SubDag& sd = subdags[(uint32_t)s.octant ^ s.signBits];
+	if (sd.node > 0) {
+		const int h = sd.height;
+		const uint32_t sizeU = 1u << h;
+		const uint32_t nx = s.signBits & 1u, ny = (s.signBits >> 1) & 1u, nz = (s.signBits >> 2) & 1u;
+		const int lx = (int)((nx ? (0u - (uint32_t)sd.lower[0]) : (uint32_t)sd.lower[0]) - nx * sizeU);
+		const int ly = (int)((ny ? (0u - (uint32_t)sd.lower[1]) : (uint32_t)sd.lower[1]) - ny * sizeU);
+		const int lz = (int)((nz ? (0u - (uint32_t)sd.lower[2]) : (uint32_t)sd.lower[2]) - nz * sizeU);
+		const float fsz = (float)sizeU;
+		const float flx = (float)lx, fly = (float)ly, flz = (float)lz;
+		const float t0x = (flx - s.ox) * s.ix, t0y = (fly - s.oy) * s.iy, t0z = (flz - s.oz) * s.iz;
+		const float t1x = ((flx + fsz) - s.ox) * s.ix, t1y = ((fly + fsz) - s.oy) * s.iy, t1z = ((flz + fsz) - s.oz) * s.iz;
+		const float entry = max3(t0x, t0y, t0z);
+		const float exit = min3(t1x, t1y, t1z);
+		if (entry < exit) {
+			s.startHeight = h;
+			s.height = h;
+			s.node = sd.node;
+			const uint32_t half = sizeU / 2;
+			s.childSize = (int)half;
+			const int cx = (int)((uint32_t)lx + half), cy = (int)((uint32_t)ly + half), cz = (int)((uint32_t)lz + half);
+			const float fx = (float)cx, fy = (float)cy, fz = (float)cz;
+			const float mx = (fx - s.ox) * s.ix, my = (fy - s.oy) * s.iy, mz = (fz - s.oz) * s.iz;
+			bool bx = mx < entry, by = my < entry, bz = mz < entry;
+			if (entry <= 0.0f) { bx |= (s.ox >= fx); by |= (s.oy >= fy); bz |= (s.oz >= fz); }
+			// The far planes of the upper children are float(int(l + half + half)), which is what the loop's
+			// childT1 would compute -- NOT the slab test's float(l) + float(size) above.
+			const float ux = planeT((int)((uint32_t)cx + half), s.ox, s.ix);
+			const float uy = planeT((int)((uint32_t)cy + half), s.oy, s.iy);
+			const float uz = planeT((int)((uint32_t)cz + half), s.oz, s.iz);
+			s.px = bx ? cx : lx; s.py = by ? cy : ly; s.pz = bz ? cz : lz;
+			s.Lx = bx ? mx : t0x; s.Ly = by ? my : t0y; s.Lz = bz ? mz : t0z;
+			s.Ux = bx ? ux : mx; s.Uy = by ? uy : my; s.Uz = bz ? uz : mz;
+			s.idBits = (bx ? 1u : 0u) | (by ? 2u : 0u) | (bz ? 4u : 0u);
+			s.lastExit = exit;
+			s.trips = iterationCap(h);      // counts DOWN in V2
+			s.phase = kPhaseEsvo;
+			return kStepContinue;
+		}
+	}
+	const float nearest = min3(s.dx, s.dy, s.dz);
+	if (s.dx <= nearest) { s.octant += 1; s.dx += kFltMax; }
+	if (s.dy <= nearest) { s.octant += 2; s.dy += kFltMax; }
+	if (s.dz <= nearest) { s.octant += 4; s.dz += kFltMax; }
+	return (s.octant <= 7) ? kStepContinue : kStepMiss;
+}
+
+template <bool kLodOff, typename Nodes, typename Stack>
+CBQ_HD StepResult stepEsvo2(RayState& s, const Nodes& nodes, Stack& stack, float maxFootprint, const bool kSurface, Hit& out)
+{
+	if (s.trips == 0u) return kStepAbandoned;
+	s.trips--;
+
+	const float tExit = min3(s.Ux, s.Uy, s.Uz);
+	const uint32_t child = nodes.child(s.node, s.idBits ^ s.signBits);
+
+	if (child > 0) {
+		const float tEntry = max3(s.Lx, s.Ly, s.Lz);
+		const bool internal = child >= kMaterialCount;
+		const bool bigEnough = kLodOff ? lodOffTest(tExit, s.childSize) : (((float)s.childSize / tExit) > maxFootprint);
+		if (internal && bigEnough) {
+			// PUSH (raytracing.cpp:279-301)
+			if (tExit < s.lastExit) stack.store(s.height, s.node);
+			s.lastExit = tExit;
+			s.height--;
+			s.node = child;
+			const uint32_t half = (uint32_t)s.childSize >> 1;   // childSize > 0, so >> 1 == / 2
+			s.childSize = (int)half;
+			const int cx = (int)((uint32_t)s.px + half), cy = (int)((uint32_t)s.py + half), cz = (int)((uint32_t)s.pz + half);
+			const float fx = (float)cx, fy = (float)cy, fz = (float)cz;
+			const float mx = (fx - s.ox) * s.ix, my = (fy - s.oy) * s.iy, mz = (fz - s.oz) * s.iz;
+			bool bx = mx < tEntry, by = my < tEntry, bz = mz < tEntry;
+			if (tEntry <= 0.0f) { bx |= (s.ox >= fx); by |= (s.oy >= fy); bz |= (s.oz >= fz); }
+			s.px = bx ? cx : s.px; s.py = by ? cy : s.py; s.pz = bz ? cz : s.pz;
+			s.Lx = bx ? mx : s.Lx; s.Ly = by ? my : s.Ly; s.Lz = bz ? mz : s.Lz;
+			s.Ux = bx ? s.Ux : mx; s.Uy = by ? s.Uy : my; s.Uz = bz ? s.Uz : mz;
+			s.idBits = (bx ? 1u : 0u) | (by ? 2u : 0u) | (bz ? 4u : 0u);
+			return kStepContinue;
+		}
+		// HIT (raytracing.cpp:302-320)
+		out.hit = 1;
+		out.distance = tEntry;
+		if (kSurface) {
+			out.material = nearestMaterial(nodes, child, s.signBits);
+			if (out.material == kNoMaterial) return kStepAbandoned;
+			const float sx = (s.signBits & 1u) ? -1.0f : 1.0f, sy = (s.signBits & 2u) ? -1.0f : 1.0f, sz = (s.signBits & 4u) ? -1.0f : 1.0f;
+			out.normal[0] = ((tEntry == s.Lx) ? 1.0f : 0.0f) * (-sx);
+			out.normal[1] = ((tEntry == s.Ly) ? 1.0f : 0.0f) * (-sy);
+			out.normal[2] = ((tEntry == s.Lz) ? 1.0f : 0.0f) * (-sz);
+		}
+		return kStepHit;
+	}
+
+	// ADVANCE (raytracing.cpp:325-332)
+	const bool fx = s.Ux <= tExit, fy = s.Uy <= tExit, fz = s.Uz <= tExit;
+	const uint32_t flips = (fx ? 1u : 0u) | (fy ? 2u : 0u) | (fz ? 4u : 0u);
+	const uint32_t newId = s.idBits ^ flips;
+	const uint32_t cs = (uint32_t)s.childSize;
+	const int oldx = s.px, oldy = s.py, oldz = s.pz;
+	s.px = (int)((uint32_t)s.px + (fx ? cs : 0u));
+	s.py = (int)((uint32_t)s.py + (fy ? cs : 0u));
+	s.pz = (int)((uint32_t)s.pz + (fz ? cs : 0u));
+	s.idBits = newId;
+	if ((newId & flips) == flips) {
+		// Stayed inside the parent: a flipped axis' old upper plane is its new lower plane.
+		const float nx = planeT((int)((uint32_t)s.px + cs), s.ox, s.ix);
+		const float ny = planeT((int)((uint32_t)s.py + cs), s.oy, s.iy);
+		const float nz = planeT((int)((uint32_t)s.pz + cs), s.oz, s.iz);
+		s.Lx = fx ? s.Ux : s.Lx; s.Ly = fy ? s.Uy : s.Ly; s.Lz = fz ? s.Uz : s.Lz;
+		s.Ux = fx ? nx : s.Ux; s.Uy = fy ? ny : s.Uy; s.Uz = fz ? nz : s.Uz;
+		return kStepContinue;
+	}
+	// POP (raytracing.cpp:339-364)
+	const uint32_t diff = (uint32_t)(oldx ^ s.px) | (uint32_t)(oldy ^ s.py) | (uint32_t)(oldz ^ s.pz);
+	const int msb = findMsb(diff);
+	s.height = msb + 1;
+	if (s.height > s.startHeight) return leaveSubDag(s);
+	s.node = stack.load(s.height);
+	const uint32_t big = 1u << msb;
+	s.childSize = (int)big;
+	const uint32_t bx = ((uint32_t)(s.px >> msb)) & 1u, by = ((uint32_t)(s.py >> msb)) & 1u, bz = ((uint32_t)(s.pz >> msb)) & 1u;
+	s.idBits = bx | (by << 1) | (bz << 2);
+	s.px = (int)((((uint32_t)(s.px >> s.height)) << s.height) + (bx ? big : 0u));
+	s.py = (int)((((uint32_t)(s.py >> s.height)) << s.height) + (by ? big : 0u));
+	s.pz = (int)((((uint32_t)(s.pz >> s.height)) << s.height) + (bz ? big : 0u));
+	s.lastExit = 0.0f;
+	s.Lx = planeT(s.px, s.ox, s.ix); s.Ly = planeT(s.py, s.oy, s.iy); s.Lz = planeT(s.pz, s.oz, s.iz);
+	s.Ux = planeT((int)((uint32_t)s.px + big), s.ox, s.ix);
+	s.Uy = planeT((int)((uint32_t)s.py + big), s.oy, s.iy);
+	s.Uz = planeT((int)((uint32_t)s.pz + big), s.oz, s.iz);
+	return kStepContinue;
+}
+
 // Fill in the fields intersectVolume adds after a hit (raytracing.cpp:463-466).
 CBQ_HD void finishHit(Hit& out, const Ray& r)
 {
@@ -335,5 +518,24 @@ CBQ_HD void traceRay(const Ray& r, const Nodes& nodes, const SubDag* subdags, St
 		return; // miss
 	}
 }
+
+// Whole ray with the V2 steps.
+template <bool kLodOff, typename Nodes, typename Stack>
+CBQ_HD void traceRay2(const Ray& r, const Nodes& nodes, const SubDag* subdags, Stack& stack, float maxFootprint, const bool kSurface, Hit& out)
+{
+	clearHit(out);
+	RayState s;
+	beginRay(s, r);
+	for (;;) {
+		StepResult res;
+		if (s.phase == kPhaseOctant) res = stepOctant2(s, subdags);
+		else res = stepEsvo2<kLodOff>(s, nodes, stack, maxFootprint, kSurface, out);
+		if (res == kStepContinue) continue;
+		if (res == kStepHit) { finishHit(out, r); return; }
+		if (res == kStepAbandoned) { clearHit(out); out.status = 1; return; }
+		return;
+	}
+}
+
 
 } // namespace cbq

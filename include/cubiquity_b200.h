@@ -145,7 +145,8 @@ int cbq_node_count(cbq_context* ctx, uint64_t* out);
 int cbq_trace(cbq_context* ctx, const cbq_ray* rays, uint64_t n, uint32_t flags, float max_footprint,
               cbq_hit* hits);
 
-/* Same with device pointers, enqueued on `stream` (a cudaStream_t; NULL = the context's stream). */
+/* Same with device pointers, enqueued on `stream` (a cudaStream_t). NULL selects the context's own
+ * non-blocking stream; to order the work on the CUDA default stream pass cudaStreamLegacy. */
 int cbq_trace_device(cbq_context* ctx, const cbq_ray* d_rays, uint64_t n, uint32_t flags,
                      float max_footprint, cbq_hit* d_hits, void* stream);
 

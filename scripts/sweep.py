@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Kernel-time sweep over launch options on the bench workload (1080p primary rays, 4096^3 terrain).
+Prints one line per configuration: cold-L2 and warm-L2 ms per frame and Grays/s. Development aid."""
+import itertools
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from cubiquity_b200 import api  # noqa: E402
+from cubiquity_b200 import rays as R  # noqa: E402
+
+W, H = 1920, 1080
+PI_F = float(np.float32(3.14159265358979))
+
+
+def time_config(ctx, d_rays, n, d_hits, flush, stream, steps=10, mf=-1.0, surface=True):
+    def step():
+        ctx.trace_device(d_rays.data_ptr(), n, d_hits.data_ptr(), surface, mf, stream)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    cold = []
+    for _ in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step(); b.record()
+        torch.cuda.synchronize()
+        cold.append(a.elapsed_time(b))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    return float(np.mean(cold)), a.elapsed_time(b) / steps
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "primary"
+    scene = api.Scene("terrain", 12, 1)
+    ctx = api.Context(0)
+    ctx.upload(scene.nodes, scene.root, scene.colours)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream().cuda_stream
+    if what == "random":
+        n = 8_000_000
+        host = R.random_rays(n, scene.lower, scene.upper, seed=100)
+        d_rays = torch.from_numpy(host.view(np.float32).reshape(-1)).to(dev)
+    else:
+        n = W * H
+        cam = api.default_camera(scene.lower, scene.upper)
+        d_rays = torch.empty(n * 6, dtype=torch.float32, device=dev)
+        ctx.primary_rays_device(cam, W, H, d_rays.data_ptr(), stream)
+    d_hits = torch.zeros(n * 10, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    grid = {
+        "refill_threshold": [1, 4, 8, 16, 32],
+        "blocks_per_sm": [4],
+        "block_threads": [256, 128],
+        "l2_persist": [1],
+    }
+    if len(sys.argv) > 2:
+        grid = json.loads(sys.argv[2])
+    keys = list(grid)
+    for combo in itertools.product(*[grid[k] for k in keys]):
+        for k, v in zip(keys, combo):
+            ctx.set_option(k, v)
+        for mf in (-1.0, 0.0035):
+            cold, warm = time_config(ctx, d_rays, n, d_hits, flush, stream, mf=mf)
+            print(json.dumps({"workload": what, **dict(zip(keys, combo)), "max_footprint": mf, "cold_ms": round(cold, 4), "warm_ms": round(warm, 4),
+                              "cold_grays": round(n / cold / 1e6, 3), "warm_grays": round(n / warm / 1e6, 3)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

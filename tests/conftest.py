@@ -65,12 +65,14 @@ def hostcore():
                         "-o", so, src], check=True)
     lib = C.CDLL(so)
     lib.host_core_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_float, C.c_void_p]
+    lib.host_core_trace_v2.argtypes = lib.host_core_trace.argtypes
 
-    def trace(nodes, subdags, rays, surface=True, max_footprint=-1.0):
+    def trace(nodes, subdags, rays, surface=True, max_footprint=-1.0, version=2):
         nodes = np.ascontiguousarray(nodes, dtype=np.uint32)
         rays = np.ascontiguousarray(rays, dtype=pyoracle.RAY_DTYPE)
         hits = np.zeros(len(rays), dtype=pyoracle.HIT_DTYPE)
-        lib.host_core_trace(nodes.ctypes.data, subdags.ctypes.data, rays.ctypes.data, len(rays), int(surface),
+        fn = lib.host_core_trace_v2 if version == 2 else lib.host_core_trace
+        fn(nodes.ctypes.data, subdags.ctypes.data, rays.ctypes.data, len(rays), int(surface),
                             float(max_footprint), hits.ctypes.data)
         return hits
     return trace
@@ -118,13 +120,22 @@ def mixed_rays(lower, upper, n, seed):
     return rays
 
 
-def assert_hits_identical(a, b, what=""):
-    """Bit equality of every field (the primary comparison)."""
+def assert_hits_identical(a, b, what="", nan_payload_insensitive=False):
+    """Bit equality of every field (the primary comparison). With nan_payload_insensitive the
+    sign/payload bits of NaNs are ignored (x86 and the GPU generate different default NaNs; only rays fed
+    NaN or 0/0 inputs ever produce them)."""
     assert a.dtype.itemsize == b.dtype.itemsize == 40 and len(a) == len(b)
     if a.tobytes() == b.tobytes():
         return
-    av = a.view(np.uint32).reshape(-1, 10)
-    bv = b.view(np.uint32).reshape(-1, 10)
+    av = a.view(np.uint32).reshape(-1, 10).copy()
+    bv = b.view(np.uint32).reshape(-1, 10).copy()
+    if nan_payload_insensitive:
+        for v in (av, bv):
+            f = v[:, [1, 3, 4, 5, 6, 7, 8]]
+            f[(f & 0x7fffffff) > 0x7f800000] = 0x7fc00000
+            v[:, [1, 3, 4, 5, 6, 7, 8]] = f
+        if (av == bv).all():
+            return
     bad = np.nonzero((av != bv).any(axis=1))[0]
     raise AssertionError("%s: %d of %d hit records differ, first at %d:\n  %r\n  %r"
                          % (what, len(bad), len(a), bad[0], a[bad[0]], b[bad[0]]))

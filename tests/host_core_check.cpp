@@ -33,3 +33,20 @@ extern "C" void host_core_trace(const uint32_t* nodes, const void* subdags, cons
 		else cbq::traceRay<false>(r[i], hn, sd, st, maxFootprint, h[i]);
 	}
 }
+
+// The V2 step functions (carried plane times, division-free LOD-off test).
+extern "C" void host_core_trace_v2(const uint32_t* nodes, const void* subdags, const void* rays, uint64_t n,
+	int surface, float maxFootprint, void* hits)
+{
+	const cbq::Ray* r = static_cast<const cbq::Ray*>(rays);
+	cbq::Hit* h = static_cast<cbq::Hit*>(hits);
+	const cbq::SubDag* sd = static_cast<const cbq::SubDag*>(subdags);
+	HostNodes hn{ nodes };
+	const bool lodOff = (maxFootprint == -1.0f);
+	for (uint64_t i = 0; i < n; i++) {
+		HostStack st;
+		std::memset(&st, 0, sizeof(st));
+		if (lodOff) cbq::traceRay2<true>(r[i], hn, sd, st, maxFootprint, surface != 0, h[i]);
+		else cbq::traceRay2<false>(r[i], hn, sd, st, maxFootprint, surface != 0, h[i]);
+	}
+}

@@ -11,12 +11,13 @@ from conftest import assert_hits_identical, mixed_rays
 
 @pytest.mark.parametrize("kind,size_log2", [("sphere_noise", 7), ("terrain", 8), ("soup", 7), ("city", 10)])
 @pytest.mark.parametrize("surface,max_footprint", [(True, -1.0), (False, -1.0), (True, 0.0035), (True, 0.05)])
-def test_core_matches_oracle(port, hostcore, scenes, kind, size_log2, surface, max_footprint):
+@pytest.mark.parametrize("version", [1, 2])
+def test_core_matches_oracle(port, hostcore, scenes, kind, size_log2, surface, max_footprint, version):
     sc = scenes(kind, size_log2)
     sd = port.find_subdags(sc.nodes, sc.root)
     rays = mixed_rays(sc.lower, sc.upper, 40000, seed=11)
     want, _, _ = port.trace(sc.nodes, sd, rays, surface, max_footprint)
-    got = hostcore(sc.nodes, sd, rays, surface, max_footprint)
+    got = hostcore(sc.nodes, sd, rays, surface, max_footprint, version=version)
     assert want["hit"].sum() > 1000
     assert_hits_identical(got, want, "%s %d" % (kind, size_log2))
 
@@ -29,6 +30,7 @@ def test_core_abandons_the_same_rays(port, hostcore, scenes):
     rays["o"] = rng.integers(-30, 30, (256, 3)) + 0.5       # on cell boundaries ...
     rays["d"] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 256)]   # ... with zero components
     want, _, _ = port.trace(sc.nodes, sd, rays, True, -1.0)
-    got = hostcore(sc.nodes, sd, rays, True, -1.0)
     assert want["pad"].sum() > 0
+    assert_hits_identical(hostcore(sc.nodes, sd, rays, True, -1.0, version=1), want, "degenerate v1")
+    got = hostcore(sc.nodes, sd, rays, True, -1.0, version=2)
     assert_hits_identical(got, want, "degenerate")
