@@ -277,7 +277,7 @@ int cbq_create(int device, cbq_context** out)
 	ctx->cfg.blockThreads = 256;
 	ctx->cfg.blocksPerSm = 4;
 	ctx->cfg.smCount = ctx->prop.multiProcessorCount;
-	ctx->cfg.refillThreshold = 8;
+	ctx->cfg.refillThreshold = 32;   // measured best for coherent rays (profiles/r01_sweeps.md)
 	ctx->cfg.kernel = 0;
 	ctx->cfg.stackLevels = 33;
 	*out = ctx;

@@ -43,11 +43,13 @@ struct GlobalNodes {
 	}
 };
 
-struct SharedStack {
+struct SharedStack {   // see trace_kernels.cu
 	uint32_t* column;
 	uint32_t stride;
-	__device__ __forceinline__ void store(int h, uint32_t n) { column[(uint32_t)h * stride] = n; }
-	__device__ __forceinline__ uint32_t load(int h) const { return column[(uint32_t)h * stride]; }
+	uint32_t written;
+	__device__ __forceinline__ void store(int h, uint32_t n) { column[(uint32_t)h * stride] = n; written |= 1u << h; }
+	__device__ __forceinline__ uint32_t load(int h) const { return ((written >> h) & 1u) ? column[(uint32_t)h * stride] : 0u; }
+	__device__ __forceinline__ void reset() { written = 0u; }
 };
 
 __device__ __forceinline__ uint64_t bitMix64(uint64_t b)   // base.cpp:72-77
@@ -130,7 +132,7 @@ renderPersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict
 	__syncthreads();
 
 	const GlobalNodes nodes{ nodeBase };
-	SharedStack stack{ stackMem + threadIdx.x, blockDim.x };
+	SharedStack stack{ stackMem + threadIdx.x, blockDim.x, 0u };
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lowerLanes = (1u << lane) - 1u;
 	uint64_t chunkNext = 0, chunkEnd = 0;   // warp-uniform window of claimed tickets
@@ -274,7 +276,7 @@ renderPersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict
 			if (s.phase == kPhaseIdle) continue;
 			Hit out;
 			StepResult res;
-			if (s.phase == kPhaseOctant) res = stepOctant2(s, subdags);
+			if (s.phase == kPhaseOctant) { stack.reset(); res = stepOctant2(s, subdags); }
 			else res = stepEsvo2<false>(s, nodes, stack, p.max_footprint, t.kind == kKindSurface, out);
 			if (res == kStepContinue) continue;
 

@@ -38,11 +38,18 @@ struct GlobalNodes {
 	}
 };
 
-struct SharedStack {          // one column of a [levels][blockDim.x] array
+// One column of a [levels][blockDim.x] array in shared memory. `written` has one bit per level that
+// has been stored to since the current sub-DAG was entered: a pop to a level that was never pushed
+// (only possible when NaNs defeat the `tExit < lastExit` guard, raytracing.cpp:285) then reads 0, the
+// value the oracle's zero-initialised array holds, instead of whatever an earlier ray left behind.
+// (The reference's own array is uninitialised there, raytracing.cpp:251.)
+struct SharedStack {
 	uint32_t* column;
 	uint32_t stride;
-	__device__ __forceinline__ void store(int h, uint32_t n) { column[(uint32_t)h * stride] = n; }
-	__device__ __forceinline__ uint32_t load(int h) const { return column[(uint32_t)h * stride]; }
+	uint32_t written;
+	__device__ __forceinline__ void store(int h, uint32_t n) { column[(uint32_t)h * stride] = n; written |= 1u << h; }
+	__device__ __forceinline__ uint32_t load(int h) const { return ((written >> h) & 1u) ? column[(uint32_t)h * stride] : 0u; }
+	__device__ __forceinline__ void reset() { written = 0u; }
 };
 
 struct LocalStack {
@@ -134,7 +141,7 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 	__syncthreads();
 
 	const GlobalNodes nodes{ nodeBase };
-	SharedStack stack{ stackMem + threadIdx.x, blockDim.x };
+	SharedStack stack{ stackMem + threadIdx.x, blockDim.x, 0u };
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lowerLanes = (1u << lane) - 1u;
 
@@ -185,7 +192,7 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 			if (s.phase == kPhaseIdle) continue;
 			Hit out;
 			StepResult res;
-			if (s.phase == kPhaseOctant) res = stepOctant2(s, subdags);
+			if (s.phase == kPhaseOctant) { stack.reset(); res = stepOctant2(s, subdags); }
 			else res = stepEsvo2<kLodOff>(s, nodes, stack, maxFootprint, kSurface, out);
 			if (res != kStepContinue) {
 				if (res == kStepHit) {

@@ -85,6 +85,12 @@ void cbqo_find_subdags(const uint32_t* nodes, uint32_t root, cbqo_subdag out[8])
 	for (uint32_t c = 0; c < 8; c++) find_one_subdag(nodes, root, c, &out[c]); /* raytracing.cpp:89-97 */
 }
 
+/* Diagnostics only (single threaded): when non-NULL, every ESVO trip appends one event byte:
+ * 'D' descend, 'A' advance within the parent, 'P' advance that pops, 'H' hit, 'O' sub-DAG entered. */
+static uint8_t* g_events = NULL;
+static uint32_t g_eventCount = 0, g_eventCap = 0;
+static inline void record_event(uint8_t e) { if (g_events && g_eventCount < g_eventCap) g_events[g_eventCount++] = e; }
+
 /* ---------------------------------------------------------------- ray cast */
 
 static uint32_t nearest_material(const uint32_t* nodes, uint32_t node, uint32_t signBits, cbqo_stats* st)
@@ -136,6 +142,7 @@ static int esvo_node(const uint32_t* nodes, uint32_t node, const int32_t nodePos
 	const float nodeExit = least3(t1);
 	if (!(nodeEntry < nodeExit)) return 0;
 	if (st) st->subdag_entries++;
+	record_event('O');
 
 	const int startHeight = nodeHeight;
 	int32_t childSize = (int32_t)(nodeSize / 2);
@@ -177,6 +184,7 @@ static int esvo_node(const uint32_t* nodes, uint32_t node, const int32_t nodePos
 			const int bigEnough = ((float)childSize / tExit) > maxFootprint;
 			if (internal && bigEnough) {
 				if (st) st->descents++;
+				record_event('D');
 				if (tExit < lastExit) stack[nodeHeight] = node;
 				lastExit = tExit;
 				nodeHeight--;
@@ -187,6 +195,7 @@ static int esvo_node(const uint32_t* nodes, uint32_t node, const int32_t nodePos
 				for (int a = 0; a < 3; a++) pos[a] = (int32_t)((uint32_t)pos[a] + (uint32_t)(id[a] * childSize));
 			} else {
 				found = 1;
+				record_event('H');
 				hit->hit = 1;
 				hit->distance = tEntry;
 				if (surf) {
@@ -208,6 +217,7 @@ static int esvo_node(const uint32_t* nodes, uint32_t node, const int32_t nodePos
 				pos[a] = (int32_t)((uint32_t)pos[a] + (uint32_t)(flips[a] * childSize));
 				if ((id[a] & flips[a]) != flips[a]) wrapped = 1;
 			}
+			record_event(wrapped ? 'P' : 'A');
 			if (wrapped) {
 				if (st) st->pops++;
 				uint32_t diff = 0;
@@ -645,4 +655,18 @@ void cbqo_trace_iterations(const uint32_t* nodes, const cbqo_subdag sd[8], const
 		cbqo_intersect(nodes, sd, &rays[i], surf, maxFootprint, &h, &st);
 		iterations[i] = (uint32_t)st.iterations;
 	}
+}
+
+
+/* Event strings per ray, for the warp-scheduling simulations in DESIGN.md. events: n * cap bytes. */
+void cbqo_trace_events(const uint32_t* nodes, const cbqo_subdag sd[8], const cbqo_ray* rays, uint64_t n,
+	int surf, float maxFootprint, uint8_t* events, uint32_t cap, uint32_t* counts)
+{
+	for (uint64_t i = 0; i < n; i++) {
+		cbqo_hit h;
+		g_events = events + i * cap; g_eventCount = 0; g_eventCap = cap;
+		cbqo_intersect(nodes, sd, &rays[i], surf, maxFootprint, &h, NULL);
+		counts[i] = g_eventCount;
+	}
+	g_events = NULL;
 }

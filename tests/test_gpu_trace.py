@@ -177,12 +177,21 @@ def test_full_size_terrain_4096(gpu, port, api):
     p = rays["o"] + rays["d"] * frame["distance"][:, None]
     assert np.array_equal(p[hit].astype(np.float32), frame["position"][hit])
     # ... on a face of an occupied voxel of the scene, whose material is what the closed form says
-    vox = R.hit_voxels(frame[hit])
-    assert (sc.voxels(vox) == frame["material"][hit]).all()
+    # (the voxel is DERIVED from the float position, so a hit within float noise of a voxel edge -- a
+    # non-normal coordinate within 0.01 of x.5 at distances of several thousand -- may round to the
+    # neighbour; the north star allows exactly this residue and bounds it at 0.01 %)
+    fh = frame[hit]
+    vox = R.hit_voxels(fh)
+    frac = np.abs((fh["position"].astype(np.float64) - 0.5) % 1.0 - 0.5)      # distance to the nearest x.5
+    tangential = np.where(np.abs(fh["normal"]) == 1, 1.0, frac)
+    grazing = tangential.min(axis=1) < 0.01
+    wrong = sc.voxels(vox) != fh["material"]
+    assert wrong.mean() < 1e-4 and not (wrong & ~grazing).any()
     # ... entered from empty space (the voxel in front of the face is empty) for rays that start outside
-    front = np.floor(frame["position"][hit].astype(np.float64) + 0.5 * frame["normal"][hit] + 0.5).astype(np.int64)
-    one_axis = (np.abs(frame["normal"][hit]).sum(axis=1) == 1)
-    assert (sc.voxels(front[one_axis]) == 0).all()
+    front = np.floor(fh["position"].astype(np.float64) + 0.5 * fh["normal"] + 0.5).astype(np.int64)
+    one_axis = (np.abs(fh["normal"]).sum(axis=1) == 1)
+    blocked = (sc.voxels(front) != 0) & one_axis
+    assert blocked.mean() < 1e-4 and not (blocked & ~grazing).any()
     # the same rays through the buffer path give the same frame
     host = gpu.intersect_volume(rays, True, -1.0)
     assert_hits_identical(host, frame, "buffer path vs fused frame path")
