@@ -76,9 +76,10 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_build.LIB):
+    path = os.environ.get("CBQ_LIBRARY") or _build.LIB      # CBQ_LIBRARY: an experimental variant for A/B runs
+    if path == _build.LIB and not os.path.exists(path):
         _build.build_library()
-    L = C.CDLL(_build.LIB)
+    L = C.CDLL(path)
     vp, u64, u32, i32, f32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_float
     L.cbq_last_error.restype = C.c_char_p
     L.cbq_create.argtypes = [i32, C.POINTER(vp)]

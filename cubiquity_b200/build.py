@@ -41,18 +41,22 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    if not force and up_to_date():
+def build_library(force=False, verbose=False, defines=(), name=None):
+    """`defines`/`name` build an experimental variant (lib/<name>.so) for A/B runs; the default build
+    takes neither."""
+    global LIB
+    lib = LIB if name is None else os.path.join(LIBDIR, name + ".so")
+    if name is None and not force and up_to_date():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = find_nvcc()
     objs = []
     procs = []
-    objdir = os.path.join(LIBDIR, "obj")
+    objdir = os.path.join(LIBDIR, "obj" if name is None else "obj_" + name)
     os.makedirs(objdir, exist_ok=True)
     for s in SOURCES:
         o = os.path.join(objdir, os.path.splitext(s)[0] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     failed = False
@@ -64,9 +68,11 @@ def build_library(force=False, verbose=False):
             failed = True
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.run([nvcc, "-shared", "-o", LIB] + objs + ["-lpthread"], check=True)
-    return LIB
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib] + objs + ["-lpthread"], check=True)
+    return lib
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    names = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--name=")]
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, name=names[0] if names else None))

@@ -232,7 +232,9 @@ int traceDevice(cbq_context* ctx, const cbq::Ray* dRays, uint64_t n, uint32_t fl
 	int rc = nextQueue(ctx, stream, &a.queue);
 	if (rc != CBQ_OK) return rc;
 	applyL2Window(ctx, stream);
-	CBQ_CUDA(cbq::launchTrace(a, (flags & CBQ_TRACE_SURFACE) != 0, ctx->cfg, stream));
+	cbq::LaunchConfig cfg = ctx->cfg;
+	if (cam) cfg.refillThreshold = 32;   // tile-ordered primary rays are coherent by construction: no mid-flight refill
+	CBQ_CUDA(cbq::launchTrace(a, (flags & CBQ_TRACE_SURFACE) != 0, cfg, stream));
 	ctx->launches++;
 	ctx->raysTraced += n;
 	return CBQ_OK;
@@ -277,7 +279,7 @@ int cbq_create(int device, cbq_context** out)
 	ctx->cfg.blockThreads = 256;
 	ctx->cfg.blocksPerSm = 4;
 	ctx->cfg.smCount = ctx->prop.multiProcessorCount;
-	ctx->cfg.refillThreshold = 32;   // measured best for coherent rays (profiles/r01_sweeps.md)
+	ctx->cfg.refillThreshold = 8;    // robust default: +68 % on incoherent rays, -7 % on coherent ones (profiles/r01_sweeps.md)
 	ctx->cfg.kernel = 0;
 	ctx->cfg.stackLevels = 33;
 	*out = ctx;

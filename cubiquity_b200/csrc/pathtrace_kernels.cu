@@ -35,20 +35,34 @@ constexpr int kChunk = 32;            // pixels (one 8x4 tile) claimed per atomi
 constexpr int kStepsPerRound = 8;
 constexpr int kMaxDepth = 6;          // bounces <= 5 => depths 0..5
 
+// GlobalNodes and SharedStack: see trace_kernels.cu for the commentary.
 struct GlobalNodes {
 	const uint32_t* __restrict__ base;
-	__device__ __forceinline__ uint32_t child(uint32_t node, uint32_t slot) const
+	__device__ __forceinline__ const uint32_t* address(uint32_t node, uint32_t slot) const
 	{
-		return __ldg(base + ((size_t)node * 8u + slot));
+		const uint64_t a = reinterpret_cast<uint64_t>(base) + (uint64_t)node * 32u;
+		const uint32_t lo = (uint32_t)a + (slot << 2);
+		return reinterpret_cast<const uint32_t*>((a & 0xffffffff00000000ull) | lo);
 	}
+	__device__ __forceinline__ uint32_t child(uint32_t node, uint32_t slot) const { return __ldg(address(node, slot)); }
+	__device__ __forceinline__ void prefetch(uint32_t) const {}
 };
 
-struct SharedStack {   // see trace_kernels.cu
-	uint32_t* column;
-	uint32_t stride;
+struct SharedStack {
+	uint32_t column;
+	uint32_t strideBytes;
 	uint32_t written;
-	__device__ __forceinline__ void store(int h, uint32_t n) { column[(uint32_t)h * stride] = n; written |= 1u << h; }
-	__device__ __forceinline__ uint32_t load(int h) const { return ((written >> h) & 1u) ? column[(uint32_t)h * stride] : 0u; }
+	__device__ __forceinline__ void store(int h, uint32_t n)
+	{
+		asm volatile("st.shared.u32 [%0], %1;" :: "r"(column + (uint32_t)h * strideBytes), "r"(n));
+		written |= 1u << h;
+	}
+	__device__ __forceinline__ uint32_t load(int h) const
+	{
+		uint32_t v;
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(column + (uint32_t)h * strideBytes));
+		return ((written >> h) & 1u) ? v : 0u;
+	}
 	__device__ __forceinline__ void reset() { written = 0u; }
 };
 
@@ -132,7 +146,7 @@ renderPersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict
 	__syncthreads();
 
 	const GlobalNodes nodes{ nodeBase };
-	SharedStack stack{ stackMem + threadIdx.x, blockDim.x, 0u };
+	SharedStack stack{ (uint32_t)__cvta_generic_to_shared(stackMem + threadIdx.x), blockDim.x * 4u, 0u };
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lowerLanes = (1u << lane) - 1u;
 	uint64_t chunkNext = 0, chunkEnd = 0;   // warp-uniform window of claimed tickets

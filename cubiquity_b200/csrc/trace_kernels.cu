@@ -30,11 +30,28 @@ constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kChunk = 32;            // rays claimed per atomic ticket (small: ~14 claims per warp per frame keeps the tail short)
 constexpr int kStepsPerRound = 8;     // traversal steps between two refill votes
 
+// Node words through the read-only path. The node array starts 32-byte aligned (cbq_internal.h), so
+// node * 32 + base never carries into the word offset: one IMAD.WIDE + one LEA instead of a 64-bit
+// scaled add.
 struct GlobalNodes {
 	const uint32_t* __restrict__ base;
-	__device__ __forceinline__ uint32_t child(uint32_t node, uint32_t slot) const
+	__device__ __forceinline__ const uint32_t* address(uint32_t node, uint32_t slot) const
 	{
-		return __ldg(base + ((size_t)node * 8u + slot));
+		const uint64_t a = reinterpret_cast<uint64_t>(base) + (uint64_t)node * 32u;
+		const uint32_t lo = (uint32_t)a + (slot << 2);
+		return reinterpret_cast<const uint32_t*>((a & 0xffffffff00000000ull) | lo);
+	}
+	__device__ __forceinline__ uint32_t child(uint32_t node, uint32_t slot) const { return __ldg(address(node, slot)); }
+	// Start pulling a node's sector towards L1 before its first word is needed (descend: the slot is
+	// only known ~40 instructions later).
+	__device__ __forceinline__ void prefetch(uint32_t node) const
+	{
+#ifdef CBQ_PREFETCH_DESCEND
+		uint32_t sink;
+		asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(sink) : "l"(address(node, 0)));
+#else
+		(void)node;
+#endif
 	}
 };
 
@@ -44,11 +61,20 @@ struct GlobalNodes {
 // value the oracle's zero-initialised array holds, instead of whatever an earlier ray left behind.
 // (The reference's own array is uninitialised there, raytracing.cpp:251.)
 struct SharedStack {
-	uint32_t* column;
-	uint32_t stride;
+	uint32_t column;      // shared-window address of this thread's level-0 slot
+	uint32_t strideBytes; // blockDim.x * 4
 	uint32_t written;
-	__device__ __forceinline__ void store(int h, uint32_t n) { column[(uint32_t)h * stride] = n; written |= 1u << h; }
-	__device__ __forceinline__ uint32_t load(int h) const { return ((written >> h) & 1u) ? column[(uint32_t)h * stride] : 0u; }
+	__device__ __forceinline__ void store(int h, uint32_t n)
+	{
+		asm volatile("st.shared.u32 [%0], %1;" :: "r"(column + (uint32_t)h * strideBytes), "r"(n));
+		written |= 1u << h;
+	}
+	__device__ __forceinline__ uint32_t load(int h) const
+	{
+		uint32_t v;
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(column + (uint32_t)h * strideBytes));
+		return ((written >> h) & 1u) ? v : 0u;
+	}
 	__device__ __forceinline__ void reset() { written = 0u; }
 };
 
@@ -141,7 +167,7 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 	__syncthreads();
 
 	const GlobalNodes nodes{ nodeBase };
-	SharedStack stack{ stackMem + threadIdx.x, blockDim.x, 0u };
+	SharedStack stack{ (uint32_t)__cvta_generic_to_shared(stackMem + threadIdx.x), blockDim.x * 4u, 0u };
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lowerLanes = (1u << lane) - 1u;
 

@@ -413,6 +413,7 @@ CBQ_HD StepResult stepEsvo2(RayState& s, const Nodes& nodes, Stack& stack, float
 		const bool bigEnough = kLodOff ? lodOffTest(tExit, s.childSize) : (((float)s.childSize / tExit) > maxFootprint);
 		if (internal && bigEnough) {
 			// PUSH (raytracing.cpp:279-301)
+			nodes.prefetch(child);
 			if (tExit < s.lastExit) stack.store(s.height, s.node);
 			s.lastExit = tExit;
 			s.height--;
@@ -453,8 +454,9 @@ CBQ_HD StepResult stepEsvo2(RayState& s, const Nodes& nodes, Stack& stack, float
 	s.px = (int)((uint32_t)s.px + (fx ? cs : 0u));
 	s.py = (int)((uint32_t)s.py + (fy ? cs : 0u));
 	s.pz = (int)((uint32_t)s.pz + (fz ? cs : 0u));
+	const bool stayed = (s.idBits & flips) == 0u;   // == ((newId & flips) == flips): no flipped axis was already at bit 1
 	s.idBits = newId;
-	if ((newId & flips) == flips) {
+	if (stayed) {
 		// Stayed inside the parent: a flipped axis' old upper plane is its new lower plane.
 		const float nx = planeT((int)((uint32_t)s.px + cs), s.ox, s.ix);
 		const float ny = planeT((int)((uint32_t)s.py + cs), s.oy, s.iy);
@@ -471,11 +473,14 @@ CBQ_HD StepResult stepEsvo2(RayState& s, const Nodes& nodes, Stack& stack, float
 	s.node = stack.load(s.height);
 	const uint32_t big = 1u << msb;
 	s.childSize = (int)big;
-	const uint32_t bx = ((uint32_t)(s.px >> msb)) & 1u, by = ((uint32_t)(s.py >> msb)) & 1u, bz = ((uint32_t)(s.pz >> msb)) & 1u;
-	s.idBits = bx | (by << 1) | (bz << 2);
-	s.px = (int)((((uint32_t)(s.px >> s.height)) << s.height) + (bx ? big : 0u));
-	s.py = (int)((((uint32_t)(s.py >> s.height)) << s.height) + (by ? big : 0u));
-	s.pz = (int)((((uint32_t)(s.pz >> s.height)) << s.height) + (bz ? big : 0u));
+	// The reference re-derives childId = (pos >> msb) & 1 and childPos = ((pos >> height) << height) +
+	// childId * size (raytracing.cpp:359-361). Aligning to 2^height and adding back bit `msb` is the same
+	// as clearing the bits BELOW msb, so: pos &= -size.
+	const uint32_t keep = 0u - big;
+	s.idBits = (((uint32_t)s.px >> msb) & 1u) | ((((uint32_t)s.py >> msb) & 1u) << 1) | ((((uint32_t)s.pz >> msb) & 1u) << 2);
+	s.px = (int)((uint32_t)s.px & keep);
+	s.py = (int)((uint32_t)s.py & keep);
+	s.pz = (int)((uint32_t)s.pz & keep);
 	s.lastExit = 0.0f;
 	s.Lx = planeT(s.px, s.ox, s.ix); s.Ly = planeT(s.py, s.oy, s.iy); s.Lz = planeT(s.pz, s.oz, s.iz);
 	s.Ux = planeT((int)((uint32_t)s.px + big), s.ox, s.ix);

@@ -1,0 +1,119 @@
+// C++ host-side mirror of the reference's ray-cast interface, over the C ABI (include/cubiquity_b200.h).
+//
+// A maintainer of Cubiquity includes this header next to raytracing.h and swaps
+//     Cubiquity::intersectVolume(volume, subDAGs, ox, oy, oz, dx, dy, dz, surf, maxFootprint)
+// for
+//     CubiquityGPU::intersectVolume(gpuVolume, ox, oy, oz, dx, dy, dz, surf, maxFootprint)
+// with the same argument meaning, the same result struct and the same "never throws" contract
+// (reference src/library/raytracing.h:48-55,69-76). The batch forms are what the GPU is for; the
+// single-ray form exists so picking code (reference viewer.cpp:157-163) ports line for line.
+//
+// Header-only, no CUDA headers needed by the includer; link against libcubiquity_b200.so.
+#ifndef CUBIQUITY_GPU_H
+#define CUBIQUITY_GPU_H
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/cubiquity_b200.h"
+
+namespace CubiquityGPU {
+
+// Field-for-field the reference's RayVolumeIntersection (raytracing.h:48-55), distance widened back to
+// double exactly as the reference stores it (raytracing.cpp:305).
+struct RayVolumeIntersection {
+	bool hit;
+	double distance;
+	unsigned int material;
+	float position[3];
+	float normal[3];
+};
+
+typedef cbq_subdag SubDAG;                 // raytracing.h:57-65
+struct SubDAGArray { SubDAG v[8]; const SubDAG& operator[](unsigned i) const { return v[i]; } };
+
+constexpr float MAX_FOOTPRINT_DISABLED = -1.0f;   // raytracing.h:71
+
+inline RayVolumeIntersection widen(const cbq_hit& h)
+{
+	RayVolumeIntersection r;
+	r.hit = h.hit != 0;
+	r.distance = static_cast<double>(h.distance);
+	r.material = h.material;
+	for (int a = 0; a < 3; a++) { r.position[a] = h.position[a]; r.normal[a] = h.normal[a]; }
+	return r;
+}
+
+// The device-resident copy of a Cubiquity::Volume's node array. Owns a cbq_context.
+class GpuVolume {
+public:
+	explicit GpuVolume(int device = 0) : mCtx(nullptr), mOk(cbq_create(device, &mCtx) == CBQ_OK) {}
+	~GpuVolume() { cbq_destroy(mCtx); }
+	GpuVolume(const GpuVolume&) = delete;
+	GpuVolume& operator=(const GpuVolume&) = delete;
+
+	bool ok() const { return mOk; }
+	static std::string lastError() { return cbq_last_error(); }
+	cbq_context* context() const { return mCtx; }
+
+	// nodes = Internals::getNodes(volume).rawBytesPtr(), count = unsharedNodesEnd(),
+	// root = Internals::getRootNodeIndex(volume)  (storage.h:87-102, storage.cpp:563-576).
+	bool upload(const void* nodes, uint64_t nodeCount, uint32_t root, const float* coloursRgb = nullptr)
+	{
+		mSynced = nodeCount;
+		return cbq_upload(mCtx, static_cast<const uint32_t*>(nodes), nodeCount, root, coloursRgb) == CBQ_OK;
+	}
+
+	// Call from onVolumeModified() (pathtracing_demo.cpp:335-341). sharedNodesEndAtLastSync is what
+	// NodeStore::sharedNodesEnd() returned when the device was last brought up to date; pass the value
+	// you remembered, then remember the current one.
+	bool update(const void* nodes, uint64_t sharedNodesEndAtLastSync, uint64_t nodeCount, uint32_t root)
+	{
+		return cbq_update(mCtx, static_cast<const uint32_t*>(nodes), sharedNodesEndAtLastSync, nodeCount, root) == CBQ_OK;
+	}
+
+	SubDAGArray subDAGs() const
+	{
+		SubDAGArray a{};
+		cbq_get_subdags(mCtx, a.v);
+		return a;
+	}
+
+private:
+	cbq_context* mCtx;
+	bool mOk;
+	uint64_t mSynced = 0;
+};
+
+// findSubDAGs (raytracing.h:69) without a device.
+inline bool findSubDAGs(const void* nodes, uint64_t nodeCount, uint32_t root, SubDAGArray& out)
+{
+	return cbq_find_subdags(static_cast<const uint32_t*>(nodes), nodeCount, root, out.v) == CBQ_OK;
+}
+
+// The six-float overload every reference call site uses (raytracing.h:72-75).
+inline RayVolumeIntersection intersectVolume(const GpuVolume& volume,
+	float ray_orig_x, float ray_orig_y, float ray_orig_z, float ray_dir_x, float ray_dir_y, float ray_dir_z,
+	bool computeSurfaceProperties, float maxFootprint = MAX_FOOTPRINT_DISABLED)
+{
+	const cbq_ray r = { { ray_orig_x, ray_orig_y, ray_orig_z }, { ray_dir_x, ray_dir_y, ray_dir_z } };
+	cbq_hit h{};
+	if (cbq_trace(volume.context(), &r, 1, computeSurfaceProperties ? CBQ_TRACE_SURFACE : 0u, maxFootprint, &h) != CBQ_OK) {
+		h = cbq_hit{};   // like the reference, report a miss rather than throw; GpuVolume::lastError() says why
+	}
+	return widen(h);
+}
+
+// Batch form: rays[i] -> out[i]. Returns false (and leaves `out` sized but zeroed) on error.
+inline bool intersectVolume(const GpuVolume& volume, const std::vector<cbq_ray>& rays, bool computeSurfaceProperties,
+	float maxFootprint, std::vector<cbq_hit>& out)
+{
+	out.assign(rays.size(), cbq_hit{});
+	return cbq_trace(volume.context(), rays.data(), rays.size(), computeSurfaceProperties ? CBQ_TRACE_SURFACE : 0u,
+		maxFootprint, out.data()) == CBQ_OK;
+}
+
+} // namespace CubiquityGPU
+
+#endif // CUBIQUITY_GPU_H

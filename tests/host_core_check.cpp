@@ -10,6 +10,7 @@ namespace {
 struct HostNodes {
 	const uint32_t* base;
 	uint32_t child(uint32_t node, uint32_t slot) const { return base[(size_t)node * 8 + slot]; }
+	void prefetch(uint32_t) const {}
 };
 struct HostStack {
 	uint32_t v[33];

@@ -182,7 +182,8 @@ def test_full_size_terrain_4096(gpu, port, api):
     # neighbour; the north star allows exactly this residue and bounds it at 0.01 %)
     fh = frame[hit]
     vox = R.hit_voxels(fh)
-    frac = np.abs((fh["position"].astype(np.float64) - 0.5) % 1.0 - 0.5)      # distance to the nearest x.5
+    q = (fh["position"].astype(np.float64) - 0.5) % 1.0
+    frac = np.minimum(q, 1.0 - q)                                            # distance to the nearest x.5
     tangential = np.where(np.abs(fh["normal"]) == 1, 1.0, frac)
     grazing = tangential.min(axis=1) < 0.01
     wrong = sc.voxels(vox) != fh["material"]
