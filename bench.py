@@ -54,6 +54,16 @@ def parse():
     return ap.parse_args()
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        t = json.load(open(path))
+        return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"]), t.get("source")
+    except Exception:
+        return None, None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -212,7 +222,13 @@ def main():
     b.lower, b.upper = lower, upper
 
     ctx = api.Context(local)
-    for kv in args.option:
+    options = list(args.option)
+    if args.workload == "primary" and not any(o.startswith("refill_threshold=") for o in options):
+        # Primary rays are coherent: mid-flight lane refill costs 7-10 % on them (profiles/r01_sweeps.md), so
+        # this workload runs with the knob at 32 (= refill only when the whole warp is done). The library
+        # default (8) is the robust choice for batches of unknown coherence.
+        options.append("refill_threshold=32")
+    for kv in options:
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
     ctx.upload(nodes, root, colours)
@@ -279,6 +295,28 @@ def main():
     torch.cuda.synchronize()
     warm_ms = e0.elapsed_time(e1) / args.steps
 
+    # ---- secondary metric of BASELINE.json: 1080p path-traced samples per second (spp/s) ------------
+    pt = None
+    if args.workload == "primary":
+        d_accum = torch.zeros(HEIGHT * WIDTH * 3, dtype=torch.float32, device=dev)
+        p = api.pt_params(WIDTH, HEIGHT, spp=args.spp, bounces=args.bounces, variant=api.VARIANT_RECURSIVE, frame_id=0)
+        ctx.render_device(cam, api.pt_params(WIDTH, HEIGHT, spp=1, bounces=args.bounces, variant=api.VARIANT_RECURSIVE), d_accum.data_ptr(), stream)
+        torch.cuda.synchronize()
+        d_accum.zero_()
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ctx.render_device(cam, p, d_accum.data_ptr(), stream)
+        b2.record()
+        torch.cuda.synchronize()
+        pt_ms = a.elapsed_time(b2)
+        if world > 1:
+            t = torch.tensor([pt_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pt_ms = float(t.item())
+        pt = {"spp_per_s": world * WIDTH * HEIGHT * args.spp / (pt_ms * 1e-3), "ms": pt_ms,
+              "config": "1920x1080, %d spp, %d bounces, traceSingleRayRecurse, sun+sky+noise, maxFootprint 0.0035, same terrain" % (args.spp, args.bounces),
+              "mean_radiance": float(d_accum.mean().item()) / args.spp}
+
     # ---- end to end through the public host-buffer call ------------------------------------------
     pin_rays = api.PinnedArray(n_rays, api.RAY_DTYPE)
     pin_hits = api.PinnedArray(n_rays, api.HIT_DTYPE)
@@ -317,6 +355,7 @@ def main():
     bytes_per_ray = 32.0 * visits + 24.0 + 40.0
     peak, peak_src = peaks()
     achieved = n_rays * bytes_per_ray / (ms_per_step * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic() if args.workload == "primary" else (None, None)
     # parity spot check of what was just timed
     want, _, _ = port.trace(nodes, sd, host_rays[pick], True, -1.0, threads=os.cpu_count() or 1)
     parity = float((want.view(np.uint32).reshape(-1, 10) == device_hits[pick].view(np.uint32).reshape(-1, 10)).all(axis=1).mean())
@@ -342,21 +381,23 @@ def main():
         "config": {"workload": workload, "scene": "%s 2^%d seed %d" % (SCENE_KIND, args.scene_log2, SCENE_SEED),
                    "nodes": int(len(nodes)), "dag_mb": round(len(nodes) * 32 / 1e6, 1), "rays_per_step_per_gpu": n_rays,
                    "l2": "warm (no flush)" if args.no_flush else "flushed between steps (256 MB memset, untimed)",
-                   "hit_fraction": round(hit_fraction, 4), "options": args.option,
+                   "hit_fraction": round(hit_fraction, 4), "options": options,
                    "parallelism": "replicated DAG, one frame per GPU" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": "Grays/s", "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * 40,
                 "ms_per_step": 1e3 * e2e_s, "call": "cbq_trace (pinned host rays -> pinned host hits, 3-stage copy/compute pipeline)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "node_visits_per_ray": visits,
-                     "kernel": "tracePersistent<surface, BufferSource>", "note": "algorithmic bytes = 32 B x V + 24 B ray + 40 B hit; the DAG working set is L2-resident so HBM is not the binding limit (see DESIGN.md)"},
+                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": n_rays * bytes_per_ray,
+                     "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "node_visits_per_ray": visits,
+                     "kernel": "tracePersistent<surface=1, lodOff=1, BufferSource>", "note": "algorithmic bytes = 32 B x V + 24 B ray + 40 B hit; node re-visits are served by L1/L2, the kernel is issue-bound under SIMT divergence, not HBM-bound (DESIGN.md 4.4, profiles/r01_analysis.md)"},
         "cpu_baseline": {"value": cpu_all, "unit": "Grays/s", "cores": threads, "kind": kind,
                          "sample": "first %d rays of the same frame, all host threads" % len(cpu_sample),
                          "single_thread_value": cpu_one, "single_thread_sample": "%d rays (every 8th of the sample)" % len(cpu_one_sample)},
         "clocks": clocks.summary(),
         "extra": {"warm_l2_ms_per_step": warm_ms, "warm_l2_value": world * n_rays / (warm_ms * 1e-3) / 1e9,
                   "step_ms_min": float(np.min(step_ms)), "step_ms_max": float(np.max(step_ms)), "timed_wall_s": wall,
-                  "scene_build_s": build_s, "parity_vs_oracle_sample": parity, "e2e_equals_device_path": bool(same)},
+                  "scene_build_s": build_s, "parity_vs_oracle_sample": parity, "e2e_equals_device_path": bool(same),
+                  "pathtrace": pt},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -44,7 +44,8 @@ int fail(int code, const char* fmt, ...)
 	} while (0)
 
 constexpr int kQueueSlots = 4096;      // ring of zeroed ticket counters, one per launch
-constexpr uint64_t kPipelineChunk = 1u << 18;  // rays per host<->device pipeline stage
+constexpr uint64_t kPipelineChunk = 1u << 16;  // rays per host<->device pipeline stage (1.5 MB in, 2.5 MB out)
+constexpr int kStages = 4;                     // staging buffers in flight
 
 // findSubDAG (reference src/library/raytracing.cpp:43-87), host side, bounds-checked because the
 // node array comes from outside.
@@ -100,7 +101,7 @@ struct cbq_context {
 	cudaDeviceProp prop{};
 	cudaStream_t stream = nullptr;       // compute + default
 	cudaStream_t copyIn = nullptr, copyOut = nullptr;
-	cudaEvent_t evIn[2]{}, evKernel[2]{}, evOut[2]{};
+	cudaEvent_t evIn[kStages]{}, evKernel[kStages]{}, evOut[kStages]{};
 
 	// The volume: one linear device buffer.
 	uint8_t* volume = nullptr;
@@ -120,8 +121,8 @@ struct cbq_context {
 	uint64_t windowGeneration = ~0ull;
 
 	// cbq_trace staging (device side), double buffered.
-	cbq::Ray* stageRays[2]{};
-	cbq::Hit* stageHits[2]{};
+	cbq::Ray* stageRays[kStages]{};
+	cbq::Hit* stageHits[kStages]{};
 
 	// cbq_render staging
 	float* stageAccum = nullptr;
@@ -211,7 +212,7 @@ void applyL2Window(cbq_context* ctx, cudaStream_t stream)
 
 int ensureStaging(cbq_context* ctx)
 {
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < kStages; i++) {
 		if (!ctx->stageRays[i]) CBQ_CUDA(cudaMalloc(&ctx->stageRays[i], kPipelineChunk * sizeof(cbq::Ray)));
 		if (!ctx->stageHits[i]) CBQ_CUDA(cudaMalloc(&ctx->stageHits[i], kPipelineChunk * sizeof(cbq::Hit)));
 	}
@@ -269,7 +270,7 @@ int cbq_create(int device, cbq_context** out)
 	CBQ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 	CBQ_CUDA(cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking));
 	CBQ_CUDA(cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking));
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < kStages; i++) {
 		CBQ_CUDA(cudaEventCreateWithFlags(&ctx->evIn[i], cudaEventDisableTiming));
 		CBQ_CUDA(cudaEventCreateWithFlags(&ctx->evKernel[i], cudaEventDisableTiming));
 		CBQ_CUDA(cudaEventCreateWithFlags(&ctx->evOut[i], cudaEventDisableTiming));
@@ -291,7 +292,7 @@ void cbq_destroy(cbq_context* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < kStages; i++) {
 		cudaFree(ctx->stageRays[i]); cudaFree(ctx->stageHits[i]);
 		if (ctx->evIn[i]) cudaEventDestroy(ctx->evIn[i]);
 		if (ctx->evKernel[i]) cudaEventDestroy(ctx->evKernel[i]);
@@ -444,19 +445,19 @@ int cbq_trace(cbq_context* ctx, const cbq_ray* rays, uint64_t n, uint32_t flags,
 	if (n == 0) return CBQ_OK;
 	if (!rays || !hits) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null ray or hit buffer");
 	rc = ensureStaging(ctx); if (rc) return rc;
-	// Three-stage pipeline over chunks: H2D on copyIn, kernel on stream, D2H on copyOut, two
+	// Three-stage pipeline over chunks: H2D on copyIn, kernel on stream, D2H on copyOut, kStages
 	// staging buffers in flight. With pinned host memory the three overlap; with pageable memory
 	// the copies degrade to synchronous but the result is the same.
 	const uint64_t chunks = (n + kPipelineChunk - 1) / kPipelineChunk;
 	for (uint64_t c = 0; c < chunks; c++) {
-		const int b = (int)(c & 1);
+		const int b = (int)(c % kStages);
 		const uint64_t begin = c * kPipelineChunk;
 		const uint64_t len = std::min(kPipelineChunk, n - begin);
-		if (c >= 2) CBQ_CUDA(cudaStreamWaitEvent(ctx->copyIn, ctx->evOut[b], 0));   // buffer b free again
+		if (c >= (uint64_t)kStages) CBQ_CUDA(cudaStreamWaitEvent(ctx->copyIn, ctx->evOut[b], 0));   // buffer b free again
 		CBQ_CUDA(cudaMemcpyAsync(ctx->stageRays[b], rays + begin, len * sizeof(cbq_ray), cudaMemcpyHostToDevice, ctx->copyIn));
 		CBQ_CUDA(cudaEventRecord(ctx->evIn[b], ctx->copyIn));
 		CBQ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evIn[b], 0));
-		if (c >= 2) CBQ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evOut[b], 0));
+		if (c >= (uint64_t)kStages) CBQ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evOut[b], 0));
 		rc = traceDevice(ctx, ctx->stageRays[b], len, flags, max_footprint, ctx->stageHits[b], ctx->stream, nullptr, 0, 0);
 		if (rc) return rc;
 		CBQ_CUDA(cudaEventRecord(ctx->evKernel[b], ctx->stream));
