@@ -37,7 +37,7 @@ def test_subdags_on_device_match_oracle(gpu, port, scenes):
     assert np.array_equal(gpu.download_nodes(), sc.nodes)
 
 
-@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 127, 129, (1 << 16) - 1, (1 << 16) + 1, 4 * (1 << 16), 9 * (1 << 16) + 17])
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 127, 129, (1 << 18) - 1, (1 << 18) + 1, 3 * (1 << 18), 4 * (1 << 18) + 17])
 def test_ragged_batch_sizes(gpu, port, scenes, n):
     sc = scenes("sphere_noise", 7)
     gpu.upload(sc.nodes, sc.root)
