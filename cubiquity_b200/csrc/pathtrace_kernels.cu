@@ -135,7 +135,11 @@ struct PathState {
 	float ar, ag, ab;       // running pixel sum
 };
 
-__global__ void __launch_bounds__(256, 2)
+#ifndef CBQ_RENDER_MIN_BLOCKS
+#define CBQ_RENDER_MIN_BLOCKS 2
+#endif
+
+__global__ void __launch_bounds__(256, CBQ_RENDER_MIN_BLOCKS)
 renderPersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict__ subdagsGlobal,
 	const float4* __restrict__ colours, cbq_camera cam, cbq_pt_params p, float* __restrict__ accum, int refillThreshold,
 	unsigned long long* __restrict__ queue, unsigned long long* __restrict__ abandoned)
@@ -351,7 +355,7 @@ cudaError_t launchRender(const RenderArgs& a, const LaunchConfig& cfg, cudaStrea
 	if (e != cudaSuccess) return e;
 	const uint32_t rectW = a.params.x1 - a.params.x0, rectH = a.params.y1 - a.params.y0;
 	const uint64_t tiles = (uint64_t)((rectW + 7u) / 8u) * ((rectH + 3u) / 4u);
-	int grid = cfg.smCount * 2;
+	int grid = cfg.smCount * CBQ_RENDER_MIN_BLOCKS;
 	const uint64_t needed = (tiles * 32u + block - 1) / block;
 	if ((uint64_t)grid > needed) grid = (int)(needed ? needed : 1);
 	renderPersistent<<<grid, block, smem, stream>>>(a.nodes, a.subdags, a.colours, a.camera, a.params, a.accum, cfg.refillThreshold, a.queue, a.abandoned);

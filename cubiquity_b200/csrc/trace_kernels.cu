@@ -28,7 +28,14 @@ namespace {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kChunk = 32;            // rays claimed per atomic ticket (small: ~14 claims per warp per frame keeps the tail short)
-constexpr int kStepsPerRound = 8;     // traversal steps between two refill votes
+#ifndef CBQ_STEPS_PER_ROUND
+#define CBQ_STEPS_PER_ROUND 8
+#endif
+#ifndef CBQ_STEP_UNROLL
+#define CBQ_STEP_UNROLL 1
+#endif
+constexpr int kStepsPerRound = CBQ_STEPS_PER_ROUND;     // traversal steps between two refill votes
+constexpr int kStepUnroll = CBQ_STEP_UNROLL;
 
 // Node words through the read-only path. The node array starts 32-byte aligned (cbq_internal.h), so
 // node * 32 + base never carries into the word offset: one IMAD.WIDE + one LEA instead of a 64-bit
@@ -213,7 +220,7 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 			continue;
 		}
 
-#pragma unroll 1
+#pragma unroll kStepUnroll
 		for (int k = 0; k < kStepsPerRound; k++) {
 			if (s.phase == kPhaseIdle) continue;
 			Hit out;

@@ -40,6 +40,27 @@ def time_config(ctx, d_rays, n, d_hits, flush, stream, steps=10, mf=-1.0, surfac
     return float(np.mean(cold)), a.elapsed_time(b) / steps
 
 
+def render_sweep(ctx, scene, dev, stream):
+    cam = api.default_camera(scene.lower, scene.upper)
+    acc = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
+    for variant, bounces, spp, thr in [(1, 4, 4, 8), (1, 4, 4, 32), (1, 4, 4, 1), (1, 1, 4, 8), (0, 1, 4, 8)]:
+        ctx.set_option("refill_threshold", thr)
+        p = api.pt_params(W, H, spp=spp, bounces=bounces, variant=variant)
+        ctx.render_device(cam, api.pt_params(W, H, spp=1, bounces=bounces, variant=variant), acc.data_ptr(), stream)
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(3):
+            acc.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); ctx.render_device(cam, p, acc.data_ptr(), stream); b.record()
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+        ms = float(np.median(times))
+        print(json.dumps({"workload": "render", "lib": os.environ.get("CBQ_LIBRARY", "default"), "variant": variant, "bounces": bounces, "spp": spp,
+                          "refill_threshold": thr, "ms": round(ms, 3), "mspp_per_s": round(W * H * spp / ms / 1e3, 1),
+                          "mean": round(float(acc.mean().item()) / spp, 5)}), flush=True)
+
+
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "primary"
     scene = api.Scene("terrain", 12, 1)
@@ -47,6 +68,9 @@ def main():
     ctx.upload(scene.nodes, scene.root, scene.colours)
     dev = torch.device("cuda", 0)
     stream = torch.cuda.current_stream().cuda_stream
+    if what == "render":
+        render_sweep(ctx, scene, dev, stream)
+        return
     if what == "random":
         n = 8_000_000
         host = R.random_rays(n, scene.lower, scene.upper, seed=100)

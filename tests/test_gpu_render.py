@@ -72,3 +72,39 @@ def test_flags_tiles_and_accumulation(gpu, port, api, scenes):
     acc = gpu.render(cam, api.pt_params(w, h, spp=1, bounces=1, variant=1, frame_id=0))
     gpu.render(cam, api.pt_params(w, h, spp=1, bounces=1, variant=1, frame_id=1), acc)
     assert np.array_equal(acc, whole)
+
+
+def test_soup_four_bounces_config4_in_miniature(gpu, port, api):
+    """BASELINE config 4 at reduced size: voxelised solids (2048^3), 4 bounces, 2 spp, LOD 0.0035."""
+    from oracle import pyoracle
+    sc = api.Scene("soup", 11, seed=5)
+    gpu.upload(sc.nodes, sc.root, sc.colours)
+    cam, ocam = both_cameras(api, port, sc)
+    p = api.pt_params(320, 180, spp=2, bounces=4, variant=api.VARIANT_RECURSIVE)
+    sd = port.find_subdags(sc.nodes, sc.root)
+    want, _, nrays = port.render(sc.nodes, sd, sc.colours, ocam, oracle_params(pyoracle, p), threads=8)
+    got = gpu.render(cam, p)
+    assert nrays > 4 * 320 * 180
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_render_device_pointer_and_sample_sharding(gpu, port, api, scenes):
+    """Device-pointer entry point; and samples split over two calls (as two GPUs would) sum to the same image
+    up to float re-association of the per-pixel sums."""
+    torch = pytest.importorskip("torch")
+    sc = scenes("sphere_noise", 7)
+    gpu.upload(sc.nodes, sc.root, sc.colours)
+    cam, _ = both_cameras(api, port, sc)
+    w, h = 128, 96
+    whole = gpu.render(cam, api.pt_params(w, h, spp=4, bounces=1, variant=1))
+    stream = torch.cuda.current_stream().cuda_stream
+    a = torch.zeros(h, w, 3, device="cuda")
+    b = torch.zeros(h, w, 3, device="cuda")
+    gpu.render_device(cam, api.pt_params(w, h, spp=2, bounces=1, variant=1, frame_id=0), a.data_ptr(), stream)
+    gpu.render_device(cam, api.pt_params(w, h, spp=2, bounces=1, variant=1, frame_id=2), b.data_ptr(), stream)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose((a + b).cpu().numpy(), whole, rtol=1e-6, atol=1e-6)
+    c = torch.zeros(h, w, 3, device="cuda")
+    gpu.render_device(cam, api.pt_params(w, h, spp=4, bounces=1, variant=1), c.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(c.cpu().numpy(), whole)

@@ -68,3 +68,35 @@ def test_update_argument_checks(gpu, api, scenes):
     with pytest.raises(api.CubiquityError) as e:
         gpu.update(bad, 256, sc.root)
     assert e.value.code == api.ERROR_CORRUPT_VOLUME
+
+
+def test_city_65536_with_runtime_edits_and_lod(gpu, port, ref, api):
+    """BASELINE config 5 in miniature: the 65536^3 city, three reference edits (checkpoint + radius-30
+    fillBrush, viewer.cpp:165-168) each shipped as a delta, ray cast with the path tracer's LOD threshold and
+    path-traced after every edit."""
+    from oracle import pyoracle
+    sc = api.Scene("city", 16, seed=2)
+    v = ref.volume().load_arrays(sc.nodes, sc.root)
+    gpu.upload(v.nodes(), v.root(), sc.colours)
+    synced = v.shared_end()
+    lower, upper = np.array([-1500, -1500, -64]), np.array([1500, 1500, 1100])
+    rays = mixed_rays(lower, upper, 120000, seed=8)
+    cam = api.camera_from_pose([0.0, -2600.0, 1800.0], -0.6, 0.0)
+    ocam = port.camera([0.0, -2600.0, 1800.0], -0.6, 0.0)
+    for step, centre in enumerate([(128.0, 128.0, 300.0), (-380.0, 250.0, 40.0), (600.0, -700.0, 5.0)]):
+        v.checkpoint()
+        v.fill_sphere(centre[0], centre[1], centre[2], 30.0, 0)
+        nodes, root = v.nodes(), v.root()
+        tail = len(nodes) - synced
+        gpu.update(nodes, synced, root)
+        synced = v.shared_end()
+        assert 0 < tail * 32 < 400000                      # SURVEY A9: tens of KB per edit, not the whole DAG
+        sd = port.find_subdags(nodes, root)
+        assert gpu.subdags().tobytes() == sd.tobytes()
+        for mf in (-1.0, 0.0035):
+            want, _, _ = port.trace(nodes, sd, rays, True, mf, threads=8)
+            assert_hits_identical(gpu.intersect_volume(rays, True, mf), want, "city edit %d mf %g" % (step, mf))
+        p = api.pt_params(160, 90, spp=1, bounces=2, variant=api.VARIANT_RECURSIVE, frame_id=step)
+        op = pyoracle.PtParams(*[getattr(p, f) for f, _ in p._fields_])
+        want_img, _, _ = port.render(nodes, sd, sc.colours, ocam, op, threads=8)
+        assert np.array_equal(gpu.render(cam, p), want_img)
