@@ -127,6 +127,8 @@ struct cbq_context {
 	// cbq_render staging
 	float* stageAccum = nullptr;
 	size_t stageAccumBytes = 0;
+	cbq::WavefrontBuffers wavefront;
+	int renderMode = 0;   // 0 wavefront (per-bounce kernels), 1 persistent megakernel
 
 	// Counters
 	uint64_t launches = 0, raysTraced = 0, bytesH2D = 0, bytesD2H = 0;
@@ -299,6 +301,7 @@ void cbq_destroy(cbq_context* ctx)
 		if (ctx->evOut[i]) cudaEventDestroy(ctx->evOut[i]);
 	}
 	cudaFree(ctx->stageAccum);
+	cbq::wavefrontRelease(ctx->wavefront);
 	cudaFree(ctx->queues);
 	cudaFree(ctx->volume);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -526,10 +529,18 @@ int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_para
 	std::memset(&a, 0, sizeof(a));
 	a.nodes = ctx->nodesPtr(); a.subdags = ctx->subdagsPtr(); a.colours = ctx->coloursPtr();
 	a.camera = *cam; a.params = *p; a.accum = d_accum; a.abandoned = ctx->abandonedPtr();
-	rc = nextQueue(ctx, s, &a.queue); if (rc) return rc;
 	applyL2Window(ctx, s);
-	CBQ_CUDA(cbq::launchRender(a, ctx->cfg, s));
-	ctx->launches++;
+	if (ctx->renderMode == 1) {
+		rc = nextQueue(ctx, s, &a.queue); if (rc) return rc;
+		CBQ_CUDA(cbq::launchRender(a, ctx->cfg, s));
+		ctx->launches++;
+		return CBQ_OK;
+	}
+	const size_t pixels = (size_t)(p->x1 - p->x0) * (p->y1 - p->y0);
+	if (pixels > ctx->wavefront.pixelCapacity) CBQ_CUDA(cudaDeviceSynchronize());   // buffers may still be in use
+	CBQ_CUDA((cudaError_t)cbq::wavefrontReserve(ctx->wavefront, pixels));
+	struct Adaptor { static int next(void* user, cudaStream_t st, unsigned long long** out) { return nextQueue(static_cast<cbq_context*>(user), st, out); } };
+	CBQ_CUDA(cbq::launchRenderWavefront(a, ctx->wavefront, ctx->cfg, s, &Adaptor::next, ctx, &ctx->launches));
 	return CBQ_OK;
 }
 
@@ -583,6 +594,9 @@ int cbq_set_option(cbq_context* ctx, const char* key, int64_t value)
 	} else if (k == "kernel") {
 		if (value < 0 || value > 1) return fail(CBQ_ERROR_INVALID_ARGUMENT, "kernel must be 0 or 1");
 		ctx->cfg.kernel = (int)value;
+	} else if (k == "render_mode") {
+		if (value < 0 || value > 1) return fail(CBQ_ERROR_INVALID_ARGUMENT, "render_mode must be 0 (wavefront) or 1 (megakernel)");
+		ctx->renderMode = (int)value;
 	} else if (k == "l2_persist") {
 		ctx->l2Persist = value ? 1 : 0;
 		ctx->windowGeneration = ~0ull; // re-apply on next launch
@@ -601,6 +615,7 @@ int cbq_get_option(cbq_context* ctx, const char* key, int64_t* value)
 	else if (k == "refill_threshold") *value = ctx->cfg.refillThreshold;
 	else if (k == "kernel") *value = ctx->cfg.kernel;
 	else if (k == "l2_persist") *value = ctx->l2Persist;
+	else if (k == "render_mode") *value = ctx->renderMode;
 	else if (k == "sm_count") *value = ctx->cfg.smCount;
 	else if (k == "stack_levels") *value = ctx->cfg.stackLevels;
 	else if (k == "l2_bytes") *value = ctx->prop.l2CacheSize;

@@ -49,9 +49,14 @@ struct TraceArgs {
 	float maxFootprint;
 	unsigned long long* queue;   // one zeroed 64-bit ticket counter for this launch
 	unsigned long long* abandoned; // device counter, incremented per abandoned ray
-	// camera source (rays == nullptr)
+	// camera source (rays == nullptr): image size and the pixel rectangle to trace (0 = whole image)
 	cbq_camera camera;
 	uint32_t width, height;
+	uint32_t x0, y0, rectW, rectH;
+	// optional: batch size read on the device (count = *countPtr * countScale), flag-only results
+	const unsigned long long* countPtr;
+	uint32_t countScale;
+	uint8_t* flags;
 };
 
 cudaError_t launchTrace(const TraceArgs& a, bool surface, const LaunchConfig& cfg, cudaStream_t stream);
@@ -68,5 +73,26 @@ struct RenderArgs {
 	unsigned long long* abandoned;
 };
 cudaError_t launchRender(const RenderArgs& a, const LaunchConfig& cfg, cudaStream_t stream);
+
+// Wavefront path tracer (wavefront_kernels.cu): per-bounce kernels around the ray-cast kernel.
+struct WavefrontBuffers {
+	size_t pixelCapacity = 0;      // pixels of the largest rectangle rendered so far
+	Hit* hits = nullptr;           // surface hits of the current depth            [pixels]
+	Ray* rays[2] = { nullptr, nullptr };        // bounce rays, ping-pong           [pixels]
+	uint32_t* pixel[2] = { nullptr, nullptr };  // rect-local pixel id of each path [pixels]
+	uint32_t* rng[2] = { nullptr, nullptr };    // RNG state of each path           [pixels]
+	float* sunTerm = nullptr;      // 0.1 * max(dot(sun, n), 0) of each live path  [pixels]
+	Ray* shadowRays = nullptr;     // sun + sky shadow rays of the live paths      [2 * pixels]
+	uint8_t* shadowFlags = nullptr;//                                              [2 * pixels]
+	float* colour = nullptr;       // c[k] per depth, SoA [depth][3][pixels]
+	float* direct = nullptr;       // D[k] per depth (grey), [depth][pixels]
+	unsigned long long* counters = nullptr;     // live paths per depth             [8]
+};
+int wavefrontReserve(WavefrontBuffers& b, size_t pixels);      // cudaError_t as int
+void wavefrontRelease(WavefrontBuffers& b);
+// nextQueue hands out zeroed ticket counters for the trace launches.
+typedef int (*QueueFn)(void* user, cudaStream_t stream, unsigned long long** out);
+cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, const LaunchConfig& cfg, cudaStream_t stream,
+	QueueFn nextQueue, void* user, uint64_t* launches);
 
 } // namespace cbq

@@ -25,6 +25,7 @@
 // pixel and sample: state = hashRay(primary ray) ^ fmix32(frame_id + s), advanced with the CPU
 // tracer's (u32)bit_mix (pathtracing_demo.cpp:67; base.cpp:72-77).
 #include "cbq_internal.h"
+#include "shading.cuh"
 
 namespace cbq {
 
@@ -66,60 +67,6 @@ struct SharedStack {
 	__device__ __forceinline__ void reset() { written = 0u; }
 };
 
-__device__ __forceinline__ uint64_t bitMix64(uint64_t b)   // base.cpp:72-77
-{
-	b = ((b >> 32) ^ b) * 0x0e9846af9b1a615dull;
-	b = ((b >> 32) ^ b) * 0x0e9846af9b1a615dull;
-	return (b >> 28) ^ b;
-}
-
-__device__ __forceinline__ uint32_t fmix32(uint32_t h)   // glsl/pathtracing.frag:287-296
-{
-	h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
-	return h;
-}
-
-__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz)
-{
-	return ((0.0f + ax * bx) + ay * by) + az * bz;   // linalg sum(a*b): fold from 0, left to right
-}
-
-// pathtracing_demo.cpp:62-79
-__device__ __forceinline__ void unitBallPoint(uint32_t& rng, float& x, float& y, float& z)
-{
-	do {
-		rng = (uint32_t)bitMix64((uint64_t)rng);
-		x = (float)(rng & 0x3FFu); y = (float)((rng >> 10) & 0x3FFu); z = (float)((rng >> 20) & 0x3FFu);
-		x = (x - 511.5f) / 511.5f; y = (y - 511.5f) / 511.5f; z = (z - 511.5f) / 511.5f;
-	} while (dot3(x, y, z, x, y, z) >= 1.0f);
-}
-
-// Camera::rayFromViewportPos, camera.cpp:19-35 (same code as in trace_kernels.cu).
-__device__ __forceinline__ void cameraRay(const cbq_camera& c, int x, int y, int width, int height, Ray& out)
-{
-	const double invWidth = (double)(1.0f / (float)width);
-	const double invHeight = (double)(1.0f / (float)height);
-	const float aspect = (float)width / (float)height;
-	const float xOff = ((float)x - ((float)width / 2.0f)) + 0.5f;
-	const float yOff = ((float)y - ((float)height / 2.0f)) + 0.5f;
-	const double kx = ((invWidth * (double)xOff) * (double)aspect) * (double)c.scale;
-	const double ky = (invHeight * (double)yOff) * (double)c.scale;
-	double dir[3];
-#pragma unroll
-	for (int a = 0; a < 3; a++) {
-		double t = c.position[a] + c.forward[a];
-		t += c.right[a] * kx;
-		t -= c.up[a] * ky;
-		dir[a] = t - c.position[a];
-	}
-	const double len = sqrt(((0.0 + dir[0] * dir[0]) + dir[1] * dir[1]) + dir[2] * dir[2]);
-#pragma unroll
-	for (int a = 0; a < 3; a++) {
-		out.o[a] = (float)c.position[a];
-		out.d[a] = (float)(dir[a] / len);
-	}
-}
-
 enum RayKind : int { kKindSurface = 0, kKindSun = 1, kKindSky = 2 };
 
 // What one lane is working on.
@@ -160,8 +107,8 @@ renderPersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict
 	const uint64_t tickets = (uint64_t)tilesX * tilesY * 32u;
 
 	// normalize(vec3(1, -2, 10)) (pathtracing_demo.cpp:89): IEEE sqrt and divides, same bits as the host.
-	const float sunLen = sqrtf(dot3(1.0f, -2.0f, 10.0f, 1.0f, -2.0f, 10.0f));
-	const float sunX = 1.0f / sunLen, sunY = -2.0f / sunLen, sunZ = 10.0f / sunLen;
+	float sunX, sunY, sunZ;
+	sunDirection(sunX, sunY, sunZ);
 
 	RayState s;
 	s.phase = kPhaseIdle;
@@ -172,10 +119,7 @@ renderPersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict
 	// Start sample t.sample of the lane's pixel: primary ray + seed.
 	auto startSample = [&]() {
 		cameraRay(cam, (int)t.x, (int)t.y, (int)p.width, (int)p.height, t.ray);
-		uint32_t h = 0;
-		h ^= fmix32(__float_as_uint(t.ray.o[0])); h ^= fmix32(__float_as_uint(t.ray.o[1])); h ^= fmix32(__float_as_uint(t.ray.o[2]));
-		h ^= fmix32(__float_as_uint(t.ray.d[0])); h ^= fmix32(__float_as_uint(t.ray.d[1])); h ^= fmix32(__float_as_uint(t.ray.d[2]));
-		t.rng = h ^ fmix32(p.frame_id + t.sample);
+		t.rng = pixelSeed(t.ray, p.frame_id + t.sample);
 		t.depth = 0;
 		t.kind = kKindSurface;
 		beginRay(s, t.ray);
@@ -307,22 +251,8 @@ renderPersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict
 					continue;
 				}
 				finishHit(out, t.ray);
-				// surfaceColour (pathtracing_demo.cpp:45-60)
-				const float4 base = __ldg(colours + out.material);
-				float cr = base.x, cg = base.y, cb = base.z;
-				if (p.add_noise) {
-					// positionBasedNoise (:36-43): fnv1a over the 12 bytes of ivec3(position + 0.499)
-					const int cell[3] = { (int)(out.position[0] + 0.499f), (int)(out.position[1] + 0.499f), (int)(out.position[2] + 0.499f) };
-					uint64_t hsh = 0xcbf29ce484222325ull;
-#pragma unroll
-					for (int a = 0; a < 3; a++) {
-#pragma unroll
-						for (int b = 0; b < 4; b++) { hsh ^= (uint64_t)(((uint32_t)cell[a] >> (8 * b)) & 0xffu); hsh *= 0x00000100000001B3ull; }
-					}
-					float noise = (float)((uint32_t)hsh & 0xffu) / 255.0f;
-					noise = (float)(((double)noise * 0.1) + 0.9);
-					cr *= noise; cg *= noise; cb *= noise;
-				}
+				float cr, cg, cb;
+				surfaceColour(colours, out.material, out.position, p.add_noise != 0, cr, cg, cb);
 				colStack[t.depth][0] = cr; colStack[t.depth][1] = cg; colStack[t.depth][2] = cb;
 				dirStack[t.depth][0] = 0.0f; dirStack[t.depth][1] = 0.0f; dirStack[t.depth][2] = 0.0f;
 				t.px = out.position[0]; t.py = out.position[1]; t.pz = out.position[2];

@@ -21,6 +21,7 @@
 //
 // traceSimple -- one thread per ray, stack in local memory; kept as the A/B baseline.
 #include "cbq_internal.h"
+#include "shading.cuh"
 
 namespace cbq {
 
@@ -110,33 +111,6 @@ __device__ __forceinline__ void storeHit(Hit* __restrict__ hits, uint64_t i, con
 	p[4] = make_uint2(__float_as_uint(h.normal[2]), h.status);
 }
 
-// Camera::rayFromViewportPos (reference src/application/commands/view/camera.cpp:19-35) followed by
-// static_cast<Ray3f> (pathtracing_demo.cpp:220). Mixed float/double exactly as written there.
-__device__ __forceinline__ void cameraRay(const cbq_camera& c, int x, int y, int width, int height, Ray& out)
-{
-	const double invWidth = (double)(1.0f / (float)width);
-	const double invHeight = (double)(1.0f / (float)height);
-	const float aspect = (float)width / (float)height;
-	const float xOff = ((float)x - ((float)width / 2.0f)) + 0.5f;
-	const float yOff = ((float)y - ((float)height / 2.0f)) + 0.5f;
-	const double kx = ((invWidth * (double)xOff) * (double)aspect) * (double)c.scale;
-	const double ky = (invHeight * (double)yOff) * (double)c.scale;
-	double dir[3];
-#pragma unroll
-	for (int a = 0; a < 3; a++) {
-		double t = c.position[a] + c.forward[a];
-		t += c.right[a] * kx;
-		t -= c.up[a] * ky;
-		dir[a] = t - c.position[a];
-	}
-	const double len = sqrt(((0.0 + dir[0] * dir[0]) + dir[1] * dir[1]) + dir[2] * dir[2]);
-#pragma unroll
-	for (int a = 0; a < 3; a++) {
-		out.o[a] = (float)c.position[a];
-		out.d[a] = (float)(dir[a] / len);
-	}
-}
-
 // Ray sources. `ticket` is the position in the queue; `slot` is where the result goes.
 struct BufferSource {
 	const Ray* __restrict__ rays;
@@ -145,29 +119,48 @@ struct BufferSource {
 
 struct CameraSource {
 	cbq_camera cam;
-	uint32_t width, height, tilesX;
+	uint32_t width, height;            // the image the camera is defined for
+	uint32_t x0, y0, rectW, rectH;     // the pixel rectangle traced; results are indexed rect-locally
+	uint32_t tilesX;
 	// Tickets enumerate 8x4-pixel tiles row by row, 32 tickets per tile, so the 32 lanes of a warp
-	// start on one compact tile. Tiles overhanging the image produce slot = ~0 (skipped).
+	// start on one compact tile. Tiles overhanging the rectangle produce slot = ~0 (skipped).
 	__device__ __forceinline__ void fetch(uint64_t ticket, Ray& r, uint64_t& slot) const
 	{
 		const uint32_t tile = (uint32_t)(ticket >> 5), within = (uint32_t)ticket & 31u;
 		const uint32_t tx = tile % tilesX, ty = tile / tilesX;
 		const uint32_t x = tx * 8u + (within & 7u), y = ty * 4u + (within >> 3);
-		if (x < width && y < height) {
-			cameraRay(cam, (int)x, (int)y, (int)width, (int)height, r);
-			slot = (uint64_t)y * width + x;
+		if (x < rectW && y < rectH) {
+			cameraRay(cam, (int)(x0 + x), (int)(y0 + y), (int)width, (int)height, r);
+			slot = (uint64_t)y * rectW + x;
 		} else {
 			slot = ~0ull;
 		}
 	}
 };
 
-template <bool kSurface, bool kLodOff, typename Source>
+// Result sinks. FullSink writes the 40-byte record; FlagSink one byte (hit or not), which is all a
+// shadow ray needs (gatherLighting only tests .hit, reference pathtracing_demo.cpp:96,111).
+struct FullSink {
+	Hit* __restrict__ hits;
+	static constexpr bool kNeedsPosition = true;
+	__device__ __forceinline__ void write(uint64_t slot, const Hit& h) const { storeHit(hits, slot, h); }
+};
+struct FlagSink {
+	uint8_t* __restrict__ flags;
+	static constexpr bool kNeedsPosition = false;
+	__device__ __forceinline__ void write(uint64_t slot, const Hit& h) const { flags[slot] = (uint8_t)h.hit; }
+};
+
+template <bool kSurface, bool kLodOff, typename Source, typename Sink>
 __global__ void __launch_bounds__(256, 4)
 tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict__ subdagsGlobal, Source source,
-	Hit* __restrict__ hits, uint64_t count, float maxFootprint, int refillThreshold,
+	Sink sink, uint64_t count, const unsigned long long* __restrict__ countPtr, uint32_t countScale,
+	float maxFootprint, int refillThreshold,
 	unsigned long long* __restrict__ queue, unsigned long long* __restrict__ abandoned)
 {
+	// The batch size may live on the device (wavefront path tracer: the number of surviving paths is
+	// produced by the previous kernel), so no host round trip is needed between bounces.
+	if (countPtr) count = (uint64_t)(*countPtr) * countScale;
 	extern __shared__ uint32_t stackMem[];
 	__shared__ SubDag subdags[8];
 	if (threadIdx.x < 64) reinterpret_cast<uint32_t*>(subdags)[threadIdx.x] = reinterpret_cast<const uint32_t*>(subdagsGlobal)[threadIdx.x];
@@ -231,14 +224,16 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 				if (res == kStepHit) {
 					if (!kSurface) { out.material = 0; out.normal[0] = out.normal[1] = out.normal[2] = 0.0f; }
 					out.status = 0;
-					Ray r; uint64_t again;
-					source.fetch(ticketOfRay, r, again);   // the un-reflected ray, for position = o + d * t
-					finishHit(out, r);
+					if (Sink::kNeedsPosition) {
+						Ray r; uint64_t again;
+						source.fetch(ticketOfRay, r, again);   // the un-reflected ray, for position = o + d * t
+						finishHit(out, r);
+					}
 				} else {
 					clearHit(out);
 					if (res == kStepAbandoned) { out.status = CBQ_HIT_ABANDONED; atomicAdd(abandoned, 1ull); }
 				}
-				storeHit(hits, slot, out);
+				sink.write(slot, out);
 				s.phase = kPhaseIdle;
 			}
 		}
@@ -278,27 +273,38 @@ primaryRays(cbq_camera cam, uint32_t width, uint32_t height, Ray* __restrict__ r
 	}
 }
 
-template <bool kSurface, bool kLodOff, typename Source>
-cudaError_t launchPersistentImpl(const TraceArgs& a, const Source& src, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
+template <bool kSurface, bool kLodOff, typename Source, typename Sink>
+cudaError_t launchPersistentImpl(const TraceArgs& a, const Source& src, const Sink& sink, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
 {
-	auto kernel = tracePersistent<kSurface, kLodOff, Source>;
+	auto kernel = tracePersistent<kSurface, kLodOff, Source, Sink>;
 	const size_t smem = (size_t)cfg.stackLevels * (size_t)cfg.blockThreads * sizeof(uint32_t);
 	cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	int grid = cfg.smCount * cfg.blocksPerSm;
 	const uint64_t needed = (tickets + (uint64_t)cfg.blockThreads - 1) / (uint64_t)cfg.blockThreads;
-	if ((uint64_t)grid > needed) grid = (int)(needed ? needed : 1);
-	kernel<<<grid, cfg.blockThreads, smem, stream>>>(a.nodes, a.subdags, src, a.hits, tickets, a.maxFootprint,
+	if (!a.countPtr && (uint64_t)grid > needed) grid = (int)(needed ? needed : 1);
+	kernel<<<grid, cfg.blockThreads, smem, stream>>>(a.nodes, a.subdags, src, sink, tickets, a.countPtr, a.countScale, a.maxFootprint,
 		cfg.refillThreshold, a.queue, a.abandoned);
 	return cudaGetLastError();
 }
 
-template <bool kSurface, typename Source>
-cudaError_t launchPersistent(const TraceArgs& a, const Source& src, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
+template <bool kSurface, typename Source, typename Sink>
+cudaError_t launchPersistentLod(const TraceArgs& a, const Source& src, const Sink& sink, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
 {
 	// maxFootprint == -1 exactly (MAX_FOOTPRINT_DISABLED) selects the division-free LOD test.
-	if (a.maxFootprint == CBQ_MAX_FOOTPRINT_DISABLED) return launchPersistentImpl<kSurface, true>(a, src, tickets, cfg, stream);
-	return launchPersistentImpl<kSurface, false>(a, src, tickets, cfg, stream);
+	if (a.maxFootprint == CBQ_MAX_FOOTPRINT_DISABLED) return launchPersistentImpl<kSurface, true>(a, src, sink, tickets, cfg, stream);
+	return launchPersistentImpl<kSurface, false>(a, src, sink, tickets, cfg, stream);
+}
+
+template <typename Source>
+cudaError_t launchPersistent(const TraceArgs& a, bool surface, const Source& src, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
+{
+	if (a.flags) {
+		// Flag-only results are for shadow rays, which never ask for surface properties.
+		return launchPersistentLod<false>(a, src, FlagSink{ a.flags }, tickets, cfg, stream);
+	}
+	return surface ? launchPersistentLod<true>(a, src, FullSink{ a.hits }, tickets, cfg, stream)
+	               : launchPersistentLod<false>(a, src, FullSink{ a.hits }, tickets, cfg, stream);
 }
 
 } // namespace
@@ -307,11 +313,13 @@ cudaError_t launchTrace(const TraceArgs& a, bool surface, const LaunchConfig& cf
 {
 	if (a.rays == nullptr) {
 		CameraSource src;
-		src.cam = a.camera; src.width = a.width; src.height = a.height; src.tilesX = (a.width + 7u) / 8u;
-		const uint64_t tickets = (uint64_t)src.tilesX * ((a.height + 3u) / 4u) * 32u;
-		return surface ? launchPersistent<true>(a, src, tickets, cfg, stream) : launchPersistent<false>(a, src, tickets, cfg, stream);
+		src.cam = a.camera; src.width = a.width; src.height = a.height;
+		src.x0 = a.x0; src.y0 = a.y0; src.rectW = a.rectW ? a.rectW : a.width; src.rectH = a.rectH ? a.rectH : a.height;
+		src.tilesX = (src.rectW + 7u) / 8u;
+		const uint64_t tickets = (uint64_t)src.tilesX * ((src.rectH + 3u) / 4u) * 32u;
+		return launchPersistent(a, surface, src, tickets, cfg, stream);
 	}
-	if (cfg.kernel == 1) {
+	if (cfg.kernel == 1 && !a.countPtr && !a.flags) {
 		const int block = 128;
 		uint64_t blocks = (a.count + block - 1) / block;
 		const uint64_t cap = (uint64_t)cfg.smCount * 64u;
@@ -322,7 +330,7 @@ cudaError_t launchTrace(const TraceArgs& a, bool surface, const LaunchConfig& cf
 		return cudaGetLastError();
 	}
 	BufferSource src{ a.rays };
-	return surface ? launchPersistent<true>(a, src, a.count, cfg, stream) : launchPersistent<false>(a, src, a.count, cfg, stream);
+	return launchPersistent(a, surface, src, a.count, cfg, stream);
 }
 
 cudaError_t launchPrimaryRays(const cbq_camera& cam, uint32_t width, uint32_t height, Ray* rays, cudaStream_t stream)

@@ -177,8 +177,9 @@ int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_para
 int cbq_host_alloc(void** out, uint64_t bytes);
 int cbq_host_free(void* p);
 
-/* Options: "block_threads", "blocks_per_sm", "refill_threshold", "l2_persist" (0/1),
- * "kernel" (0 = persistent queue kernel, 1 = plain one-thread-per-ray), "sort_rays" (0/1). */
+/* Options: "block_threads", "blocks_per_sm", "refill_threshold" (idle lanes of a warp that trigger a
+ * mid-flight refill, 1..32), "l2_persist" (0/1), "kernel" (0 = persistent queue kernel, 1 = plain
+ * one-thread-per-ray), "render_mode" (0 = wavefront path tracer, 1 = persistent megakernel). */
 int cbq_set_option(cbq_context* ctx, const char* key, int64_t value);
 int cbq_get_option(cbq_context* ctx, const char* key, int64_t* value);
 

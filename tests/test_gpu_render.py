@@ -108,3 +108,22 @@ def test_render_device_pointer_and_sample_sharding(gpu, port, api, scenes):
     gpu.render_device(cam, api.pt_params(w, h, spp=4, bounces=1, variant=1), c.data_ptr(), stream)
     torch.cuda.synchronize()
     assert np.array_equal(c.cpu().numpy(), whole)
+
+
+@pytest.mark.parametrize("variant,bounces", [(0, 1), (1, 0), (1, 3)])
+def test_wavefront_and_megakernel_agree_bit_for_bit(gpu, port, api, scenes, variant, bounces):
+    """render_mode 0 (per-bounce kernels, compaction between bounces) and 1 (one persistent kernel) are two
+    schedules of the same arithmetic: identical images, including the one-bounce variant's powf."""
+    sc = scenes("soup", 8)
+    gpu.upload(sc.nodes, sc.root, sc.colours)
+    cam, _ = both_cameras(api, port, sc)
+    p = api.pt_params(200, 120, spp=3, bounces=bounces, variant=variant, rect=(8, 4, 197, 118))
+    imgs = []
+    try:
+        for mode in (0, 1):
+            gpu.set_option("render_mode", mode)
+            imgs.append(gpu.render(cam, p))
+    finally:
+        gpu.set_option("render_mode", 0)
+    assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32))
+    assert imgs[0][4:118, 8:197].std() > 0.05 and not imgs[0][:4].any() and not imgs[0][:, :8].any()
