@@ -537,8 +537,10 @@ int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_para
 		return CBQ_OK;
 	}
 	const size_t pixels = (size_t)(p->x1 - p->x0) * (p->y1 - p->y0);
-	if (pixels > ctx->wavefront.pixelCapacity) CBQ_CUDA(cudaDeviceSynchronize());   // buffers may still be in use
-	CBQ_CUDA((cudaError_t)cbq::wavefrontReserve(ctx->wavefront, pixels));
+	const size_t paths = pixels * std::min<size_t>(p->spp, cbq::wavefrontGroupSize());
+	if (paths > 0xffffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "rectangle too large for 32-bit path ids");
+	if (paths > ctx->wavefront.pixelCapacity) CBQ_CUDA(cudaDeviceSynchronize());   // buffers may still be in use
+	CBQ_CUDA((cudaError_t)cbq::wavefrontReserve(ctx->wavefront, paths));
 	struct Adaptor { static int next(void* user, cudaStream_t st, unsigned long long** out) { return nextQueue(static_cast<cbq_context*>(user), st, out); } };
 	CBQ_CUDA(cbq::launchRenderWavefront(a, ctx->wavefront, ctx->cfg, s, &Adaptor::next, ctx, &ctx->launches));
 	return CBQ_OK;

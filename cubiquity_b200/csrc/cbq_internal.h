@@ -76,7 +76,7 @@ cudaError_t launchRender(const RenderArgs& a, const LaunchConfig& cfg, cudaStrea
 
 // Wavefront path tracer (wavefront_kernels.cu): per-bounce kernels around the ray-cast kernel.
 struct WavefrontBuffers {
-	size_t pixelCapacity = 0;      // pixels of the largest rectangle rendered so far
+	size_t pixelCapacity = 0;      // PATHS (pixels x samples per group) of the largest wave so far; all sizes below are in paths
 	Hit* hits = nullptr;           // surface hits of the current depth            [pixels]
 	Ray* rays[2] = { nullptr, nullptr };        // bounce rays, ping-pong           [pixels]
 	uint32_t* pixel[2] = { nullptr, nullptr };  // rect-local pixel id of each path [pixels]
@@ -86,9 +86,11 @@ struct WavefrontBuffers {
 	uint8_t* shadowFlags = nullptr;//                                              [2 * pixels]
 	float* colour = nullptr;       // c[k] per depth, SoA [depth][3][pixels]
 	float* direct = nullptr;       // D[k] per depth (grey), [depth][pixels]
+	float* radiance = nullptr;     // finished radiance of each path, SoA [3][pixels]
 	unsigned long long* counters = nullptr;     // live paths per depth             [8]
 };
-int wavefrontReserve(WavefrontBuffers& b, size_t pixels);      // cudaError_t as int
+int wavefrontReserve(WavefrontBuffers& b, size_t paths);       // cudaError_t as int
+uint32_t wavefrontGroupSize();
 void wavefrontRelease(WavefrontBuffers& b);
 // nextQueue hands out zeroed ticket counters for the trace launches.
 typedef int (*QueueFn)(void* user, cudaStream_t stream, unsigned long long** out);

@@ -4,7 +4,11 @@
 //
 // COMPILE WITH -fmad=false.
 //
-// One "wave" = one sample of every pixel of the requested rectangle. Per depth d:
+// One "wave" = a GROUP of up to kGroup samples of every pixel of the requested rectangle, traced
+// together so that the deeper, thinner bounces still fill the machine; the samples of a group share
+// one primary-ray trace (same pixel, same ray). Each path writes its radiance to its own slot and a
+// final kernel adds the group's samples to the image IN SAMPLE ORDER, so the result is bit-identical
+// to tracing the samples one after another. Per depth d:
 //
 //   trace   surface rays of depth d  (d = 0: straight from the camera, 8x4-pixel tiles; d > 0: the
 //           compacted bounce-ray buffer)                         tracePersistent<surface>  -> 40-byte hits
@@ -33,23 +37,25 @@ namespace {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kMaxDepth = 6;   // bounces <= 5
+constexpr uint32_t kGroup = 4; // samples traced together
 
 struct WaveParams {
 	cbq_camera cam;
 	cbq_pt_params p;
 	uint32_t rectW, rectH;
 	uint32_t pixels;          // rectW * rectH
-	uint32_t sampleIndex;     // frame_id + s
+	uint32_t paths;           // pixels * samples in this group; path id = sample * pixels + pixel
+	uint32_t sampleIndex;     // frame_id + index of the group's first sample
 	int depth;
 	int lastDepth;            // paths alive after the lighting of this depth end here
 	uint32_t shadowsPerPath;  // include_sun + include_sky
 };
 
-// Fold a finished path back to front (pathtracing_demo.cpp:143, :182-185) and add it to its pixel.
+// Fold a finished path back to front (pathtracing_demo.cpp:143, :182-185) into its radiance slot.
 __device__ __forceinline__ void finishPath(const WaveParams& w, const float* __restrict__ colour, const float* __restrict__ direct,
-	float* __restrict__ accum, uint32_t pixel, int levels, float r, float g, float b)
+	float* __restrict__ radiance, uint32_t pixel /* path id */, int levels, float r, float g, float b)
 {
-	const size_t n = w.pixels;
+	const size_t n = w.paths;
 	if (w.p.variant == CBQ_VARIANT_RECURSIVE) {
 		for (int k = levels - 1; k >= 0; k--) {
 			const float d = direct[(size_t)k * n + pixel];
@@ -70,19 +76,35 @@ __device__ __forceinline__ void finishPath(const WaveParams& w, const float* __r
 		const float gamma = (float)(1.0 / 2.2);
 		r = powf(r, gamma); g = powf(g, gamma); b = powf(b, gamma);
 	}
-	const uint32_t x = w.p.x0 + pixel % w.rectW, y = w.p.y0 + pixel / w.rectW;
-	float* px = accum + 3ull * ((uint64_t)y * w.p.width + x);
-	px[0] += r; px[1] += g; px[2] += b;
+	radiance[pixel] = r; radiance[n + pixel] = g; radiance[2 * n + pixel] = b;
+}
+
+// mImage[...] += pixel (pathtracing_demo.cpp:224), the group's samples in order.
+__global__ void __launch_bounds__(256)
+accumulateKernel(WaveParams w, const float* __restrict__ radiance, float* __restrict__ accum)
+{
+	const size_t n = w.paths;
+	const uint32_t samples = w.paths / w.pixels;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < w.pixels; i += gridDim.x * blockDim.x) {
+		const uint32_t x = w.p.x0 + i % w.rectW, y = w.p.y0 + i / w.rectW;
+		float* px = accum + 3ull * ((uint64_t)y * w.p.width + x);
+		float r = px[0], g = px[1], b = px[2];
+		for (uint32_t s = 0; s < samples; s++) {
+			const size_t id = (size_t)s * w.pixels + i;
+			r += radiance[id]; g += radiance[n + id]; b += radiance[2 * n + id];
+		}
+		px[0] = r; px[1] = g; px[2] = b;
+	}
 }
 
 __global__ void __launch_bounds__(256)
 shadeKernel(WaveParams w, const float4* __restrict__ colours, const Hit* __restrict__ hits,
 	const uint32_t* __restrict__ pathPixel, const uint32_t* __restrict__ pathRng, const unsigned long long* __restrict__ pathCount,
-	float* __restrict__ colour, float* __restrict__ direct, float* __restrict__ accum,
+	float* __restrict__ colour, float* __restrict__ direct, float* __restrict__ accum /* radiance slots */,
 	unsigned long long* __restrict__ liveCount, uint32_t* __restrict__ livePixel, uint32_t* __restrict__ liveRng,
 	float* __restrict__ sunTerm, Ray* __restrict__ shadowRays, Ray* __restrict__ bounceRays)
 {
-	const uint64_t count = (w.depth == 0) ? (uint64_t)w.pixels : (uint64_t)(*pathCount);
+	const uint64_t count = (w.depth == 0) ? (uint64_t)w.paths : (uint64_t)(*pathCount);
 	const unsigned lane = threadIdx.x & 31u;
 	float sunX, sunY, sunZ;
 	sunDirection(sunX, sunY, sunZ);
@@ -94,16 +116,18 @@ shadeKernel(WaveParams w, const float4* __restrict__ colours, const Hit* __restr
 		uint32_t pixel = 0, rng = 0;
 		Hit h;
 		if (i < count) {
-			pixel = (w.depth == 0) ? (uint32_t)i : pathPixel[i];
-			const uint2* hp = reinterpret_cast<const uint2*>(hits + i);
+			pixel = (w.depth == 0) ? (uint32_t)i : pathPixel[i];   // the path id
+			// depth 0: every sample of a pixel shares the pixel's primary hit
+			const uint2* hp = reinterpret_cast<const uint2*>(hits + ((w.depth == 0) ? (i % w.pixels) : i));
 			const uint2 a = hp[0], b = hp[1], c = hp[2], d = hp[3], e = hp[4];
 			h.hit = a.x; h.distance = __uint_as_float(a.y); h.material = b.x;
 			h.position[0] = __uint_as_float(b.y); h.position[1] = __uint_as_float(c.x); h.position[2] = __uint_as_float(c.y);
 			h.normal[0] = __uint_as_float(d.x); h.normal[1] = __uint_as_float(d.y); h.normal[2] = __uint_as_float(e.x);
 			if (w.depth == 0) {
+				const uint32_t pix = pixel % w.pixels, sample = pixel / w.pixels;
 				Ray r;
-				cameraRay(w.cam, (int)(w.p.x0 + pixel % w.rectW), (int)(w.p.y0 + pixel / w.rectW), (int)w.p.width, (int)w.p.height, r);
-				rng = pixelSeed(r, w.sampleIndex);
+				cameraRay(w.cam, (int)(w.p.x0 + pix % w.rectW), (int)(w.p.y0 + pix / w.rectW), (int)w.p.width, (int)w.p.height, r);
+				rng = pixelSeed(r, w.sampleIndex + sample);
 			} else {
 				rng = pathRng[i];
 			}
@@ -126,7 +150,7 @@ shadeKernel(WaveParams w, const float4* __restrict__ colours, const Hit* __restr
 		// surfaceColour (pathtracing_demo.cpp:45-60)
 		float cr, cg, cb;
 		surfaceColour(colours, h.material, h.position, w.p.add_noise != 0, cr, cg, cb);
-		const size_t n = w.pixels;
+		const size_t n = w.paths;
 		colour[((size_t)w.depth * 3 + 0) * n + pixel] = cr;
 		colour[((size_t)w.depth * 3 + 1) * n + pixel] = cg;
 		colour[((size_t)w.depth * 3 + 2) * n + pixel] = cb;
@@ -179,7 +203,7 @@ lightKernel(WaveParams w, const unsigned long long* __restrict__ liveCount, cons
 		uint32_t k = 0;
 		if (w.p.include_sun) { if (!shadowFlags[j * w.shadowsPerPath + k]) d += sunTerm[j]; k++; }   // :96-99
 		if (w.p.include_sky) { if (!shadowFlags[j * w.shadowsPerPath + k]) d += 1.5f; }              // :111-114
-		direct[(size_t)w.depth * w.pixels + pixel] = d;
+		direct[(size_t)w.depth * w.paths + pixel] = d;
 		if (w.depth == w.lastDepth) finishPath(w, colour, direct, accum, pixel, w.depth + 1, 0.0f, 0.0f, 0.0f);
 	}
 }
@@ -194,7 +218,9 @@ cudaError_t grow(T*& p, size_t count)
 
 } // namespace
 
-int wavefrontReserve(WavefrontBuffers& b, size_t pixels)
+uint32_t wavefrontGroupSize() { return kGroup; }
+
+int wavefrontReserve(WavefrontBuffers& b, size_t pixels /* paths */)
 {
 	if (pixels <= b.pixelCapacity) return (int)cudaSuccess;
 	cudaError_t e;
@@ -206,6 +232,7 @@ int wavefrontReserve(WavefrontBuffers& b, size_t pixels)
 	CBQ_TRY(grow(b.shadowFlags, 2 * pixels));
 	CBQ_TRY(grow(b.colour, (size_t)kMaxDepth * 3 * pixels));
 	CBQ_TRY(grow(b.direct, (size_t)kMaxDepth * pixels));
+	CBQ_TRY(grow(b.radiance, 3 * pixels));
 	if (!b.counters) CBQ_TRY(cudaMalloc(&b.counters, 8 * sizeof(unsigned long long)));
 #undef CBQ_TRY
 	b.pixelCapacity = pixels;
@@ -216,7 +243,7 @@ void wavefrontRelease(WavefrontBuffers& b)
 {
 	cudaFree(b.hits);
 	for (int i = 0; i < 2; i++) { cudaFree(b.rays[i]); cudaFree(b.pixel[i]); cudaFree(b.rng[i]); }
-	cudaFree(b.sunTerm); cudaFree(b.shadowRays); cudaFree(b.shadowFlags); cudaFree(b.colour); cudaFree(b.direct); cudaFree(b.counters);
+	cudaFree(b.sunTerm); cudaFree(b.shadowRays); cudaFree(b.shadowFlags); cudaFree(b.colour); cudaFree(b.direct); cudaFree(b.radiance); cudaFree(b.counters);
 	b = WavefrontBuffers();
 }
 
@@ -236,8 +263,10 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 	const int shadeGrid = cfg.smCount * 8;
 	LaunchConfig surfaceCfg = cfg, shadowCfg = cfg;
 	cudaError_t e;
-	for (uint32_t s = 0; s < p.spp; s++) {
-		w.sampleIndex = p.frame_id + s;
+	for (uint32_t s0 = 0; s0 < p.spp; s0 += kGroup) {
+		const uint32_t group = (p.spp - s0 < kGroup) ? (p.spp - s0) : kGroup;
+		w.sampleIndex = p.frame_id + s0;
+		w.paths = w.pixels * group;
 		e = cudaMemsetAsync(b.counters, 0, 8 * sizeof(unsigned long long), stream);
 		if (e != cudaSuccess) return e;
 		for (int d = 0; d <= w.lastDepth; d++) {
@@ -249,18 +278,19 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 			t.nodes = a.nodes; t.subdags = a.subdags; t.hits = b.hits; t.maxFootprint = p.max_footprint; t.abandoned = a.abandoned;
 			if (nextQueue(user, stream, &t.queue) != 0) return cudaErrorUnknown;
 			if (d == 0) {
+				// one primary ray per PIXEL: the samples of the group share it
 				t.rays = nullptr; t.camera = a.camera; t.width = p.width; t.height = p.height;
 				t.x0 = p.x0; t.y0 = p.y0; t.rectW = w.rectW; t.rectH = w.rectH; t.count = w.pixels;
 				surfaceCfg.refillThreshold = 32;           // coherent tiles
 			} else {
-				t.rays = b.rays[cur]; t.countPtr = b.counters + (d - 1); t.countScale = 1; t.count = w.pixels;
+				t.rays = b.rays[cur]; t.countPtr = b.counters + (d - 1); t.countScale = 1; t.count = w.paths;
 				surfaceCfg.refillThreshold = cfg.refillThreshold;
 			}
 			e = launchTrace(t, true, surfaceCfg, stream);
 			if (e != cudaSuccess) return e;
 			// ---- shade + compact + spawn
 			shadeKernel<<<shadeGrid, 256, 0, stream>>>(w, a.colours, b.hits, b.pixel[cur], b.rng[cur], d ? b.counters + (d - 1) : nullptr,
-				b.colour, b.direct, a.accum, b.counters + d, b.pixel[nxt], b.rng[nxt], b.sunTerm, b.shadowRays, b.rays[nxt]);
+				b.colour, b.direct, b.radiance, b.counters + d, b.pixel[nxt], b.rng[nxt], b.sunTerm, b.shadowRays, b.rays[nxt]);
 			e = cudaGetLastError();
 			if (e != cudaSuccess) return e;
 			*launches += 2;
@@ -270,17 +300,21 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 				memset(&sh, 0, sizeof(sh));
 				sh.nodes = a.nodes; sh.subdags = a.subdags; sh.rays = b.shadowRays; sh.flags = b.shadowFlags;
 				sh.maxFootprint = p.max_footprint; sh.abandoned = a.abandoned;
-				sh.countPtr = b.counters + d; sh.countScale = w.shadowsPerPath; sh.count = (uint64_t)w.pixels * w.shadowsPerPath;
+				sh.countPtr = b.counters + d; sh.countScale = w.shadowsPerPath; sh.count = (uint64_t)w.paths * w.shadowsPerPath;
 				if (nextQueue(user, stream, &sh.queue) != 0) return cudaErrorUnknown;
 				e = launchTrace(sh, false, shadowCfg, stream);
 				if (e != cudaSuccess) return e;
 				*launches += 1;
 			}
-			lightKernel<<<shadeGrid, 256, 0, stream>>>(w, b.counters + d, b.pixel[nxt], b.sunTerm, b.shadowFlags, b.colour, b.direct, a.accum);
+			lightKernel<<<shadeGrid, 256, 0, stream>>>(w, b.counters + d, b.pixel[nxt], b.sunTerm, b.shadowFlags, b.colour, b.direct, b.radiance);
 			e = cudaGetLastError();
 			if (e != cudaSuccess) return e;
 			*launches += 1;
 		}
+		accumulateKernel<<<shadeGrid, 256, 0, stream>>>(w, b.radiance, a.accum);
+		e = cudaGetLastError();
+		if (e != cudaSuccess) return e;
+		*launches += 1;
 	}
 	return cudaSuccess;
 }
