@@ -285,6 +285,7 @@ int cbq_create(int device, cbq_context** out)
 	ctx->cfg.refillThreshold = 8;    // robust default: +68 % on incoherent rays, -7 % on coherent ones (profiles/r01_sweeps.md)
 	ctx->cfg.kernel = 0;
 	ctx->cfg.stackLevels = 33;
+	ctx->cfg.sampleGroup = 4;
 	*out = ctx;
 	return CBQ_OK;
 }
@@ -537,7 +538,7 @@ int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_para
 		return CBQ_OK;
 	}
 	const size_t pixels = (size_t)(p->x1 - p->x0) * (p->y1 - p->y0);
-	const size_t paths = pixels * std::min<size_t>(p->spp, cbq::wavefrontGroupSize());
+	const size_t paths = pixels * std::min<size_t>(p->spp, (size_t)ctx->cfg.sampleGroup);
 	if (paths > 0xffffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "rectangle too large for 32-bit path ids");
 	if (paths > ctx->wavefront.pixelCapacity) CBQ_CUDA(cudaDeviceSynchronize());   // buffers may still be in use
 	CBQ_CUDA((cudaError_t)cbq::wavefrontReserve(ctx->wavefront, paths));
@@ -596,6 +597,9 @@ int cbq_set_option(cbq_context* ctx, const char* key, int64_t value)
 	} else if (k == "kernel") {
 		if (value < 0 || value > 1) return fail(CBQ_ERROR_INVALID_ARGUMENT, "kernel must be 0 or 1");
 		ctx->cfg.kernel = (int)value;
+	} else if (k == "sample_group") {
+		if (value < 1 || value > 16) return fail(CBQ_ERROR_INVALID_ARGUMENT, "sample_group must be in [1, 16]");
+		ctx->cfg.sampleGroup = (int)value;
 	} else if (k == "render_mode") {
 		if (value < 0 || value > 1) return fail(CBQ_ERROR_INVALID_ARGUMENT, "render_mode must be 0 (wavefront) or 1 (megakernel)");
 		ctx->renderMode = (int)value;
@@ -618,6 +622,7 @@ int cbq_get_option(cbq_context* ctx, const char* key, int64_t* value)
 	else if (k == "kernel") *value = ctx->cfg.kernel;
 	else if (k == "l2_persist") *value = ctx->l2Persist;
 	else if (k == "render_mode") *value = ctx->renderMode;
+	else if (k == "sample_group") *value = ctx->cfg.sampleGroup;
 	else if (k == "sm_count") *value = ctx->cfg.smCount;
 	else if (k == "stack_levels") *value = ctx->cfg.stackLevels;
 	else if (k == "l2_bytes") *value = ctx->prop.l2CacheSize;

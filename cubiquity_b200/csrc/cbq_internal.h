@@ -38,6 +38,7 @@ struct LaunchConfig {
 	int refillThreshold;   // idle lanes in a warp that trigger a refill from the ray queue (1..32)
 	int kernel;            // 0 persistent queue kernel, 1 one-thread-per-ray
 	int stackLevels;       // entries per lane in the shared-memory stack (max sub-DAG height + 1)
+	int sampleGroup;       // wavefront path tracer: samples of a pixel traced together (1..16)
 };
 
 struct TraceArgs {
@@ -90,7 +91,6 @@ struct WavefrontBuffers {
 	unsigned long long* counters = nullptr;     // live paths per depth             [8]
 };
 int wavefrontReserve(WavefrontBuffers& b, size_t paths);       // cudaError_t as int
-uint32_t wavefrontGroupSize();
 void wavefrontRelease(WavefrontBuffers& b);
 // nextQueue hands out zeroed ticket counters for the trace launches.
 typedef int (*QueueFn)(void* user, cudaStream_t stream, unsigned long long** out);

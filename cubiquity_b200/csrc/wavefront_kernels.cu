@@ -4,7 +4,7 @@
 //
 // COMPILE WITH -fmad=false.
 //
-// One "wave" = a GROUP of up to kGroup samples of every pixel of the requested rectangle, traced
+// One "wave" = a GROUP of up to `sample_group` (default 4) samples of every pixel of the requested rectangle, traced
 // together so that the deeper, thinner bounces still fill the machine; the samples of a group share
 // one primary-ray trace (same pixel, same ray). Each path writes its radiance to its own slot and a
 // final kernel adds the group's samples to the image IN SAMPLE ORDER, so the result is bit-identical
@@ -37,7 +37,6 @@ namespace {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kMaxDepth = 6;   // bounces <= 5
-constexpr uint32_t kGroup = 4; // samples traced together
 
 struct WaveParams {
 	cbq_camera cam;
@@ -218,8 +217,6 @@ cudaError_t grow(T*& p, size_t count)
 
 } // namespace
 
-uint32_t wavefrontGroupSize() { return kGroup; }
-
 int wavefrontReserve(WavefrontBuffers& b, size_t pixels /* paths */)
 {
 	if (pixels <= b.pixelCapacity) return (int)cudaSuccess;
@@ -263,6 +260,7 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 	const int shadeGrid = cfg.smCount * 8;
 	LaunchConfig surfaceCfg = cfg, shadowCfg = cfg;
 	cudaError_t e;
+	const uint32_t kGroup = (uint32_t)(cfg.sampleGroup > 0 ? cfg.sampleGroup : 1);
 	for (uint32_t s0 = 0; s0 < p.spp; s0 += kGroup) {
 		const uint32_t group = (p.spp - s0 < kGroup) ? (p.spp - s0) : kGroup;
 		w.sampleIndex = p.frame_id + s0;

@@ -43,9 +43,10 @@ def time_config(ctx, d_rays, n, d_hits, flush, stream, steps=10, mf=-1.0, surfac
 def render_sweep(ctx, scene, dev, stream):
     cam = api.default_camera(scene.lower, scene.upper)
     acc = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
-    for mode, variant, bounces, spp, thr in [(0, 1, 4, 4, 8), (0, 1, 4, 4, 32), (0, 1, 4, 4, 4), (0, 1, 1, 4, 8), (0, 0, 1, 4, 8),
-                                             (1, 1, 4, 4, 8), (1, 1, 1, 4, 8), (1, 0, 1, 4, 8), (0, 1, 4, 16, 8)]:
+    for mode, variant, bounces, spp, thr, grp in [(0, 1, 4, 16, 8, 1), (0, 1, 4, 16, 8, 2), (0, 1, 4, 16, 8, 4), (0, 1, 4, 16, 8, 8), (0, 1, 4, 16, 8, 16),
+                                                  (0, 1, 4, 16, 4, 8), (0, 1, 4, 16, 2, 8), (0, 1, 1, 16, 8, 8), (0, 0, 1, 16, 8, 8), (1, 1, 4, 4, 8, 4)]:
         ctx.set_option("render_mode", mode)
+        ctx.set_option("sample_group", grp)
         ctx.set_option("refill_threshold", thr)
         p = api.pt_params(W, H, spp=spp, bounces=bounces, variant=variant)
         ctx.render_device(cam, api.pt_params(W, H, spp=1, bounces=bounces, variant=variant), acc.data_ptr(), stream)
@@ -59,7 +60,7 @@ def render_sweep(ctx, scene, dev, stream):
             times.append(a.elapsed_time(b))
         ms = float(np.median(times))
         print(json.dumps({"workload": "render", "lib": os.environ.get("CBQ_LIBRARY", "default"), "mode": "wavefront" if mode == 0 else "megakernel", "variant": variant, "bounces": bounces, "spp": spp,
-                          "refill_threshold": thr, "ms": round(ms, 3), "mspp_per_s": round(W * H * spp / ms / 1e3, 1),
+                          "refill_threshold": thr, "sample_group": grp, "ms": round(ms, 3), "mspp_per_s": round(W * H * spp / ms / 1e3, 1),
                           "mean": round(float(acc.mean().item()) / spp, 5)}), flush=True)
 
 

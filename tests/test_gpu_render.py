@@ -127,3 +127,19 @@ def test_wavefront_and_megakernel_agree_bit_for_bit(gpu, port, api, scenes, vari
         gpu.set_option("render_mode", 0)
     assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32))
     assert imgs[0][4:118, 8:197].std() > 0.05 and not imgs[0][:4].any() and not imgs[0][:, :8].any()
+
+
+def test_sample_group_size_does_not_change_the_image(gpu, port, api, scenes):
+    sc = scenes("sphere_noise", 7)
+    gpu.upload(sc.nodes, sc.root, sc.colours)
+    cam, _ = both_cameras(api, port, sc)
+    p = api.pt_params(120, 90, spp=7, bounces=2, variant=1)
+    imgs = []
+    try:
+        for g in (1, 3, 4, 16):
+            gpu.set_option("sample_group", g)
+            imgs.append(gpu.render(cam, p))
+    finally:
+        gpu.set_option("sample_group", 4)
+    for im in imgs[1:]:
+        assert np.array_equal(im.view(np.uint32), imgs[0].view(np.uint32))
