@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--option", action="append", default=[], help="key=value passed to cbq_set_option")
     ap.add_argument("--spp", type=int, default=4)
     ap.add_argument("--bounces", type=int, default=4)
-    ap.add_argument("--random-rays", type=int, default=8_000_000)
+    ap.add_argument("--random-rays", type=int, default=100_000_000)
     return ap.parse_args()
 
 
@@ -175,10 +175,110 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def pathtrace_workload(args):
+    """--workload pathtrace: tile-sharded 1080p path tracing (BASELINE metric "1080p spp/s", config 4 style:
+    recursive bounce loop, `--bounces` bounces, `--spp` samples, LOD 0.0035). Strong scaling: the frame's
+    64-row tile bands are dealt round-robin to the ranks, the DAG is replicated, and ONE collective -- a sum of
+    the disjoint partial images onto rank 0 -- ends the frame (inside the timed region)."""
+    import torch
+    import torch.distributed as dist
+    from cubiquity_b200 import api, sharding
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    kind, log2 = ("terrain", args.scene_log2)
+    scene = api.Scene(kind, log2, SCENE_SEED) if rank == 0 else None
+    if world > 1:
+        nodes, root = sharding.broadcast_volume(dist, scene.nodes if rank == 0 else None, scene.root if rank == 0 else None, device=dev)
+        meta = torch.zeros(6, dtype=torch.int64, device=dev)
+        col = torch.zeros(256, 3, device=dev)
+        if rank == 0:
+            meta[:3] = torch.from_numpy(scene.lower.astype(np.int64)); meta[3:] = torch.from_numpy(scene.upper.astype(np.int64))
+            col = torch.from_numpy(scene.colours.copy()).to(dev)
+        dist.broadcast(meta, src=0); dist.broadcast(col, src=0)
+        lower, upper, colours = meta[:3].cpu().numpy(), meta[3:].cpu().numpy(), col.cpu().numpy()
+    else:
+        nodes, root, lower, upper, colours = scene.nodes, scene.root, scene.lower, scene.upper, scene.colours
+    ctx = api.Context(local)
+    for kv in args.option:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
+    ctx.upload(nodes, root, colours)
+    cam = api.default_camera(lower, upper)
+    stream = torch.cuda.current_stream().cuda_stream
+    accum = torch.zeros(HEIGHT, WIDTH, 3, dtype=torch.float32, device=dev)
+    bands = sharding.tile_rows(HEIGHT, world, rank, tile=64)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(frame):
+        accum.zero_()
+        for y0, y1 in bands:
+            p = api.pt_params(WIDTH, HEIGHT, spp=args.spp, bounces=args.bounces, variant=api.VARIANT_RECURSIVE,
+                              frame_id=frame * args.spp, rect=(0, y0, WIDTH, y1))
+            ctx.render_device(cam, p, accum.data_ptr(), stream)
+        if world > 1:
+            sharding.reduce_image(dist, accum, dst=0)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ctx.reset_counters()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        for i in range(args.steps):
+            flush.zero_()
+            starts[i].record(); step(100 + i); stops[i].record()
+        torch.cuda.synchronize()
+    launches = ctx.counter("kernel_launches")
+    total_ms = float(np.sum([a.elapsed_time(b) for a, b in zip(starts, stops)]))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms = total_ms / args.steps
+    value = WIDTH * HEIGHT * args.spp / (ms * 1e-3)
+    # end to end: the host-image call (image up, render, image down) on this rank's bands
+    host = api.PinnedArray(HEIGHT * WIDTH * 3, np.float32)
+    img = host.array.reshape(HEIGHT, WIDTH, 3)
+    img[:] = 0
+    t0 = time.perf_counter()
+    for y0, y1 in bands:
+        ctx.render(cam, api.pt_params(WIDTH, HEIGHT, spp=args.spp, bounces=args.bounces, variant=api.VARIANT_RECURSIVE, rect=(0, y0, WIDTH, y1)), img)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    if rank == 0:
+        mean = float(accum.mean().item()) / args.spp
+        line = {"metric": "1080p path-traced spp/s", "value": value, "unit": "spp/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32+i32", "data": "synthetic",
+                "config": {"workload": "path tracing 1920x1080, %d spp, %d bounces (traceSingleRayRecurse), sun+sky+noise, maxFootprint 0.0035, procedural 4096^3 terrain SVDAG" % (args.spp, args.bounces),
+                           "nodes": int(len(nodes)), "l2": "flushed between steps", "options": args.option,
+                           "parallelism": "replicated DAG, 64-row tile bands round-robin over %d GPU(s), one NCCL reduce per frame" % world},
+                "e2e": {"value": WIDTH * HEIGHT * args.spp / e2e_s, "unit": "spp/s", "h2d_bytes_per_step": len(bands) * HEIGHT * WIDTH * 12,
+                        "d2h_bytes_per_step": len(bands) * HEIGHT * WIDTH * 12, "call": "cbq_render (host image in, rendered, host image out) per tile band"},
+                "gpu_launches": int(launches), "clocks": clocks.summary(), "extra": {"mean_radiance": mean}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         reference_arm(args)
+        return
+    if args.workload == "pathtrace":
+        pathtrace_workload(args)
         return
 
     import torch
@@ -238,9 +338,10 @@ def main():
     cam, pos, yaw = orbit_camera(api, b, rank)
     if args.workload == "random":
         n_rays = args.random_rays
-        host_rays = R.random_rays(n_rays, lower, upper, seed=100 + rank)
-        d_rays = torch.from_numpy(host_rays.view(np.float32).reshape(-1)).to(dev)
-        workload = "incoherent batch of %d random rays (origin U(bounds+10%%), random direction) vs procedural 4096^3 terrain SVDAG (BASELINE configs[2], reduced count)" % n_rays
+        ext = (np.asarray(upper, dtype=np.float64) - np.asarray(lower, dtype=np.float64)) * 0.1
+        d_rays = torch.empty(n_rays * 6, dtype=torch.float32, device=dev)
+        ctx.random_rays_device(100 + rank, (lower - ext).astype(np.float32), (upper + ext).astype(np.float32), n_rays, d_rays.data_ptr(), stream)
+        workload = "incoherent batch of %d random rays (origin U(bounds+10%%), direction uniform on the sphere, device generated) vs procedural 4096^3 terrain SVDAG (BASELINE configs[2])" % n_rays
     else:
         n_rays = WIDTH * HEIGHT
         d_rays = torch.empty(n_rays * 6, dtype=torch.float32, device=dev)
@@ -318,9 +419,10 @@ def main():
               "mean_radiance": float(d_accum.mean().item()) / args.spp}
 
     # ---- end to end through the public host-buffer call ------------------------------------------
-    pin_rays = api.PinnedArray(n_rays, api.RAY_DTYPE)
-    pin_hits = api.PinnedArray(n_rays, api.HIT_DTYPE)
-    pin_rays.array[:] = d_rays.cpu().numpy().view(api.RAY_DTYPE).reshape(-1)
+    n_e2e = min(n_rays, 8_000_000)      # the end-to-end leg moves at most 8 M rays (192 MB in, 320 MB out) per call
+    pin_rays = api.PinnedArray(n_e2e, api.RAY_DTYPE)
+    pin_hits = api.PinnedArray(n_e2e, api.HIT_DTYPE)
+    pin_rays.array[:] = d_rays[: n_e2e * 6].cpu().numpy().view(api.RAY_DTYPE).reshape(-1)
     for _ in range(2):
         ctx.intersect_volume(pin_rays.array, True, -1.0, out=pin_hits.array)
     e2e_steps = max(3, min(args.steps, 10))
@@ -334,9 +436,9 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = world * n_rays / e2e_s / 1e9
+    e2e_value = world * n_e2e / e2e_s / 1e9
     hit_fraction = float((pin_hits.array["hit"] == 1).mean())
-    device_hits = d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)
+    device_hits = d_hits[: n_e2e * 10].cpu().numpy().view(api.HIT_DTYPE).reshape(-1)
     same = device_hits.tobytes() == pin_hits.array.tobytes()
 
     if rank != 0:
@@ -349,7 +451,7 @@ def main():
     port = pyoracle.Port()
     host_rays = pin_rays.array.copy()
     sd = port.find_subdags(nodes, root)
-    pick = np.arange(0, n_rays, max(1, n_rays // 200000))
+    pick = np.arange(0, n_e2e, max(1, n_e2e // 200000))
     _, _, st = port.trace(nodes, sd, host_rays[pick], True, -1.0, threads=os.cpu_count() or 1, want_hits=False, want_stats=True)
     visits = st.node_visits() / len(pick)
     bytes_per_ray = 32.0 * visits + 24.0 + 40.0
@@ -368,14 +470,14 @@ def main():
     except Exception:
         kind = "port"
         run = lambda r, t: port.trace(nodes, sd, r, True, -1.0, threads=t)[1]
-    cpu_sample = host_rays[: min(n_rays, 1 << 20)]
+    cpu_sample = host_rays[: min(n_e2e, 1 << 20)]
     run(cpu_sample[:50000], threads)
     cpu_all = len(cpu_sample) / run(cpu_sample, threads) / 1e9
     cpu_one_sample = cpu_sample[:: 8]
     cpu_one = len(cpu_one_sample) / run(cpu_one_sample, 1) / 1e9
 
     line = {
-        "metric": "Grays/s SVDAG traversal (primary rays)", "value": value, "unit": "Grays/s",
+        "metric": "Grays/s SVDAG traversal (%s rays)" % ("primary" if args.workload == "primary" else "incoherent"), "value": value, "unit": "Grays/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
         "config": {"workload": workload, "scene": "%s 2^%d seed %d" % (SCENE_KIND, args.scene_log2, SCENE_SEED),
@@ -383,7 +485,7 @@ def main():
                    "l2": "warm (no flush)" if args.no_flush else "flushed between steps (256 MB memset, untimed)",
                    "hit_fraction": round(hit_fraction, 4), "options": options,
                    "parallelism": "replicated DAG, one frame per GPU" if world > 1 else "single GPU"},
-        "e2e": {"value": e2e_value, "unit": "Grays/s", "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * 40,
+        "e2e": {"value": e2e_value, "unit": "Grays/s", "h2d_bytes_per_step": n_e2e * 24, "d2h_bytes_per_step": n_e2e * 40, "rays_per_step": n_e2e,
                 "ms_per_step": 1e3 * e2e_s, "call": "cbq_trace (pinned host rays -> pinned host hits, 3-stage copy/compute pipeline)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

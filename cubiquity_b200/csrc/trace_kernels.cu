@@ -273,6 +273,46 @@ primaryRays(cbq_camera cam, uint32_t width, uint32_t height, Ray* __restrict__ r
 	}
 }
 
+// BASELINE config 3: collision-query style rays, generated on the device from a counter-based hash so
+// that 100 M of them need no host memory. Ray i, draw k: u = top 24 bits of mix64(seed + (8 i + k + 1) * phi).
+// origin = lower + u * (upper - lower); direction = a point drawn in the unit ball by rejection (draws
+// 3.., at most 5 tries, then +z), normalised. cubiquity_b200/rays.py:counter_rays is the same in numpy.
+__device__ __forceinline__ float counterUniform(uint64_t seed, uint64_t i, uint32_t k)
+{
+	uint64_t x = seed + (8ull * i + k + 1ull) * 0x9E3779B97F4A7C15ull;
+	x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+	x ^= x >> 27; x *= 0x94d049bb133111ebull;
+	x ^= x >> 31;
+	return (float)(uint32_t)(x >> 40) * (1.0f / 16777216.0f);
+}
+
+__global__ void __launch_bounds__(256)
+randomRays(uint64_t seed, float lx, float ly, float lz, float ex, float ey, float ez, uint64_t n, Ray* __restrict__ rays)
+{
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		Ray r;
+		r.o[0] = lx + counterUniform(seed, i, 0) * ex;
+		r.o[1] = ly + counterUniform(seed, i, 1) * ey;
+		r.o[2] = lz + counterUniform(seed, i, 2) * ez;
+		float dx = 0.0f, dy = 0.0f, dz = 1.0f;
+		// One try per counter pair: (3,4,5) then the same hash at i + n, i + 2n ... keeps 8 draws per ray.
+		for (uint32_t t = 0; t < 5; t++) {
+			const float x = counterUniform(seed, i + t * n, 3) * 2.0f - 1.0f;
+			const float y = counterUniform(seed, i + t * n, 4) * 2.0f - 1.0f;
+			const float z = counterUniform(seed, i + t * n, 5) * 2.0f - 1.0f;
+			const float r2 = (x * x + y * y) + z * z;
+			if (r2 < 1.0f && r2 > 1e-12f) {
+				const float len = sqrtf(r2);
+				dx = x / len; dy = y / len; dz = z / len;
+				break;
+			}
+		}
+		r.d[0] = dx; r.d[1] = dy; r.d[2] = dz;
+		float2* p = reinterpret_cast<float2*>(rays + i);
+		p[0] = make_float2(r.o[0], r.o[1]); p[1] = make_float2(r.o[2], r.d[0]); p[2] = make_float2(r.d[1], r.d[2]);
+	}
+}
+
 template <bool kSurface, bool kLodOff, typename Source, typename Sink>
 cudaError_t launchPersistentImpl(const TraceArgs& a, const Source& src, const Sink& sink, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
 {
@@ -331,6 +371,15 @@ cudaError_t launchTrace(const TraceArgs& a, bool surface, const LaunchConfig& cf
 	}
 	BufferSource src{ a.rays };
 	return launchPersistent(a, surface, src, a.count, cfg, stream);
+}
+
+cudaError_t launchRandomRays(uint64_t seed, const float lower[3], const float upper[3], uint64_t n, Ray* rays, cudaStream_t stream)
+{
+	uint64_t blocks = (n + 255) / 256;
+	if (blocks > 148u * 16u) blocks = 148u * 16u;
+	if (blocks == 0) blocks = 1;
+	randomRays<<<(int)blocks, 256, 0, stream>>>(seed, lower[0], lower[1], lower[2], upper[0] - lower[0], upper[1] - lower[1], upper[2] - lower[2], n, rays);
+	return cudaGetLastError();
 }
 
 cudaError_t launchPrimaryRays(const cbq_camera& cam, uint32_t width, uint32_t height, Ray* rays, cudaStream_t stream)

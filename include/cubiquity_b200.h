@@ -157,6 +157,13 @@ int cbq_camera_from_pose(const double position[3], double pitch, double yaw, dou
 int cbq_primary_rays_device(cbq_context* ctx, const cbq_camera* cam, uint32_t width, uint32_t height,
                             cbq_ray* d_rays, void* stream);
 
+/* Synthetic collision-query rays generated on the device (BASELINE config 3): origin uniform in
+ * [lower, upper), direction uniform on the sphere, from a counter-based hash of (seed, ray index), so
+ * ray i is the same whatever the batch it is generated in. cubiquity_b200/rays.py:counter_rays is the
+ * identical host generator. */
+int cbq_random_rays_device(cbq_context* ctx, uint64_t seed, const float lower[3], const float upper[3],
+                           uint64_t n, cbq_ray* d_rays, void* stream);
+
 /* Fused: generate the primary ray of every pixel (8x4-pixel tiles per warp for coherence) and
  * trace it; d_hits is row-major width x height. */
 int cbq_raycast_frame_device(cbq_context* ctx, const cbq_camera* cam, uint32_t width, uint32_t height,

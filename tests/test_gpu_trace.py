@@ -201,3 +201,29 @@ def test_full_size_terrain_4096(gpu, port, api):
     rnd = R.random_rays(400000, sc.lower, sc.upper, seed=3)
     for mf in (-1.0, 0.0035):
         assert_hits_identical(gpu.intersect_volume(rnd, True, mf), oracle_hits(port, sc, rnd, True, mf), "random rays mf=%g" % mf)
+
+
+def test_device_ray_generator_matches_host_twin_and_config3(gpu, port, api):
+    """BASELINE config 3 at reduced count: 4 M device-generated collision-query rays against the 4096^3
+    terrain; the generator is checked against its numpy twin, the hits against the oracle on a sample."""
+    torch = pytest.importorskip("torch")
+    sc = api.Scene("terrain", 12, seed=1)
+    gpu.upload(sc.nodes, sc.root, sc.colours)
+    n = 4_000_000
+    ext = (sc.upper.astype(np.float64) - sc.lower) * 0.1
+    lower, upper = (sc.lower - ext).astype(np.float32), (sc.upper + ext).astype(np.float32)
+    d_rays = torch.empty(n * 6, dtype=torch.float32, device="cuda")
+    d_hits = torch.zeros(n * 10, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    gpu.random_rays_device(12345, lower, upper, n, d_rays.data_ptr(), stream)
+    gpu.trace_device(d_rays.data_ptr(), n, d_hits.data_ptr(), True, -1.0, stream)
+    torch.cuda.synchronize()
+    pick = np.sort(np.random.default_rng(1).choice(n, 300000, replace=False))
+    rays = d_rays.cpu().numpy().view(api.RAY_DTYPE).reshape(-1)[pick]
+    twin = R.counter_rays(pick, n, lower, upper, seed=12345)
+    assert rays.tobytes() == twin.tobytes()
+    assert np.allclose(np.linalg.norm(rays["d"], axis=1), 1.0, atol=1e-6)
+    hits = d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)
+    want = oracle_hits(port, sc, rays, True, -1.0)
+    assert_hits_identical(hits[pick], want, "config 3 sample")
+    assert 0.2 < (hits["hit"] == 1).mean() < 0.9
