@@ -42,15 +42,18 @@ class PtParams(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("spp", C.c_uint32), ("bounces", C.c_uint32),
                 ("variant", C.c_uint32), ("include_sun", C.c_uint32), ("include_sky", C.c_uint32),
                 ("add_noise", C.c_uint32), ("max_footprint", C.c_float), ("frame_id", C.c_uint32),
-                ("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32), ("y1", C.c_uint32), ("pad", C.c_uint32)]
+                ("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32), ("y1", C.c_uint32),
+                ("band_count", C.c_uint32), ("band_index", C.c_uint32)]
 
 
 def pt_params(width, height, spp=1, bounces=1, variant=VARIANT_ONE_BOUNCE, include_sun=True, include_sky=True,
-              add_noise=True, max_footprint=0.0035, frame_id=0, rect=None):
-    """Defaults are PathtracingDemo's (reference pathtracing_demo.h:80-84)."""
+              add_noise=True, max_footprint=0.0035, frame_id=0, rect=None, bands=None):
+    """Defaults are PathtracingDemo's (reference pathtracing_demo.h:80-84). bands = (count, index) renders only
+    the 64-row bands b of the rectangle with b % count == index (round-robin tile sharding)."""
     x0, y0, x1, y1 = rect if rect is not None else (0, 0, width, height)
+    bc, bi = bands if bands is not None else (1, 0)
     return PtParams(width, height, spp, bounces, variant, int(include_sun), int(include_sky), int(add_noise),
-                    max_footprint, frame_id, x0, y0, x1, y1, 0)
+                    max_footprint, frame_id, x0, y0, x1, y1, bc, bi)
 
 
 EXPORTS = [

@@ -535,6 +535,7 @@ int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_para
 	if (!p->width || !p->height || p->x1 > p->width || p->y1 > p->height || p->x0 > p->x1 || p->y0 > p->y1)
 		return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad image rectangle");
 	if (p->variant > 1 || p->bounces > 5) return fail(CBQ_ERROR_INVALID_ARGUMENT, "variant must be 0/1 and bounces <= 5 (the viewer's F2 limit, pathtracing_demo.cpp:280)");
+	if (p->band_count > 1 && p->band_index >= p->band_count) return fail(CBQ_ERROR_INVALID_ARGUMENT, "band_index must be < band_count");
 	if (p->x0 == p->x1 || p->y0 == p->y1 || p->spp == 0) return CBQ_OK;
 	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
 	cbq::RenderArgs a;
@@ -548,7 +549,8 @@ int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_para
 		ctx->launches++;
 		return CBQ_OK;
 	}
-	const size_t pixels = (size_t)(p->x1 - p->x0) * (p->y1 - p->y0);
+	const size_t pixels = (size_t)(p->x1 - p->x0) * cbq::bandedRowCount(p->y1 - p->y0, p->band_count, p->band_index);
+	if (pixels == 0) return CBQ_OK;
 	const size_t paths = pixels * std::min<size_t>(p->spp, (size_t)ctx->cfg.sampleGroup);
 	if (paths > 0xffffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "rectangle too large for 32-bit path ids");
 	if (paths > ctx->wavefront.pixelCapacity) CBQ_CUDA(cudaDeviceSynchronize());   // buffers may still be in use

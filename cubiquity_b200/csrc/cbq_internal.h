@@ -31,6 +31,21 @@ struct VolumeHeader {
 };
 static_assert(sizeof(VolumeHeader) == 256, "header is 256 bytes");
 
+// Row l of a banded rectangle -> image row: bands of 64 rows counted from y0, this share owns every
+// bandCount-th band starting at bandIndex. bandCount <= 1: identity.
+CBQ_HD uint32_t bandedRow(uint32_t y0, uint32_t localRow, uint32_t bandCount, uint32_t bandIndex)
+{
+	if (bandCount <= 1u) return y0 + localRow;
+	return y0 + ((localRow >> 6) * bandCount + bandIndex) * 64u + (localRow & 63u);
+}
+inline uint32_t bandedRowCount(uint32_t rectH, uint32_t bandCount, uint32_t bandIndex)
+{
+	if (bandCount <= 1u) return rectH;
+	uint32_t rows = 0;
+	for (uint32_t b = bandIndex; b * 64u < rectH; b += bandCount) rows += (rectH - b * 64u < 64u) ? (rectH - b * 64u) : 64u;
+	return rows;
+}
+
 struct LaunchConfig {
 	int blockThreads;      // threads per CTA
 	int blocksPerSm;       // resident CTAs per SM the grid is sized for
@@ -53,7 +68,8 @@ struct TraceArgs {
 	// camera source (rays == nullptr): image size and the pixel rectangle to trace (0 = whole image)
 	cbq_camera camera;
 	uint32_t width, height;
-	uint32_t x0, y0, rectW, rectH;
+	uint32_t x0, y0, rectW, rectH;   // rectH counts the rows actually traced (owned rows when banded)
+	uint32_t bandCount, bandIndex;   // 64-row band interleave (cbq_pt_params::band_count / band_index)
 	// optional: batch size read on the device (count = *countPtr * countScale), flag-only results
 	const unsigned long long* countPtr;
 	uint32_t countScale;

@@ -88,7 +88,7 @@ struct PathState {
 
 __global__ void __launch_bounds__(256, CBQ_RENDER_MIN_BLOCKS)
 renderPersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict__ subdagsGlobal,
-	const float4* __restrict__ colours, cbq_camera cam, cbq_pt_params p, float* __restrict__ accum, int refillThreshold,
+	const float4* __restrict__ colours, cbq_camera cam, cbq_pt_params p, uint32_t rectH, float* __restrict__ accum, int refillThreshold,
 	unsigned long long* __restrict__ queue, unsigned long long* __restrict__ abandoned)
 {
 	extern __shared__ uint32_t stackMem[];
@@ -102,8 +102,8 @@ renderPersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict
 	const unsigned lowerLanes = (1u << lane) - 1u;
 	uint64_t chunkNext = 0, chunkEnd = 0;   // warp-uniform window of claimed tickets
 
-	const uint32_t rectW = p.x1 - p.x0, rectH = p.y1 - p.y0;
-	const uint32_t tilesX = (rectW + 7u) / 8u, tilesY = (rectH + 3u) / 4u;
+	const uint32_t rectW = p.x1 - p.x0;
+	const uint32_t tilesX = (rectW + 7u) / 8u, tilesY = (rectH + 3u) / 4u;   // rectH = owned rows (band interleave)
 	const uint64_t tickets = (uint64_t)tilesX * tilesY * 32u;
 
 	// normalize(vec3(1, -2, 10)) (pathtracing_demo.cpp:89): IEEE sqrt and divides, same bits as the host.
@@ -213,8 +213,9 @@ renderPersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict
 					const uint64_t ticket = chunkNext + (uint64_t)myRank;
 					const uint32_t tile = (uint32_t)(ticket >> 5), within = (uint32_t)ticket & 31u;
 					const uint32_t tx = tile % tilesX, ty = tile / tilesX;
-					const uint32_t x = p.x0 + tx * 8u + (within & 7u), y = p.y0 + ty * 4u + (within >> 3);
-					if (x < p.x1 && y < p.y1) {
+					const uint32_t x = p.x0 + tx * 8u + (within & 7u), ly = ty * 4u + (within >> 3);
+					const uint32_t y = bandedRow(p.y0, ly, p.band_count, p.band_index);
+					if (x < p.x1 && ly < rectH) {
 						t.x = x; t.y = y; t.sample = 0;
 						const float* px = accum + 3ull * ((uint64_t)y * p.width + x);
 						t.ar = px[0]; t.ag = px[1]; t.ab = px[2];
@@ -283,12 +284,13 @@ cudaError_t launchRender(const RenderArgs& a, const LaunchConfig& cfg, cudaStrea
 	const size_t smem = (size_t)cfg.stackLevels * block * sizeof(uint32_t);
 	cudaError_t e = cudaFuncSetAttribute(renderPersistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
-	const uint32_t rectW = a.params.x1 - a.params.x0, rectH = a.params.y1 - a.params.y0;
+	const uint32_t rectW = a.params.x1 - a.params.x0, rectH = bandedRowCount(a.params.y1 - a.params.y0, a.params.band_count, a.params.band_index);
+	if (rectW == 0 || rectH == 0) return cudaSuccess;
 	const uint64_t tiles = (uint64_t)((rectW + 7u) / 8u) * ((rectH + 3u) / 4u);
 	int grid = cfg.smCount * CBQ_RENDER_MIN_BLOCKS;
 	const uint64_t needed = (tiles * 32u + block - 1) / block;
 	if ((uint64_t)grid > needed) grid = (int)(needed ? needed : 1);
-	renderPersistent<<<grid, block, smem, stream>>>(a.nodes, a.subdags, a.colours, a.camera, a.params, a.accum, cfg.refillThreshold, a.queue, a.abandoned);
+	renderPersistent<<<grid, block, smem, stream>>>(a.nodes, a.subdags, a.colours, a.camera, a.params, rectH, a.accum, cfg.refillThreshold, a.queue, a.abandoned);
 	return cudaGetLastError();
 }
 

@@ -85,7 +85,7 @@ accumulateKernel(WaveParams w, const float* __restrict__ radiance, float* __rest
 	const size_t n = w.paths;
 	const uint32_t samples = w.paths / w.pixels;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < w.pixels; i += gridDim.x * blockDim.x) {
-		const uint32_t x = w.p.x0 + i % w.rectW, y = w.p.y0 + i / w.rectW;
+		const uint32_t x = w.p.x0 + i % w.rectW, y = bandedRow(w.p.y0, i / w.rectW, w.p.band_count, w.p.band_index);
 		float* px = accum + 3ull * ((uint64_t)y * w.p.width + x);
 		float r = px[0], g = px[1], b = px[2];
 		for (uint32_t s = 0; s < samples; s++) {
@@ -125,7 +125,8 @@ shadeKernel(WaveParams w, const float4* __restrict__ colours, const Hit* __restr
 			if (w.depth == 0) {
 				const uint32_t pix = pixel % w.pixels, sample = pixel / w.pixels;
 				Ray r;
-				cameraRay(w.cam, (int)(w.p.x0 + pix % w.rectW), (int)(w.p.y0 + pix / w.rectW), (int)w.p.width, (int)w.p.height, r);
+				cameraRay(w.cam, (int)(w.p.x0 + pix % w.rectW), (int)bandedRow(w.p.y0, pix / w.rectW, w.p.band_count, w.p.band_index),
+					(int)w.p.width, (int)w.p.height, r);
 				rng = pixelSeed(r, w.sampleIndex + sample);
 			} else {
 				rng = pathRng[i];
@@ -250,7 +251,8 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 	const cbq_pt_params& p = a.params;
 	WaveParams w;
 	w.cam = a.camera; w.p = p;
-	w.rectW = p.x1 - p.x0; w.rectH = p.y1 - p.y0;
+	w.rectW = p.x1 - p.x0; w.rectH = bandedRowCount(p.y1 - p.y0, p.band_count, p.band_index);
+	if (w.rectW == 0 || w.rectH == 0) return cudaSuccess;
 	w.pixels = w.rectW * w.rectH;
 	w.shadowsPerPath = (p.include_sun ? 1u : 0u) + (p.include_sky ? 1u : 0u);
 	// Depth at which surviving paths stop: traceSingleRay lights depth 1 and stops (:173-180);
@@ -279,6 +281,7 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 				// one primary ray per PIXEL: the samples of the group share it
 				t.rays = nullptr; t.camera = a.camera; t.width = p.width; t.height = p.height;
 				t.x0 = p.x0; t.y0 = p.y0; t.rectW = w.rectW; t.rectH = w.rectH; t.count = w.pixels;
+				t.bandCount = p.band_count; t.bandIndex = p.band_index;
 				surfaceCfg.refillThreshold = 32;           // coherent tiles
 			} else {
 				t.rays = b.rays[cur]; t.countPtr = b.counters + (d - 1); t.countScale = 1; t.count = w.paths;

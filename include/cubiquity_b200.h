@@ -84,7 +84,10 @@ typedef struct cbq_pt_params {
 	float    max_footprint;    /* 0.0035 in the reference; -1 disables LOD */
 	uint32_t frame_id;         /* index of the first sample: sample s is seeded with frame_id + s */
 	uint32_t x0, y0, x1, y1;   /* pixel rectangle [x0,x1) x [y0,y1) this call renders (tile sharding) */
-	uint32_t pad;
+	uint32_t band_count;       /* 0 or 1: every row of the rectangle. N > 1: the rectangle's rows are cut into */
+	uint32_t band_index;       /* 64-row bands (the GLSL renderer's tile size, glsl/pathtracing.frag:789-803) and
+	                              this call renders bands b with b % band_count == band_index -- one call per GPU
+	                              for a round-robin tile-sharded frame */
 } cbq_pt_params;
 
 #define CBQ_VARIANT_ONE_BOUNCE 0u

@@ -51,6 +51,13 @@ class PtParams(C.Structure):
                 ("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32), ("y1", C.c_uint32), ("pad", C.c_uint32)]
 
 
+def pt_params_from(p):
+    """Oracle PtParams from the product's (cubiquity_b200.api.PtParams): same fields by name; the product's
+    band interleave has no oracle counterpart (tests compare banded renders with masked whole frames)."""
+    names = [n for n, _ in PtParams._fields_ if n != "pad"]
+    return PtParams(**{n: getattr(p, n) for n in names})
+
+
 def build(port=True, ref=None):
     """Compile the checker(s). `ref` defaults to "if /root/reference exists"."""
     if ref is None:

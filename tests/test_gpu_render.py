@@ -15,7 +15,7 @@ def both_cameras(api, port, sc):
 
 
 def oracle_params(pyoracle, p):
-    return pyoracle.PtParams(*[getattr(p, f) for f, _ in p._fields_])
+    return pyoracle.pt_params_from(p)
 
 
 @pytest.mark.parametrize("kind,size_log2", [("sphere_noise", 8), ("soup", 8)])
@@ -143,3 +143,31 @@ def test_sample_group_size_does_not_change_the_image(gpu, port, api, scenes):
         gpu.set_option("sample_group", 8)
     for im in imgs[1:]:
         assert np.array_equal(im.view(np.uint32), imgs[0].view(np.uint32))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_band_interleaved_shares_tile_the_frame_exactly(gpu, port, api, scenes, mode):
+    """Round-robin tile sharding in ONE call per GPU: `bands=(count, index)` renders every count-th 64-row
+    band. The shares are disjoint, cover the frame, and sum to the whole-frame render bit for bit."""
+    sc = scenes("sphere_noise", 7)
+    gpu.upload(sc.nodes, sc.root, sc.colours)
+    cam, _ = both_cameras(api, port, sc)
+    w, h = 90, 200            # 4 bands: 64 + 64 + 64 + 8 rows
+    try:
+        gpu.set_option("render_mode", mode)
+        whole = gpu.render(cam, api.pt_params(w, h, spp=2, bounces=2, variant=1))
+        for count in (2, 3, 8):
+            total = np.zeros_like(whole)
+            for index in range(count):
+                share = gpu.render(cam, api.pt_params(w, h, spp=2, bounces=2, variant=1, bands=(count, index)))
+                rows = np.array([((y // 64) % count) == index for y in range(h)])
+                assert not share[~rows].any()                       # nothing outside the share
+                assert np.array_equal(share[rows], whole[rows])     # and exactly the frame inside it
+                total += share
+            assert np.array_equal(total, whole)
+        # a banded sub-rectangle
+        part = gpu.render(cam, api.pt_params(w, h, spp=2, bounces=2, variant=1, rect=(10, 30, 80, 190), bands=(2, 1)))
+        rows = np.array([30 <= y < 190 and (((y - 30) // 64) % 2) == 1 for y in range(h)])
+        assert np.array_equal(part[rows][:, 10:80], whole[rows][:, 10:80]) and not part[~rows].any() and not part[:, :10].any()
+    finally:
+        gpu.set_option("render_mode", 0)

@@ -97,6 +97,6 @@ def test_city_65536_with_runtime_edits_and_lod(gpu, port, ref, api):
             want, _, _ = port.trace(nodes, sd, rays, True, mf, threads=8)
             assert_hits_identical(gpu.intersect_volume(rays, True, mf), want, "city edit %d mf %g" % (step, mf))
         p = api.pt_params(160, 90, spp=1, bounces=2, variant=api.VARIANT_RECURSIVE, frame_id=step)
-        op = pyoracle.PtParams(*[getattr(p, f) for f, _ in p._fields_])
+        op = pyoracle.pt_params_from(p)
         want_img, _, _ = port.render(nodes, sd, sc.colours, ocam, op, threads=8)
         assert np.array_equal(gpu.render(cam, p), want_img)
