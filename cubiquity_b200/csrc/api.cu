@@ -551,12 +551,15 @@ int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_para
 	}
 	const size_t pixels = (size_t)(p->x1 - p->x0) * cbq::bandedRowCount(p->y1 - p->y0, p->band_count, p->band_index);
 	if (pixels == 0) return CBQ_OK;
-	const size_t paths = pixels * std::min<size_t>(p->spp, (size_t)ctx->cfg.sampleGroup);
+	// Samples traced together: the option, capped so that a wave stays below 32 M paths (~8.5 GB of buffers).
+	cbq::LaunchConfig renderCfg = ctx->cfg;
+	renderCfg.sampleGroup = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->cfg.sampleGroup, (32u << 20) / pixels));
+	const size_t paths = pixels * std::min<size_t>(p->spp, (size_t)renderCfg.sampleGroup);
 	if (paths > 0xffffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "rectangle too large for 32-bit path ids");
 	if (paths > ctx->wavefront.pixelCapacity) CBQ_CUDA(cudaDeviceSynchronize());   // buffers may still be in use
 	CBQ_CUDA((cudaError_t)cbq::wavefrontReserve(ctx->wavefront, paths));
 	struct Adaptor { static int next(void* user, cudaStream_t st, unsigned long long** out) { return nextQueue(static_cast<cbq_context*>(user), st, out); } };
-	CBQ_CUDA(cbq::launchRenderWavefront(a, ctx->wavefront, ctx->cfg, s, &Adaptor::next, ctx, &ctx->launches));
+	CBQ_CUDA(cbq::launchRenderWavefront(a, ctx->wavefront, renderCfg, s, &Adaptor::next, ctx, &ctx->launches));
 	return CBQ_OK;
 }
 

@@ -152,8 +152,12 @@ struct FlagSink {
 	__device__ __forceinline__ void write(uint64_t slot, const Hit& h) const { flags[slot] = (uint8_t)h.hit; }
 };
 
+#ifndef CBQ_TRACE_MIN_BLOCKS
+#define CBQ_TRACE_MIN_BLOCKS 4
+#endif
+
 template <bool kSurface, bool kLodOff, typename Source, typename Sink>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, CBQ_TRACE_MIN_BLOCKS)
 tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict__ subdagsGlobal, Source source,
 	Sink sink, uint64_t count, const unsigned long long* __restrict__ countPtr, uint32_t countScale,
 	float maxFootprint, int refillThreshold,
