@@ -227,3 +227,67 @@ def test_device_ray_generator_matches_host_twin_and_config3(gpu, port, api):
     want = oracle_hits(port, sc, rays, True, -1.0)
     assert_hits_identical(hits[pick], want, "config 3 sample")
     assert 0.2 < (hits["hit"] == 1).mean() < 0.9
+
+
+def test_full_height_volume_with_extreme_coordinates(gpu, port, ref):
+    """Sub-DAG roots at height 31 (32 stack levels in shared memory), INT_MIN / INT_MAX voxel coordinates."""
+    from test_oracle_vs_reference import extreme_volume, extreme_rays
+    v = extreme_volume(ref)
+    nodes, root = v.nodes(), v.root()
+    gpu.upload(nodes, root)
+    assert gpu.get_option("stack_levels") == 32
+    rays = extreme_rays(200000, seed=12)
+    sd = port.find_subdags(nodes, root)
+    for surf, mf in [(True, -1.0), (True, 0.0035), (False, 0.05)]:
+        want, _, _ = port.trace(nodes, sd, rays, surf, mf, threads=8)
+        assert_hits_identical(gpu.intersect_volume(rays, surf, mf), want, "extreme coordinates")
+    assert want["hit"].sum() > 500
+
+
+def test_error_codes_and_option_validation(gpu, api, scenes):
+    fresh = api.Context(0)
+    try:
+        rays = R.random_rays(10, [-1] * 3, [1] * 3)
+        with pytest.raises(api.CubiquityError) as e:
+            fresh.intersect_volume(rays)
+        assert e.value.code == api.ERROR_NO_VOLUME
+        with pytest.raises(api.CubiquityError) as e:
+            fresh.render(api.camera_from_pose([0, 0, 0], 0, 0), api.pt_params(8, 8))
+        assert e.value.code == api.ERROR_NO_VOLUME
+        for key, bad in [("block_threads", 100), ("block_threads", 512), ("blocks_per_sm", 0), ("refill_threshold", 33),
+                         ("kernel", 2), ("render_mode", 5), ("sample_group", 0), ("no_such_option", 1)]:
+            with pytest.raises(api.CubiquityError) as e:
+                fresh.set_option(key, bad)
+            assert e.value.code == api.ERROR_INVALID_ARGUMENT
+        sc = scenes("sphere_noise", 6)
+        fresh.upload(sc.nodes, sc.root)
+        cam = api.camera_from_pose([0, -100, 100], -0.7, 0)
+        for kw in [dict(rect=(0, 0, 9, 8)), dict(rect=(5, 0, 4, 8)), dict(bounces=6, variant=1), dict(variant=2), dict(bands=(2, 2))]:
+            with pytest.raises(api.CubiquityError) as e:
+                fresh.render(cam, api.pt_params(8, 8, **kw))
+            assert e.value.code == api.ERROR_INVALID_ARGUMENT
+        assert not fresh.render(cam, api.pt_params(8, 8, spp=0)).any()      # nothing to do is not an error
+    finally:
+        fresh.close()
+
+
+def test_two_contexts_from_two_threads(gpu, port, api, scenes):
+    import threading
+    sc_a, sc_b = scenes("sphere_noise", 7), scenes("soup", 7)
+    results = {}
+
+    def work(name, sc):
+        with api.Context(0) as ctx:
+            ctx.upload(sc.nodes, sc.root)
+            rays = mixed_rays(sc.lower, sc.upper, 150000, seed=len(name))
+            for _ in range(3):
+                got = ctx.intersect_volume(rays, True, 0.0035)
+            results[name] = (rays, got)
+    threads = [threading.Thread(target=work, args=("a", sc_a)), threading.Thread(target=work, args=("bb", sc_b))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for name, sc in (("a", sc_a), ("bb", sc_b)):
+        rays, got = results[name]
+        assert_hits_identical(got, oracle_hits(port, sc, rays, True, 0.0035), "context " + name)

@@ -106,3 +106,42 @@ def test_degenerate_rays_terminate(port, ref):
     got, _, _ = port.trace(nodes, port.find_subdags(nodes, root), rays, True, -1.0)
     assert (got["pad"] == 1).any()
     assert (got["hit"][got["pad"] == 1] == 0).all()
+
+
+def extreme_volume(ref):
+    """Voxels at the corners of the 2^32 grid and at the origin: sub-DAG roots at height 31, INT_MIN lower
+    bounds, wrap-around in `lowerBound * sign - signBit * size` (raytracing.cpp:454-456)."""
+    v = ref.volume()
+    lo, hi = -(1 << 31), (1 << 31) - 1
+    pts = [(lo, lo, lo, 3), (hi, hi, hi, 4), (lo, hi, 0, 5), (0, 0, 0, 6), (-1, -1, -1, 7), (hi, lo, hi, 8), (1000, -2000, 3000, 9)]
+    v.set_voxels(np.array(pts, dtype=np.int32))
+    v.bake()
+    return v
+
+
+def extreme_rays(n, seed):
+    rng = np.random.default_rng(seed)
+    targets = np.array([(-2.0**31, -2.0**31, -2.0**31), (2.0**31, 2.0**31, 2.0**31), (-2.0**31, 2.0**31, 0), (0, 0, 0),
+                        (-1, -1, -1), (2.0**31, -2.0**31, 2.0**31), (1000, -2000, 3000)])
+    t = targets[rng.integers(0, len(targets), n)]
+    o = t + rng.normal(0, 1, (n, 3)) * np.where(np.abs(t) > 1e6, 3e5, 50.0)
+    d = (t + rng.normal(0, 0.3, (n, 3)) * np.where(np.abs(t) > 1e6, 200.0, 0.4)) - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.zeros(n, dtype=[("o", "<f4", 3), ("d", "<f4", 3)])
+    rays["o"], rays["d"] = o.astype(np.float32), d.astype(np.float32)
+    return rays
+
+
+def test_full_height_volume_with_extreme_coordinates(port, ref, hostcore):
+    v = extreme_volume(ref)
+    sd = port.find_subdags(v.nodes(), v.root())
+    # four occupied octants; the one holding a single voxel chains all the way down to a MATERIAL node at
+    # height 0 (the "FIXME" case of raytracing.cpp:448-449, quirk Q2), the others branch at height 31
+    assert sd["height"].max() == 31 and (sd["node"] > 0).sum() == 4 and ((sd["node"] > 0) & (sd["node"] < 256)).sum() == 1
+    rays = extreme_rays(40000, seed=12)
+    for surf, mf in [(True, -1.0), (True, 0.0035), (False, 0.05)]:
+        got, want, mask = reference_hits(v, port, rays, surf, mf)
+        assert mask.mean() > 0.99
+        assert_hits_identical(got[mask], want, "extreme coordinates")
+        assert_hits_identical(hostcore(v.nodes(), sd, rays, surf, mf), got, "extreme coordinates, device core on host")
+    assert want["hit"].sum() > 100
