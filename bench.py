@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--scene-log2", type=int, default=SCENE_LOG2)
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (reported as such)")
     ap.add_argument("--option", action="append", default=[], help="key=value passed to cbq_set_option")
-    ap.add_argument("--spp", type=int, default=4)
+    ap.add_argument("--spp", type=int, default=8)
     ap.add_argument("--bounces", type=int, default=4)
     ap.add_argument("--random-rays", type=int, default=100_000_000)
     return ap.parse_args()
@@ -400,7 +400,7 @@ def main():
     if args.workload == "primary":
         d_accum = torch.zeros(HEIGHT * WIDTH * 3, dtype=torch.float32, device=dev)
         p = api.pt_params(WIDTH, HEIGHT, spp=args.spp, bounces=args.bounces, variant=api.VARIANT_RECURSIVE, frame_id=0)
-        ctx.render_device(cam, api.pt_params(WIDTH, HEIGHT, spp=1, bounces=args.bounces, variant=api.VARIANT_RECURSIVE), d_accum.data_ptr(), stream)
+        ctx.render_device(cam, p, d_accum.data_ptr(), stream)     # warm-up with the same shape (buffers get sized here)
         torch.cuda.synchronize()
         d_accum.zero_()
         a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

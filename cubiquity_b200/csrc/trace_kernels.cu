@@ -156,16 +156,17 @@ struct FlagSink {
 #define CBQ_TRACE_MIN_BLOCKS 4
 #endif
 
-template <bool kSurface, bool kLodOff, typename Source, typename Sink>
+template <bool kSurface, bool kLodOff, bool kDeviceCount, typename Source, typename Sink>
 __global__ void __launch_bounds__(256, CBQ_TRACE_MIN_BLOCKS)
 tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict__ subdagsGlobal, Source source,
-	Sink sink, uint64_t count, const unsigned long long* __restrict__ countPtr, uint32_t countScale,
+	Sink sink, const uint64_t hostCount, const unsigned long long* __restrict__ countPtr, uint32_t countScale,
 	float maxFootprint, int refillThreshold,
 	unsigned long long* __restrict__ queue, unsigned long long* __restrict__ abandoned)
 {
 	// The batch size may live on the device (wavefront path tracer: the number of surviving paths is
-	// produced by the previous kernel), so no host round trip is needed between bounces.
-	if (countPtr) count = (uint64_t)(*countPtr) * countScale;
+	// produced by the previous kernel), so no host round trip is needed between bounces. The plain
+	// instantiation keeps it a kernel parameter (constant bank, no registers).
+	const uint64_t count = kDeviceCount ? (uint64_t)(*countPtr) * countScale : hostCount;
 	extern __shared__ uint32_t stackMem[];
 	__shared__ SubDag subdags[8];
 	if (threadIdx.x < 64) reinterpret_cast<uint32_t*>(subdags)[threadIdx.x] = reinterpret_cast<const uint32_t*>(subdagsGlobal)[threadIdx.x];
@@ -224,7 +225,11 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 			Hit out;
 			StepResult res;
 			if (s.phase == kPhaseOctant) { stack.reset(); res = stepOctant2(s, subdags); }
+#ifdef CBQ_STEP_V2
 			else res = stepEsvo2<kLodOff>(s, nodes, stack, maxFootprint, kSurface, out);
+#else
+			else res = tripEsvo3<kLodOff>(s, nodes, stack, maxFootprint, kSurface, out);
+#endif
 			if (res != kStepContinue) {
 				if (res == kStepHit) {
 					if (!kSurface) { out.material = 0; out.normal[0] = out.normal[1] = out.normal[2] = 0.0f; }
@@ -318,10 +323,19 @@ randomRays(uint64_t seed, float lx, float ly, float lz, float ex, float ey, floa
 	}
 }
 
+template <typename Kernel, typename Source, typename Sink>
+cudaError_t launchKernel(Kernel kernel, const TraceArgs& a, const Source& src, const Sink& sink, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream);
+
 template <bool kSurface, bool kLodOff, typename Source, typename Sink>
 cudaError_t launchPersistentImpl(const TraceArgs& a, const Source& src, const Sink& sink, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
 {
-	auto kernel = tracePersistent<kSurface, kLodOff, Source, Sink>;
+	if (a.countPtr) return launchKernel(tracePersistent<kSurface, kLodOff, true, Source, Sink>, a, src, sink, tickets, cfg, stream);
+	return launchKernel(tracePersistent<kSurface, kLodOff, false, Source, Sink>, a, src, sink, tickets, cfg, stream);
+}
+
+template <typename Kernel, typename Source, typename Sink>
+cudaError_t launchKernel(Kernel kernel, const TraceArgs& a, const Source& src, const Sink& sink, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
+{
 	const size_t smem = (size_t)cfg.stackLevels * (size_t)cfg.blockThreads * sizeof(uint32_t);
 	cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;

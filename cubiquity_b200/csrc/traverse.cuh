@@ -36,6 +36,7 @@ namespace cbq {
 constexpr uint32_t kMaterialCount = 256;   // Internals::MaterialCount, storage.h:55
 constexpr float kFltMax = 3.402823466e+38f;
 constexpr uint32_t kNoMaterial = 0xffffffffu;
+constexpr uint32_t kNeedFetch = 0xffffffffu;   // never a real child: indices are < node count <= 2^32 - 1
 
 struct SubDag {          // struct SubDAG, raytracing.h:57-65 (32 bytes)
 	int32_t lower[3];
@@ -110,6 +111,8 @@ struct RayState {
 	// childT0 / childT1 of raytracing.cpp:259,270 for the current childPos, carried between steps.
 	float Lx, Ly, Lz;
 	float Ux, Uy, Uz;
+	// V3 only: the node word fetched for the current child (kNeedFetch = not fetched yet).
+	uint32_t child;
 };
 
 template <typename Nodes>
@@ -387,6 +390,7 @@ CBQ_HD StepResult stepOctant2(RayState& s, const SubDag* subdags)
 			s.idBits = (bx ? 1u : 0u) | (by ? 2u : 0u) | (bz ? 4u : 0u);
 			s.lastExit = exit;
 			s.trips = iterationCap(h);      // counts DOWN in V2
+			s.child = kNeedFetch;
 			s.phase = kPhaseEsvo;
 			return kStepContinue;
 		}
@@ -489,6 +493,127 @@ CBQ_HD StepResult stepEsvo2(RayState& s, const Nodes& nodes, Stack& stack, float
 	return kStepContinue;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// V3: the V2 trip split into two SECTIONS that a warp executes back to back,
+//     descendSection: lanes whose current child is OCCUPIED descend (or hit),
+//     advanceSection: lanes whose current child is EMPTY advance (or pop),
+// each starting with "fetch the child word unless it is already known". In V2 a lane performs one
+// event per warp step while the warp pays for BOTH divergent paths every step; here a lane that
+// descends and lands on an empty child advances in the same trip (and an advance followed by a
+// descend takes consecutive sections too), so the same instruction stream retires ~1.4 events per
+// lane. One fetch == one trip of the reference's loop (raytracing.cpp:253-367), so the trip budget
+// and every arithmetic result are exactly those of V2.
+
+template <typename Nodes>
+CBQ_HD bool fetchChild(RayState& s, const Nodes& nodes)
+{
+	if (s.child != kNeedFetch) return true;
+	if (s.trips == 0u) return false;          // abandoned
+	s.trips--;
+	s.child = nodes.child(s.node, s.idBits ^ s.signBits);
+	return true;
+}
+
+template <bool kLodOff, typename Nodes, typename Stack>
+CBQ_HD StepResult descendSection(RayState& s, const Nodes& nodes, Stack& stack, float maxFootprint, const bool kSurface, Hit& out)
+{
+	if (!fetchChild(s, nodes)) return kStepAbandoned;
+	const uint32_t child = s.child;
+	if (child == 0u) return kStepContinue;    // the advance section's business
+	const float tExit = min3(s.Ux, s.Uy, s.Uz);
+	const float tEntry = max3(s.Lx, s.Ly, s.Lz);
+	const bool internal = child >= kMaterialCount;
+	const bool bigEnough = kLodOff ? lodOffTest(tExit, s.childSize) : (((float)s.childSize / tExit) > maxFootprint);
+	if (internal && bigEnough) {
+		// PUSH (raytracing.cpp:279-301)
+		if (tExit < s.lastExit) stack.store(s.height, s.node);
+		s.lastExit = tExit;
+		s.height--;
+		s.node = child;
+		const uint32_t half = (uint32_t)s.childSize >> 1;
+		s.childSize = (int)half;
+		const int cx = (int)((uint32_t)s.px + half), cy = (int)((uint32_t)s.py + half), cz = (int)((uint32_t)s.pz + half);
+		const float fx = (float)cx, fy = (float)cy, fz = (float)cz;
+		const float mx = (fx - s.ox) * s.ix, my = (fy - s.oy) * s.iy, mz = (fz - s.oz) * s.iz;
+		bool bx = mx < tEntry, by = my < tEntry, bz = mz < tEntry;
+		if (tEntry <= 0.0f) { bx |= (s.ox >= fx); by |= (s.oy >= fy); bz |= (s.oz >= fz); }
+		s.px = bx ? cx : s.px; s.py = by ? cy : s.py; s.pz = bz ? cz : s.pz;
+		s.Lx = bx ? mx : s.Lx; s.Ly = by ? my : s.Ly; s.Lz = bz ? mz : s.Lz;
+		s.Ux = bx ? s.Ux : mx; s.Uy = by ? s.Uy : my; s.Uz = bz ? s.Uz : mz;
+		s.idBits = (bx ? 1u : 0u) | (by ? 2u : 0u) | (bz ? 4u : 0u);
+		s.child = kNeedFetch;
+		return kStepContinue;
+	}
+	// HIT (raytracing.cpp:302-320)
+	out.hit = 1;
+	out.distance = tEntry;
+	if (kSurface) {
+		out.material = nearestMaterial(nodes, child, s.signBits);
+		if (out.material == kNoMaterial) return kStepAbandoned;
+		const float sx = (s.signBits & 1u) ? -1.0f : 1.0f, sy = (s.signBits & 2u) ? -1.0f : 1.0f, sz = (s.signBits & 4u) ? -1.0f : 1.0f;
+		out.normal[0] = ((tEntry == s.Lx) ? 1.0f : 0.0f) * (-sx);
+		out.normal[1] = ((tEntry == s.Ly) ? 1.0f : 0.0f) * (-sy);
+		out.normal[2] = ((tEntry == s.Lz) ? 1.0f : 0.0f) * (-sz);
+	}
+	return kStepHit;
+}
+
+template <typename Nodes, typename Stack>
+CBQ_HD StepResult advanceSection(RayState& s, const Nodes& nodes, Stack& stack)
+{
+	if (!fetchChild(s, nodes)) return kStepAbandoned;
+	if (s.child != 0u) return kStepContinue;  // occupied: the next descend section's business
+	s.child = kNeedFetch;
+	// ADVANCE (raytracing.cpp:325-332)
+	const float tExit = min3(s.Ux, s.Uy, s.Uz);
+	const bool fx = s.Ux <= tExit, fy = s.Uy <= tExit, fz = s.Uz <= tExit;
+	const uint32_t flips = (fx ? 1u : 0u) | (fy ? 2u : 0u) | (fz ? 4u : 0u);
+	const uint32_t cs = (uint32_t)s.childSize;
+	const int oldx = s.px, oldy = s.py, oldz = s.pz;
+	s.px = (int)((uint32_t)s.px + (fx ? cs : 0u));
+	s.py = (int)((uint32_t)s.py + (fy ? cs : 0u));
+	s.pz = (int)((uint32_t)s.pz + (fz ? cs : 0u));
+	const bool stayed = (s.idBits & flips) == 0u;
+	s.idBits ^= flips;
+	if (stayed) {
+		const float nx = planeT((int)((uint32_t)s.px + cs), s.ox, s.ix);
+		const float ny = planeT((int)((uint32_t)s.py + cs), s.oy, s.iy);
+		const float nz = planeT((int)((uint32_t)s.pz + cs), s.oz, s.iz);
+		s.Lx = fx ? s.Ux : s.Lx; s.Ly = fy ? s.Uy : s.Ly; s.Lz = fz ? s.Uz : s.Lz;
+		s.Ux = fx ? nx : s.Ux; s.Uy = fy ? ny : s.Uy; s.Uz = fz ? nz : s.Uz;
+		return kStepContinue;
+	}
+	// POP (raytracing.cpp:339-364)
+	const uint32_t diff = (uint32_t)(oldx ^ s.px) | (uint32_t)(oldy ^ s.py) | (uint32_t)(oldz ^ s.pz);
+	const int msb = findMsb(diff);
+	s.height = msb + 1;
+	if (s.height > s.startHeight) return leaveSubDag(s);
+	s.node = stack.load(s.height);
+	const uint32_t big = 1u << msb;
+	s.childSize = (int)big;
+	const uint32_t keep = 0u - big;
+	s.idBits = (((uint32_t)s.px >> msb) & 1u) | ((((uint32_t)s.py >> msb) & 1u) << 1) | ((((uint32_t)s.pz >> msb) & 1u) << 2);
+	s.px = (int)((uint32_t)s.px & keep);
+	s.py = (int)((uint32_t)s.py & keep);
+	s.pz = (int)((uint32_t)s.pz & keep);
+	s.lastExit = 0.0f;
+	s.Lx = planeT(s.px, s.ox, s.ix); s.Ly = planeT(s.py, s.oy, s.iy); s.Lz = planeT(s.pz, s.oz, s.iz);
+	s.Ux = planeT((int)((uint32_t)s.px + big), s.ox, s.ix);
+	s.Uy = planeT((int)((uint32_t)s.py + big), s.oy, s.iy);
+	s.Uz = planeT((int)((uint32_t)s.pz + big), s.oz, s.iz);
+	return kStepContinue;
+}
+
+// One V3 trip for a lane that is inside a sub-DAG: descend section, then advance section.
+template <bool kLodOff, typename Nodes, typename Stack>
+CBQ_HD StepResult tripEsvo3(RayState& s, const Nodes& nodes, Stack& stack, float maxFootprint, const bool kSurface, Hit& out)
+{
+	StepResult res = descendSection<kLodOff>(s, nodes, stack, maxFootprint, kSurface, out);
+	if (res == kStepContinue && s.phase == kPhaseEsvo) res = advanceSection(s, nodes, stack);
+	return res;
+}
+
 // Fill in the fields intersectVolume adds after a hit (raytracing.cpp:463-466).
 CBQ_HD void finishHit(Hit& out, const Ray& r)
 {
@@ -542,5 +667,23 @@ CBQ_HD void traceRay2(const Ray& r, const Nodes& nodes, const SubDag* subdags, S
 	}
 }
 
+
+// Whole ray with the V3 trips.
+template <bool kLodOff, typename Nodes, typename Stack>
+CBQ_HD void traceRay3(const Ray& r, const Nodes& nodes, const SubDag* subdags, Stack& stack, float maxFootprint, const bool kSurface, Hit& out)
+{
+	clearHit(out);
+	RayState s;
+	beginRay(s, r);
+	for (;;) {
+		StepResult res;
+		if (s.phase == kPhaseOctant) res = stepOctant2(s, subdags);
+		else res = tripEsvo3<kLodOff>(s, nodes, stack, maxFootprint, kSurface, out);
+		if (res == kStepContinue) continue;
+		if (res == kStepHit) { finishHit(out, r); return; }
+		if (res == kStepAbandoned) { clearHit(out); out.status = 1; return; }
+		return;
+	}
+}
 
 } // namespace cbq

@@ -66,12 +66,13 @@ def hostcore():
     lib = C.CDLL(so)
     lib.host_core_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_float, C.c_void_p]
     lib.host_core_trace_v2.argtypes = lib.host_core_trace.argtypes
+    lib.host_core_trace_v3.argtypes = lib.host_core_trace.argtypes
 
-    def trace(nodes, subdags, rays, surface=True, max_footprint=-1.0, version=2):
+    def trace(nodes, subdags, rays, surface=True, max_footprint=-1.0, version=3):
         nodes = np.ascontiguousarray(nodes, dtype=np.uint32)
         rays = np.ascontiguousarray(rays, dtype=pyoracle.RAY_DTYPE)
         hits = np.zeros(len(rays), dtype=pyoracle.HIT_DTYPE)
-        fn = lib.host_core_trace_v2 if version == 2 else lib.host_core_trace
+        fn = {1: lib.host_core_trace, 2: lib.host_core_trace_v2, 3: lib.host_core_trace_v3}[version]
         fn(nodes.ctypes.data, subdags.ctypes.data, rays.ctypes.data, len(rays), int(surface),
                             float(max_footprint), hits.ctypes.data)
         return hits

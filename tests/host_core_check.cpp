@@ -51,3 +51,20 @@ extern "C" void host_core_trace_v2(const uint32_t* nodes, const void* subdags, c
 		else cbq::traceRay2<false>(r[i], hn, sd, st, maxFootprint, surface != 0, h[i]);
 	}
 }
+
+// The V3 trips (descend section + advance section).
+extern "C" void host_core_trace_v3(const uint32_t* nodes, const void* subdags, const void* rays, uint64_t n,
+	int surface, float maxFootprint, void* hits)
+{
+	const cbq::Ray* r = static_cast<const cbq::Ray*>(rays);
+	cbq::Hit* h = static_cast<cbq::Hit*>(hits);
+	const cbq::SubDag* sd = static_cast<const cbq::SubDag*>(subdags);
+	HostNodes hn{ nodes };
+	const bool lodOff = (maxFootprint == -1.0f);
+	for (uint64_t i = 0; i < n; i++) {
+		HostStack st;
+		std::memset(&st, 0, sizeof(st));
+		if (lodOff) cbq::traceRay3<true>(r[i], hn, sd, st, maxFootprint, surface != 0, h[i]);
+		else cbq::traceRay3<false>(r[i], hn, sd, st, maxFootprint, surface != 0, h[i]);
+	}
+}

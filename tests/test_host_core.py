@@ -11,7 +11,7 @@ from conftest import assert_hits_identical, mixed_rays
 
 @pytest.mark.parametrize("kind,size_log2", [("sphere_noise", 7), ("terrain", 8), ("soup", 7), ("city", 10)])
 @pytest.mark.parametrize("surface,max_footprint", [(True, -1.0), (False, -1.0), (True, 0.0035), (True, 0.05)])
-@pytest.mark.parametrize("version", [1, 2])
+@pytest.mark.parametrize("version", [1, 2, 3])
 def test_core_matches_oracle(port, hostcore, scenes, kind, size_log2, surface, max_footprint, version):
     sc = scenes(kind, size_log2)
     sd = port.find_subdags(sc.nodes, sc.root)
@@ -32,5 +32,6 @@ def test_core_abandons_the_same_rays(port, hostcore, scenes):
     want, _, _ = port.trace(sc.nodes, sd, rays, True, -1.0)
     assert want["pad"].sum() > 0
     assert_hits_identical(hostcore(sc.nodes, sd, rays, True, -1.0, version=1), want, "degenerate v1")
-    got = hostcore(sc.nodes, sd, rays, True, -1.0, version=2)
+    assert_hits_identical(hostcore(sc.nodes, sd, rays, True, -1.0, version=2), want, "degenerate v2")
+    got = hostcore(sc.nodes, sd, rays, True, -1.0, version=3)
     assert_hits_identical(got, want, "degenerate")
