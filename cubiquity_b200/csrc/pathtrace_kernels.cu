@@ -240,7 +240,7 @@ renderPersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict
 			Hit out;
 			StepResult res;
 			if (s.phase == kPhaseOctant) { stack.reset(); res = stepOctant2(s, subdags); }
-			else res = tripEsvo3<false>(s, nodes, stack, p.max_footprint, t.kind == kKindSurface, out);
+			else res = stepEsvo2<false>(s, nodes, stack, p.max_footprint, t.kind == kKindSurface, out);
 			if (res == kStepContinue) continue;
 
 			const bool hit = (res == kStepHit);

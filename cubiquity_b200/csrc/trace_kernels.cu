@@ -225,10 +225,10 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 			Hit out;
 			StepResult res;
 			if (s.phase == kPhaseOctant) { stack.reset(); res = stepOctant2(s, subdags); }
-#ifdef CBQ_STEP_V2
-			else res = stepEsvo2<kLodOff>(s, nodes, stack, maxFootprint, kSurface, out);
-#else
+#ifdef CBQ_TRIP_V3   // measured slower on B200 (3.58 vs 4.23 Grays/s): two exposed load->use waits per trip; kept for A/B
 			else res = tripEsvo3<kLodOff>(s, nodes, stack, maxFootprint, kSurface, out);
+#else
+			else res = stepEsvo2<kLodOff>(s, nodes, stack, maxFootprint, kSurface, out);
 #endif
 			if (res != kStepContinue) {
 				if (res == kStepHit) {

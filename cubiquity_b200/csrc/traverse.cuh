@@ -504,6 +504,9 @@ CBQ_HD StepResult stepEsvo2(RayState& s, const Nodes& nodes, Stack& stack, float
 // descend takes consecutive sections too), so the same instruction stream retires ~1.4 events per
 // lane. One fetch == one trip of the reference's loop (raytracing.cpp:253-367), so the trip budget
 // and every arithmetic result are exactly those of V2.
+// MEASURED (profiles/r01_analysis.md): a warp-scheduling simulation predicted -13 % instructions, the
+// B200 says 3.58 vs 4.23 Grays/s -- each section exposes its own load->use wait, and 63 registers. The
+// kernels therefore use V2; V3 stays here (host-checked, -DCBQ_TRIP_V3) as a recorded negative result.
 
 template <typename Nodes>
 CBQ_HD bool fetchChild(RayState& s, const Nodes& nodes)
