@@ -402,14 +402,19 @@ CBQ_HD StepResult stepOctant2(RayState& s, const SubDag* subdags)
 	return (s.octant <= 7) ? kStepContinue : kStepMiss;
 }
 
+// `child` is the node word of the current position, nodes.child(s.node, s.idBits ^ s.signBits). The
+// caller supplies it so that a kernel can issue that load at the END of the previous step (right after
+// the position changed) and hide its latency behind the loop's bookkeeping: fetchNext() below.
+template <typename Nodes>
+CBQ_HD uint32_t fetchNext(const RayState& s, const Nodes& nodes) { return nodes.child(s.node, s.idBits ^ s.signBits); }
+
 template <bool kLodOff, typename Nodes, typename Stack>
-CBQ_HD StepResult stepEsvo2(RayState& s, const Nodes& nodes, Stack& stack, float maxFootprint, const bool kSurface, Hit& out)
+CBQ_HD StepResult stepEsvo2(RayState& s, const uint32_t child, const Nodes& nodes, Stack& stack, float maxFootprint, const bool kSurface, Hit& out)
 {
 	if (s.trips == 0u) return kStepAbandoned;
 	s.trips--;
 
 	const float tExit = min3(s.Ux, s.Uy, s.Uz);
-	const uint32_t child = nodes.child(s.node, s.idBits ^ s.signBits);
 
 	if (child > 0) {
 		const float tEntry = max3(s.Lx, s.Ly, s.Lz);
@@ -662,8 +667,8 @@ CBQ_HD void traceRay2(const Ray& r, const Nodes& nodes, const SubDag* subdags, S
 	for (;;) {
 		StepResult res;
 		if (s.phase == kPhaseOctant) res = stepOctant2(s, subdags);
-		else res = stepEsvo2<kLodOff>(s, nodes, stack, maxFootprint, kSurface, out);
-		if (res == kStepContinue) continue;
+		else res = stepEsvo2<kLodOff>(s, s.child, nodes, stack, maxFootprint, kSurface, out);
+		if (res == kStepContinue) { if (s.phase == kPhaseEsvo) s.child = fetchNext(s, nodes); continue; }
 		if (res == kStepHit) { finishHit(out, r); return; }
 		if (res == kStepAbandoned) { clearHit(out); out.status = 1; return; }
 		return;
