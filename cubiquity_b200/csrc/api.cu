@@ -285,7 +285,7 @@ int cbq_create(int device, cbq_context** out)
 	ctx->cfg.refillThreshold = 8;    // robust default: +68 % on incoherent rays, -7 % on coherent ones (profiles/r01_sweeps.md)
 	ctx->cfg.kernel = 0;
 	ctx->cfg.stackLevels = 33;
-	ctx->cfg.sampleGroup = 8;    // 789 vs 734 (4) vs 512 (1) Mspp/s at 1080p, 4 bounces (profiles/r01_analysis.md)
+	ctx->cfg.sampleGroup = 0;    // auto; 1080p, 4 bounces: 512 / 734 / 789 / 812 M spp/s for groups of 1 / 4 / 8 / 16 (profiles/r01_analysis.md)
 	*out = ctx;
 	return CBQ_OK;
 }
@@ -551,9 +551,11 @@ int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_para
 	}
 	const size_t pixels = (size_t)(p->x1 - p->x0) * cbq::bandedRowCount(p->y1 - p->y0, p->band_count, p->band_index);
 	if (pixels == 0) return CBQ_OK;
-	// Samples traced together: the option, capped so that a wave stays below 32 M paths (~8.5 GB of buffers).
+	// Samples traced together. 0 = auto: aim at ~16 M paths per wave (8 samples of a 1080p frame, 16 of a
+	// 1/8 share), between 1 and 16; an explicit value is still capped at 32 M paths (~8.5 GB of buffers).
 	cbq::LaunchConfig renderCfg = ctx->cfg;
-	renderCfg.sampleGroup = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->cfg.sampleGroup, (32u << 20) / pixels));
+	if (ctx->cfg.sampleGroup <= 0) renderCfg.sampleGroup = (int)std::max<size_t>(1, std::min<size_t>(16, (16u << 20) / pixels));
+	else renderCfg.sampleGroup = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->cfg.sampleGroup, (32u << 20) / pixels));
 	const size_t paths = pixels * std::min<size_t>(p->spp, (size_t)renderCfg.sampleGroup);
 	if (paths > 0xffffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "rectangle too large for 32-bit path ids");
 	if (paths > ctx->wavefront.pixelCapacity) CBQ_CUDA(cudaDeviceSynchronize());   // buffers may still be in use
@@ -614,7 +616,7 @@ int cbq_set_option(cbq_context* ctx, const char* key, int64_t value)
 		if (value < 0 || value > 1) return fail(CBQ_ERROR_INVALID_ARGUMENT, "kernel must be 0 or 1");
 		ctx->cfg.kernel = (int)value;
 	} else if (k == "sample_group") {
-		if (value < 1 || value > 16) return fail(CBQ_ERROR_INVALID_ARGUMENT, "sample_group must be in [1, 16]");
+		if (value < 0 || value > 16) return fail(CBQ_ERROR_INVALID_ARGUMENT, "sample_group must be 0 (auto) or in [1, 16]");
 		ctx->cfg.sampleGroup = (int)value;
 	} else if (k == "render_mode") {
 		if (value < 0 || value > 1) return fail(CBQ_ERROR_INVALID_ARGUMENT, "render_mode must be 0 (wavefront) or 1 (megakernel)");

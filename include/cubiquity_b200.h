@@ -190,7 +190,7 @@ int cbq_host_free(void* p);
 /* Options: "block_threads", "blocks_per_sm", "refill_threshold" (idle lanes of a warp that trigger a
  * mid-flight refill, 1..32), "l2_persist" (0/1), "kernel" (0 = persistent queue kernel, 1 = plain
  * one-thread-per-ray), "render_mode" (0 = wavefront path tracer, 1 = persistent megakernel), "sample_group" (samples of a
- * pixel the wavefront tracer traces together, 1..16). */
+ * pixel the wavefront tracer traces together, 1..16; 0 = choose from the size of the rectangle). */
 int cbq_set_option(cbq_context* ctx, const char* key, int64_t value);
 int cbq_get_option(cbq_context* ctx, const char* key, int64_t* value);
 

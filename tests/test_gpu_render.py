@@ -140,7 +140,7 @@ def test_sample_group_size_does_not_change_the_image(gpu, port, api, scenes):
             gpu.set_option("sample_group", g)
             imgs.append(gpu.render(cam, p))
     finally:
-        gpu.set_option("sample_group", 8)
+        gpu.set_option("sample_group", 0)
     for im in imgs[1:]:
         assert np.array_equal(im.view(np.uint32), imgs[0].view(np.uint32))
 

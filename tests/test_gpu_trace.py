@@ -255,7 +255,7 @@ def test_error_codes_and_option_validation(gpu, api, scenes):
             fresh.render(api.camera_from_pose([0, 0, 0], 0, 0), api.pt_params(8, 8))
         assert e.value.code == api.ERROR_NO_VOLUME
         for key, bad in [("block_threads", 100), ("block_threads", 512), ("blocks_per_sm", 0), ("refill_threshold", 33),
-                         ("kernel", 2), ("render_mode", 5), ("sample_group", 0), ("no_such_option", 1)]:
+                         ("kernel", 2), ("render_mode", 5), ("sample_group", 17), ("no_such_option", 1)]:
             with pytest.raises(api.CubiquityError) as e:
                 fresh.set_option(key, bad)
             assert e.value.code == api.ERROR_INVALID_ARGUMENT
