@@ -240,8 +240,8 @@ renderPersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict
 			Hit out;
 			StepResult res;
 			if (s.phase == kPhaseOctant) { stack.reset(); res = stepOctant2(s, subdags); }
-			else res = stepEsvo2<false>(s, s.child, nodes, stack, p.max_footprint, t.kind == kKindSurface, out);
-			if (res == kStepContinue) { if (s.phase == kPhaseEsvo) s.child = fetchNext(s, nodes); continue; }
+			else res = stepEsvo2<false>(s, fetchNext(s, nodes), nodes, stack, p.max_footprint, t.kind == kKindSurface, out);
+			if (res == kStepContinue) continue;
 
 			const bool hit = (res == kStepHit);
 			if (res == kStepAbandoned) atomicAdd(abandoned, 1ull);   // treated as a miss

@@ -227,15 +227,15 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 			if (s.phase == kPhaseOctant) { stack.reset(); res = stepOctant2(s, subdags); }
 #ifdef CBQ_TRIP_V3   // measured slower on B200 (3.58 vs 4.23 Grays/s): two exposed load->use waits per trip; kept for A/B
 			else res = tripEsvo3<kLodOff>(s, nodes, stack, maxFootprint, kSurface, out);
-#elif defined(CBQ_NO_PIPELINED_FETCH)
-			else res = stepEsvo2<kLodOff>(s, fetchNext(s, nodes), nodes, stack, maxFootprint, kSurface, out);
-#else
+#elif defined(CBQ_PIPELINED_FETCH)   // measured 2.5 % slower on primary rays, neutral on random rays: off
 			else res = stepEsvo2<kLodOff>(s, s.child, nodes, stack, maxFootprint, kSurface, out);
+#else
+			else res = stepEsvo2<kLodOff>(s, fetchNext(s, nodes), nodes, stack, maxFootprint, kSurface, out);
 #endif
 			if (res == kStepContinue) {
-				// Software-pipelined node fetch: the word the NEXT step needs is requested now, so the
-				// load->use distance spans the loop bookkeeping instead of being zero.
-#if !defined(CBQ_NO_PIPELINED_FETCH) && !defined(CBQ_TRIP_V3)
+				// Optional software-pipelined node fetch: request the word the NEXT step needs now, so the
+				// load->use distance spans the loop bookkeeping (-DCBQ_PIPELINED_FETCH; see the A/B above).
+#if defined(CBQ_PIPELINED_FETCH) && !defined(CBQ_TRIP_V3)
 				if (s.phase == kPhaseEsvo) s.child = fetchNext(s, nodes);
 #endif
 			} else {

@@ -667,8 +667,8 @@ CBQ_HD void traceRay2(const Ray& r, const Nodes& nodes, const SubDag* subdags, S
 	for (;;) {
 		StepResult res;
 		if (s.phase == kPhaseOctant) res = stepOctant2(s, subdags);
-		else res = stepEsvo2<kLodOff>(s, s.child, nodes, stack, maxFootprint, kSurface, out);
-		if (res == kStepContinue) { if (s.phase == kPhaseEsvo) s.child = fetchNext(s, nodes); continue; }
+		else res = stepEsvo2<kLodOff>(s, fetchNext(s, nodes), nodes, stack, maxFootprint, kSurface, out);
+		if (res == kStepContinue) continue;
 		if (res == kStepHit) { finishHit(out, r); return; }
 		if (res == kStepAbandoned) { clearHit(out); out.status = 1; return; }
 		return;
