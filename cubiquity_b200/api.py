@@ -60,7 +60,7 @@ EXPORTS = [
     "cbq_create", "cbq_destroy", "cbq_last_error", "cbq_device_count", "cbq_synchronize",
     "cbq_upload", "cbq_update", "cbq_set_colours", "cbq_get_subdags", "cbq_find_subdags",
     "cbq_download_nodes", "cbq_node_count",
-    "cbq_trace", "cbq_trace_device", "cbq_camera_from_pose", "cbq_primary_rays_device", "cbq_random_rays_device",
+    "cbq_trace", "cbq_trace_device", "cbq_camera_from_pose", "cbq_primary_rays_device", "cbq_primary_rays_tiled_device", "cbq_random_rays_device",
     "cbq_raycast_frame_device",
     "cbq_render", "cbq_render_device",
     "cbq_host_alloc", "cbq_host_free", "cbq_set_option", "cbq_get_option", "cbq_get_counter", "cbq_reset_counters",
@@ -101,6 +101,7 @@ def load_library():
     L.cbq_trace_device.argtypes = [vp, vp, u64, u32, f32, vp, vp]
     L.cbq_camera_from_pose.argtypes = [C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double, C.POINTER(Camera)]
     L.cbq_primary_rays_device.argtypes = [vp, C.POINTER(Camera), u32, u32, vp, vp]
+    L.cbq_primary_rays_tiled_device.argtypes = [vp, C.POINTER(Camera), u32, u32, vp, vp, vp]
     L.cbq_random_rays_device.argtypes = [vp, u64, C.POINTER(C.c_float), C.POINTER(C.c_float), u64, vp, vp]
     L.cbq_raycast_frame_device.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, f32, vp, vp]
     L.cbq_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(PtParams), vp]
@@ -316,6 +317,10 @@ class Context:
     def primary_rays_device(self, cam, width, height, d_rays, stream=None):
         _check(self.L.cbq_primary_rays_device(self._h, C.byref(cam), int(width), int(height), C.c_void_p(int(d_rays)),
                                               _stream(stream)))
+
+    def primary_rays_tiled_device(self, cam, width, height, d_rays, d_pixel_of=None, stream=None):
+        _check(self.L.cbq_primary_rays_tiled_device(self._h, C.byref(cam), int(width), int(height), C.c_void_p(int(d_rays)),
+                                                    C.c_void_p(int(d_pixel_of)) if d_pixel_of else None, _stream(stream)))
 
     def random_rays_device(self, seed, lower, upper, n, d_rays, stream=None):
         lo = (C.c_float * 3)(*[float(v) for v in lower])

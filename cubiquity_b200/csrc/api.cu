@@ -507,6 +507,18 @@ int cbq_primary_rays_device(cbq_context* ctx, const cbq_camera* cam, uint32_t wi
 	return CBQ_OK;
 }
 
+int cbq_primary_rays_tiled_device(cbq_context* ctx, const cbq_camera* cam, uint32_t width, uint32_t height, cbq_ray* d_rays,
+	uint32_t* d_pixel_of, void* stream)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!cam || !d_rays || !width || !height) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad argument");
+	if ((width % 8u) != 0 || (height % 4u) != 0) return fail(CBQ_ERROR_INVALID_ARGUMENT, "tiled ray order needs width %% 8 == 0 and height %% 4 == 0");
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	CBQ_CUDA(cbq::launchPrimaryRays(*cam, width, height, reinterpret_cast<cbq::Ray*>(d_rays), s, 1, d_pixel_of));
+	ctx->launches++;
+	return CBQ_OK;
+}
+
 int cbq_random_rays_device(cbq_context* ctx, uint64_t seed, const float lower[3], const float upper[3], uint64_t n, cbq_ray* d_rays, void* stream)
 {
 	int rc = bind(ctx); if (rc) return rc;

@@ -77,7 +77,7 @@ struct TraceArgs {
 };
 
 cudaError_t launchTrace(const TraceArgs& a, bool surface, const LaunchConfig& cfg, cudaStream_t stream);
-cudaError_t launchPrimaryRays(const cbq_camera& cam, uint32_t width, uint32_t height, Ray* rays, cudaStream_t stream);
+cudaError_t launchPrimaryRays(const cbq_camera& cam, uint32_t width, uint32_t height, Ray* rays, cudaStream_t stream, int tiled = 0, uint32_t* pixelOf = nullptr);
 cudaError_t launchRandomRays(uint64_t seed, const float lower[3], const float upper[3], uint64_t n, Ray* rays, cudaStream_t stream);
 
 struct RenderArgs {

@@ -278,12 +278,22 @@ traceSimple(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict__ su
 	}
 }
 
+// tiled != 0 (needs width % 8 == 0 and height % 4 == 0): ray i belongs to pixel (tile i / 32, lane i % 32) of
+// the 8x4-pixel tile enumeration, so the 32 consecutive rays a warp claims from a buffer form one compact
+// tile ("Morton-ordered primary rays"); `pixelOf` (nullable) receives y * width + x of every ray.
 __global__ void __launch_bounds__(256)
-primaryRays(cbq_camera cam, uint32_t width, uint32_t height, Ray* __restrict__ rays)
+primaryRays(cbq_camera cam, uint32_t width, uint32_t height, int tiled, Ray* __restrict__ rays, uint32_t* __restrict__ pixelOf)
 {
 	const uint64_t total = (uint64_t)width * height;
+	const uint32_t tilesX = width / 8u;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-		const uint32_t x = (uint32_t)(i % width), y = (uint32_t)(i / width);
+		uint32_t x = (uint32_t)(i % width), y = (uint32_t)(i / width);
+		if (tiled) {
+			const uint32_t tile = (uint32_t)(i >> 5), within = (uint32_t)i & 31u;
+			x = (tile % tilesX) * 8u + (within & 7u);
+			y = (tile / tilesX) * 4u + (within >> 3);
+		}
+		if (pixelOf) pixelOf[i] = y * width + x;
 		Ray r;
 		cameraRay(cam, (int)x, (int)y, (int)width, (int)height, r);
 		float2* p = reinterpret_cast<float2*>(rays + i);
@@ -410,13 +420,13 @@ cudaError_t launchRandomRays(uint64_t seed, const float lower[3], const float up
 	return cudaGetLastError();
 }
 
-cudaError_t launchPrimaryRays(const cbq_camera& cam, uint32_t width, uint32_t height, Ray* rays, cudaStream_t stream)
+cudaError_t launchPrimaryRays(const cbq_camera& cam, uint32_t width, uint32_t height, Ray* rays, cudaStream_t stream, int tiled, uint32_t* pixelOf)
 {
 	const uint64_t total = (uint64_t)width * height;
 	uint64_t blocks = (total + 255) / 256;
 	if (blocks > 148u * 8u) blocks = 148u * 8u;
 	if (blocks == 0) blocks = 1;
-	primaryRays<<<(int)blocks, 256, 0, stream>>>(cam, width, height, rays);
+	primaryRays<<<(int)blocks, 256, 0, stream>>>(cam, width, height, tiled, rays, pixelOf);
 	return cudaGetLastError();
 }
 

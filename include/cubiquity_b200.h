@@ -160,6 +160,12 @@ int cbq_camera_from_pose(const double position[3], double pitch, double yaw, dou
 int cbq_primary_rays_device(cbq_context* ctx, const cbq_camera* cam, uint32_t width, uint32_t height,
                             cbq_ray* d_rays, void* stream);
 
+/* The same rays in 8x4-pixel tile order (width % 8 == 0, height % 4 == 0): ray i is pixel (i % 32) of tile
+ * (i / 32), so every 32 consecutive rays -- what one warp claims from a buffer -- are one compact tile
+ * (Morton-like locality for primary rays). d_pixel_of (nullable) receives y * width + x of each ray. */
+int cbq_primary_rays_tiled_device(cbq_context* ctx, const cbq_camera* cam, uint32_t width, uint32_t height,
+                                  cbq_ray* d_rays, uint32_t* d_pixel_of, void* stream);
+
 /* Synthetic collision-query rays generated on the device (BASELINE config 3): origin uniform in
  * [lower, upper), direction uniform on the sphere, from a counter-based hash of (seed, ray index), so
  * ray i is the same whatever the batch it is generated in. cubiquity_b200/rays.py:counter_rays is the

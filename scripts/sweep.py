@@ -74,6 +74,36 @@ def main():
     if what == "render":
         render_sweep(ctx, scene, dev, stream)
         return
+    if what == "frame":
+        # fused camera path (8x4-pixel tiles per warp) vs the row-major ray buffer, and the L2 window on/off
+        cam = api.default_camera(scene.lower, scene.upper)
+        n = W * H
+        d_rays = torch.empty(n * 6, dtype=torch.float32, device=dev)
+        ctx.primary_rays_device(cam, W, H, d_rays.data_ptr(), stream)
+        d_tiled = torch.empty(n * 6, dtype=torch.float32, device=dev)
+        ctx.primary_rays_tiled_device(cam, W, H, d_tiled.data_ptr(), None, stream)
+        d_hits = torch.zeros(n * 10, dtype=torch.int32, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ctx.set_option("refill_threshold", 32)
+        for l2 in (1, 0):
+            ctx.set_option("l2_persist", l2)
+            for mf in (-1.0, 0.0035):
+                for name, fn in (("buffer_row_major", lambda: ctx.trace_device(d_rays.data_ptr(), n, d_hits.data_ptr(), True, mf, stream)),
+                                 ("buffer_8x4_tiles", lambda: ctx.trace_device(d_tiled.data_ptr(), n, d_hits.data_ptr(), True, mf, stream)),
+                                 ("fused_camera_tiles", lambda: ctx.raycast_frame_device(cam, W, H, d_hits.data_ptr(), True, mf, stream))):
+                    for _ in range(3):
+                        fn()
+                    torch.cuda.synchronize()
+                    ts = []
+                    for _ in range(10):
+                        flush.zero_()
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record(); fn(); b.record()
+                        torch.cuda.synchronize()
+                        ts.append(a.elapsed_time(b))
+                    print(json.dumps({"workload": "frame", "path": name, "l2_persist": l2, "max_footprint": mf, "cold_ms": round(float(np.mean(ts)), 4),
+                                      "cold_grays": round(n / float(np.mean(ts)) / 1e6, 3)}), flush=True)
+        return
     if what == "random":
         n = 8_000_000
         host = R.random_rays(n, scene.lower, scene.upper, seed=100)

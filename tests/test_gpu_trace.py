@@ -291,3 +291,26 @@ def test_two_contexts_from_two_threads(gpu, port, api, scenes):
     for name, sc in (("a", sc_a), ("bb", sc_b)):
         rays, got = results[name]
         assert_hits_identical(got, oracle_hits(port, sc, rays, True, 0.0035), "context " + name)
+
+
+def test_tiled_primary_rays_are_a_permutation_of_the_frame(gpu, port, api, scenes):
+    torch = pytest.importorskip("torch")
+    sc = scenes("terrain", 9)
+    gpu.upload(sc.nodes, sc.root)
+    w, h = 256, 96
+    cam = api.default_camera(sc.lower, sc.upper)
+    ocam = port.camera(list(cam.position), -(float(np.float32(3.14159265358979)) / 4.0), 0.0)
+    want = port.camera_rays(ocam, w, h)
+    d_rays = torch.empty(w * h * 6, dtype=torch.float32, device="cuda")
+    d_pix = torch.empty(w * h, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    gpu.primary_rays_tiled_device(cam, w, h, d_rays.data_ptr(), d_pix.data_ptr(), stream)
+    torch.cuda.synchronize()
+    pix = d_pix.cpu().numpy().astype(np.int64)
+    assert np.array_equal(np.sort(pix), np.arange(w * h))
+    rays = d_rays.cpu().numpy().view(api.RAY_DTYPE).reshape(-1)
+    assert rays.tobytes() == want[pix].tobytes()
+    first = pix[:32]
+    assert set(first % w) == set(range(8)) and set(first // w) == set(range(4))      # one 8x4 tile per 32 rays
+    with pytest.raises(api.CubiquityError):
+        gpu.primary_rays_tiled_device(cam, 100, 96, d_rays.data_ptr(), None, stream)
