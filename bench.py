@@ -344,8 +344,10 @@ def main():
     else:
         n_rays = WIDTH * HEIGHT
         d_rays = torch.empty(n_rays * 6, dtype=torch.float32, device=dev)
-        ctx.primary_rays_device(cam, WIDTH, HEIGHT, d_rays.data_ptr(), stream)
-        workload = "primary rays 1920x1080 vs procedural 4096^3 terrain SVDAG (BASELINE configs[1]), LOD off, surface properties on"
+        # Morton-like ray order (north star): ray i is pixel i % 32 of 8x4-pixel tile i / 32, so the 32 rays a warp
+        # claims are one compact tile; hits come back in the same order. +7 % over row-major (profiles/r01_analysis.md).
+        ctx.primary_rays_tiled_device(cam, WIDTH, HEIGHT, d_rays.data_ptr(), None, stream)
+        workload = "primary rays 1920x1080 (8x4-pixel tile order) vs procedural 4096^3 terrain SVDAG (BASELINE configs[1]), LOD off, surface properties on"
     d_hits = torch.zeros(n_rays * 10, dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # 2x the 126 MB L2
     torch.cuda.synchronize()

@@ -124,6 +124,10 @@ struct cbq_context {
 	cbq::Ray* stageRays[kStages]{};
 	cbq::Hit* stageHits[kStages]{};
 
+	// cbq_raycast_frame_device: primary rays of the frame in 8x4-tile order
+	cbq::Ray* frameRays = nullptr;
+	size_t frameRayCapacity = 0;
+
 	// cbq_render staging
 	float* stageAccum = nullptr;
 	size_t stageAccumBytes = 0;
@@ -302,6 +306,7 @@ void cbq_destroy(cbq_context* ctx)
 		if (ctx->evOut[i]) cudaEventDestroy(ctx->evOut[i]);
 	}
 	cudaFree(ctx->stageAccum);
+	cudaFree(ctx->frameRays);
 	cbq::wavefrontRelease(ctx->wavefront);
 	cudaFree(ctx->queues);
 	cudaFree(ctx->volume);
@@ -536,6 +541,35 @@ int cbq_raycast_frame_device(cbq_context* ctx, const cbq_camera* cam, uint32_t w
 	int rc = bind(ctx); if (rc) return rc;
 	if (!cam || !d_hits || !width || !height) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad argument");
 	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	if ((width % 8u) == 0 && (height % 4u) == 0) {
+		// Generate the frame's rays once, in 8x4-pixel tile order, and trace them from the buffer: 7-17 % faster
+		// than the row-major order and 20 % faster than generating rays inside the trace kernel (which pays for
+		// the camera's double-precision maths twice per ray and for its registers): profiles/r01_analysis.md.
+		if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "no volume uploaded");
+		const size_t n = (size_t)width * height;
+		if (n > ctx->frameRayCapacity) {
+			CBQ_CUDA(cudaDeviceSynchronize());
+			cudaFree(ctx->frameRays); ctx->frameRays = nullptr; ctx->frameRayCapacity = 0;
+			CBQ_CUDA(cudaMalloc(&ctx->frameRays, n * sizeof(cbq::Ray)));
+			ctx->frameRayCapacity = n;
+		}
+		CBQ_CUDA(cbq::launchPrimaryRays(*cam, width, height, ctx->frameRays, s, 1, nullptr));
+		ctx->launches++;
+		cbq::TraceArgs a;
+		std::memset(&a, 0, sizeof(a));
+		a.nodes = ctx->nodesPtr(); a.subdags = ctx->subdagsPtr();
+		a.rays = ctx->frameRays; a.hits = reinterpret_cast<cbq::Hit*>(d_hits); a.count = n; a.maxFootprint = max_footprint;
+		a.abandoned = ctx->abandonedPtr(); a.untileWidth = width;
+		rc = nextQueue(ctx, s, &a.queue); if (rc) return rc;
+		applyL2Window(ctx, s);
+		cbq::LaunchConfig cfg = ctx->cfg;
+		cfg.refillThreshold = 32;
+		cfg.kernel = 0;
+		CBQ_CUDA(cbq::launchTrace(a, (flags & CBQ_TRACE_SURFACE) != 0, cfg, s));
+		ctx->launches++;
+		ctx->raysTraced += n;
+		return CBQ_OK;
+	}
 	return traceDevice(ctx, nullptr, (uint64_t)width * height, flags, max_footprint, reinterpret_cast<cbq::Hit*>(d_hits), s, cam, width, height);
 }
 

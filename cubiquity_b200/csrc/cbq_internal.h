@@ -74,6 +74,7 @@ struct TraceArgs {
 	const unsigned long long* countPtr;
 	uint32_t countScale;
 	uint8_t* flags;
+	uint32_t untileWidth;            // != 0: rays are in 8x4-tile order of an image this wide; write hits row-major
 };
 
 cudaError_t launchTrace(const TraceArgs& a, bool surface, const LaunchConfig& cfg, cudaStream_t stream);

@@ -146,6 +146,18 @@ struct FullSink {
 	static constexpr bool kNeedsPosition = true;
 	__device__ __forceinline__ void write(uint64_t slot, const Hit& h) const { storeHit(hits, slot, h); }
 };
+// Rays arrive in 8x4-tile order (primaryRays, tiled); results go back to row-major pixel order.
+struct TiledSink {
+	Hit* __restrict__ hits;
+	uint32_t width, tilesX;
+	static constexpr bool kNeedsPosition = true;
+	__device__ __forceinline__ void write(uint64_t slot, const Hit& h) const
+	{
+		const uint32_t tile = (uint32_t)(slot >> 5), within = (uint32_t)slot & 31u;
+		const uint32_t x = (tile % tilesX) * 8u + (within & 7u), y = (tile / tilesX) * 4u + (within >> 3);
+		storeHit(hits, (uint64_t)y * width + x, h);
+	}
+};
 struct FlagSink {
 	uint8_t* __restrict__ flags;
 	static constexpr bool kNeedsPosition = false;
@@ -379,6 +391,10 @@ cudaError_t launchPersistent(const TraceArgs& a, bool surface, const Source& src
 	if (a.flags) {
 		// Flag-only results are for shadow rays, which never ask for surface properties.
 		return launchPersistentLod<false>(a, src, FlagSink{ a.flags }, tickets, cfg, stream);
+	}
+	if (a.untileWidth) {
+		const TiledSink sink{ a.hits, a.untileWidth, a.untileWidth / 8u };
+		return surface ? launchPersistentLod<true>(a, src, sink, tickets, cfg, stream) : launchPersistentLod<false>(a, src, sink, tickets, cfg, stream);
 	}
 	return surface ? launchPersistentLod<true>(a, src, FullSink{ a.hits }, tickets, cfg, stream)
 	               : launchPersistentLod<false>(a, src, FullSink{ a.hits }, tickets, cfg, stream);
