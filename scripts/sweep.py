@@ -74,6 +74,19 @@ def main():
     if what == "render":
         render_sweep(ctx, scene, dev, stream)
         return
+    if what == "tiled_refill":
+        cam = api.default_camera(scene.lower, scene.upper)
+        n = W * H
+        d_tiled = torch.empty(n * 6, dtype=torch.float32, device=dev)
+        ctx.primary_rays_tiled_device(cam, W, H, d_tiled.data_ptr(), None, stream)
+        d_hits = torch.zeros(n * 10, dtype=torch.int32, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for thr in (32, 28, 24, 16, 8, 32):
+            ctx.set_option("refill_threshold", thr)
+            for mf in (-1.0, 0.0035):
+                cold, warm = time_config(ctx, d_tiled, n, d_hits, flush, stream, mf=mf)
+                print(json.dumps({"workload": "tiled_refill", "refill_threshold": thr, "max_footprint": mf, "cold_ms": round(cold, 4), "cold_grays": round(n / cold / 1e6, 3)}), flush=True)
+        return
     if what == "frame":
         # fused camera path (8x4-pixel tiles per warp) vs the row-major ray buffer, and the L2 window on/off
         cam = api.default_camera(scene.lower, scene.upper)
