@@ -51,6 +51,13 @@ def parse():
     ap.add_argument("--spp", type=int, default=16)
     ap.add_argument("--bounces", type=int, default=4)
     ap.add_argument("--random-rays", type=int, default=100_000_000)
+    ap.add_argument("--config", type=int, default=0, choices=[0, 4, 5],
+                    help="pathtrace presets: 4 = BASELINE configs[3] (16384^3 solids, 1080p, 4 bounces, 64 spp); "
+                         "5 = configs[4] (65536^3 city, 3840x2160, 256 spp, a sphere-brush edit + delta re-upload before every frame)")
+    ap.add_argument("--scene", default=None, choices=[None, "terrain", "soup", "city", "sphere_noise"])
+    ap.add_argument("--width", type=int, default=WIDTH)
+    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--edits", action="store_true", help="pathtrace: carve a radius-30 sphere and delta re-upload before every frame")
     return ap.parse_args()
 
 
@@ -190,8 +197,15 @@ def pathtrace_workload(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    kind, log2 = ("terrain", args.scene_log2)
+    if args.config == 4:
+        args.scene, args.scene_log2, args.spp, args.bounces = args.scene or "soup", 14, 64, 4
+    elif args.config == 5:
+        args.scene, args.scene_log2, args.spp, args.bounces, args.width, args.height, args.edits = args.scene or "city", 16, 256, 4, 3840, 2160, True
+    kind, log2 = (args.scene or "terrain", args.scene_log2)
+    W, H = args.width, args.height
+    t_build = time.time()
     scene = api.Scene(kind, log2, SCENE_SEED) if rank == 0 else None
+    t_build = time.time() - t_build
     if world > 1:
         nodes, root = sharding.broadcast_volume(dist, scene.nodes if rank == 0 else None, scene.root if rank == 0 else None, device=dev)
         meta = torch.zeros(6, dtype=torch.int64, device=dev)
@@ -208,16 +222,57 @@ def pathtrace_workload(args):
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
     ctx.upload(nodes, root, colours)
-    cam = api.default_camera(lower, upper)
+    if kind == "city":
+        cam = api.camera_from_pose([0.0, -2600.0, 1800.0], -0.6, 0.0)      # over the roofs, looking down the avenues
+    else:
+        cam = api.default_camera(lower, upper)
     stream = torch.cuda.current_stream().cuda_stream
-    accum = torch.zeros(HEIGHT, WIDTH, 3, dtype=torch.float32, device=dev)
+    accum = torch.zeros(H, W, 3, dtype=torch.float32, device=dev)
+    # Runtime edits (config 5): rank 0 owns the editable copy (csrc/edit.cpp restates the reference's checkpoint +
+    # sphere brush); every frame it carves a radius-30 sphere, ships the dirty tail to the other ranks, and every rank
+    # applies it with cbq_update -- the delta, not the DAG, crosses PCIe and NVLink.
+    editable = api.Editable(nodes, root) if (args.edits and rank == 0) else None
+    replica = np.array(nodes, dtype=np.uint32, copy=True) if (args.edits and rank != 0) else None
+    synced = len(nodes)
+    edit_stats = {"tail_bytes": [], "edit_ms": [], "sync_ms": []}
+
+    def edit(frame):
+        nonlocal replica, synced
+        if not args.edits:
+            return
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if rank == 0:
+            editable.checkpoint()
+            rng = np.random.default_rng(frame)
+            editable.fill_sphere(float(rng.uniform(-1200, 1200)), float(rng.uniform(-1200, 1200)), float(rng.uniform(0, 400)), 30.0, 0)
+            cur, cur_root, dirty = editable.nodes(), editable.root(), synced
+        t1 = time.perf_counter()
+        if world > 1:
+            if rank == 0:
+                fresh, new_root, dirty = sharding.broadcast_tail(dist, cur, dirty, cur_root, device=dev)
+            else:
+                fresh, new_root, dirty = sharding.broadcast_tail(dist, replica, 0, 0, device=dev)
+                replica = fresh
+        else:
+            fresh, new_root = cur, cur_root
+        ctx.update(fresh, dirty, new_root)
+        edit_stats["tail_bytes"].append((len(fresh) - dirty) * 32)
+        synced = editable.shared_end() if rank == 0 else len(fresh)
+        if world > 1:
+            t = torch.tensor([synced], dtype=torch.int64, device=dev)
+            dist.broadcast(t, src=0)
+            synced = int(t.item())
+        edit_stats["edit_ms"].append(1e3 * (t1 - t0))
+        edit_stats["sync_ms"].append(1e3 * (time.perf_counter() - t1))
     # this rank's share = every world-th 64-row band, rendered by ONE call (cbq_pt_params.band_count/index)
     bands = (world, rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step(frame):
+        edit(frame)
         accum.zero_()
-        p = api.pt_params(WIDTH, HEIGHT, spp=args.spp, bounces=args.bounces, variant=api.VARIANT_RECURSIVE,
+        p = api.pt_params(W, H, spp=args.spp, bounces=args.bounces, variant=api.VARIANT_RECURSIVE,
                           frame_id=frame * args.spp, bands=bands)
         ctx.render_device(cam, p, accum.data_ptr(), stream)
         if world > 1:
@@ -243,13 +298,13 @@ def pathtrace_workload(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms = total_ms / args.steps
-    value = WIDTH * HEIGHT * args.spp / (ms * 1e-3)
+    value = W * H * args.spp / (ms * 1e-3)
     # end to end: the host-image call (image up, render, image down) on this rank's bands
-    host = api.PinnedArray(HEIGHT * WIDTH * 3, np.float32)
-    img = host.array.reshape(HEIGHT, WIDTH, 3)
+    host = api.PinnedArray(H * W * 3, np.float32)
+    img = host.array.reshape(H, W, 3)
     img[:] = 0
     t0 = time.perf_counter()
-    ctx.render(cam, api.pt_params(WIDTH, HEIGHT, spp=args.spp, bounces=args.bounces, variant=api.VARIANT_RECURSIVE, bands=bands), img)
+    ctx.render(cam, api.pt_params(W, H, spp=args.spp, bounces=args.bounces, variant=api.VARIANT_RECURSIVE, bands=bands), img)
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -257,15 +312,16 @@ def pathtrace_workload(args):
         e2e_s = float(t.item())
     if rank == 0:
         mean = float(accum.mean().item()) / args.spp
-        line = {"metric": "1080p path-traced spp/s", "value": value, "unit": "spp/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": "%dp path-traced spp/s" % H, "value": value, "unit": "spp/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32+i32", "data": "synthetic",
-                "config": {"workload": "path tracing 1920x1080, %d spp, %d bounces (traceSingleRayRecurse), sun+sky+noise, maxFootprint 0.0035, procedural 4096^3 terrain SVDAG" % (args.spp, args.bounces),
+                "config": {"workload": "path tracing %dx%d, %d spp, %d bounces (traceSingleRayRecurse), sun+sky+noise, maxFootprint 0.0035, procedural %s 2^%d SVDAG%s" % (W, H, args.spp, args.bounces, kind, log2, ", radius-30 sphere edit + delta re-upload before every frame" if args.edits else ""),
+                           "dag_mb": round(len(nodes) * 32 / 1e6, 1), "scene_build_s": round(t_build, 2),
                            "nodes": int(len(nodes)), "l2": "flushed between steps", "options": args.option,
                            "parallelism": "replicated DAG, 64-row tile bands round-robin over %d GPU(s) (one render call per GPU), one NCCL reduce per frame" % world},
-                "e2e": {"value": WIDTH * HEIGHT * args.spp / e2e_s, "unit": "spp/s", "h2d_bytes_per_step": HEIGHT * WIDTH * 12,
-                        "d2h_bytes_per_step": HEIGHT * WIDTH * 12, "call": "cbq_render (host image in, this rank's bands rendered, host image out)"},
-                "gpu_launches": int(launches), "clocks": clocks.summary(), "extra": {"mean_radiance": mean}}
+                "e2e": {"value": W * H * args.spp / e2e_s, "unit": "spp/s", "h2d_bytes_per_step": H * W * 12,
+                        "d2h_bytes_per_step": H * W * 12, "call": "cbq_render (host image in, this rank's bands rendered, host image out)"},
+                "gpu_launches": int(launches), "clocks": clocks.summary(), "extra": {"mean_radiance": mean, "edits": {k: [round(float(x), 3) for x in v] for k, v in edit_stats.items()} if args.edits else None}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

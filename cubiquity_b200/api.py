@@ -64,6 +64,8 @@ EXPORTS = [
     "cbq_raycast_frame_device",
     "cbq_render", "cbq_render_device",
     "cbq_host_alloc", "cbq_host_free", "cbq_set_option", "cbq_get_option", "cbq_get_counter", "cbq_reset_counters",
+    "cbq_editable_create", "cbq_editable_destroy", "cbq_editable_checkpoint", "cbq_editable_undo", "cbq_editable_redo",
+    "cbq_editable_fill_sphere", "cbq_editable_nodes", "cbq_editable_root", "cbq_editable_shared_end", "cbq_editable_sync",
     "cbq_scene_build", "cbq_scene_nodes", "cbq_scene_root", "cbq_scene_bounds", "cbq_scene_colours",
     "cbq_scene_voxels", "cbq_scene_free",
 ]
@@ -112,6 +114,19 @@ def load_library():
     L.cbq_get_option.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
     L.cbq_get_counter.argtypes = [vp, C.c_char_p, C.POINTER(u64)]
     L.cbq_reset_counters.argtypes = [vp]
+    L.cbq_editable_create.argtypes = [vp, u64, u32, C.POINTER(vp)]
+    L.cbq_editable_destroy.restype = None
+    L.cbq_editable_destroy.argtypes = [vp]
+    for f in ("cbq_editable_checkpoint", "cbq_editable_undo", "cbq_editable_redo"):
+        getattr(L, f).argtypes = [vp]
+    L.cbq_editable_fill_sphere.argtypes = [vp, f32, f32, f32, f32, C.c_uint8]
+    L.cbq_editable_nodes.restype = C.POINTER(u32)
+    L.cbq_editable_nodes.argtypes = [vp, C.POINTER(u64)]
+    L.cbq_editable_root.restype = u32
+    L.cbq_editable_root.argtypes = [vp]
+    L.cbq_editable_shared_end.restype = u64
+    L.cbq_editable_shared_end.argtypes = [vp]
+    L.cbq_editable_sync.argtypes = [vp, vp, i32, vp]
     L.cbq_scene_build.argtypes = [C.c_char_p, u32, u64, C.POINTER(vp)]
     L.cbq_scene_nodes.restype = C.POINTER(u32)
     L.cbq_scene_nodes.argtypes = [vp, C.POINTER(u64)]
@@ -242,6 +257,58 @@ class Scene:
             self.close()
         except Exception:
             pass
+
+
+class Editable:
+    """Host-side copy-on-write edits of a node array (csrc/edit.cpp): the reference's checkpoint / sphere brush /
+    undo / redo, producing the same array the reference would, for the edit -> delta re-upload protocol."""
+
+    def __init__(self, nodes, root):
+        self.L = load_library()
+        nodes = np.ascontiguousarray(nodes, dtype=np.uint32).reshape(-1, 8)
+        h = C.c_void_p()
+        _check(self.L.cbq_editable_create(_ptr(nodes), len(nodes), int(root), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.cbq_editable_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def checkpoint(self):
+        _check(self.L.cbq_editable_checkpoint(self._h))
+
+    def undo(self):
+        _check(self.L.cbq_editable_undo(self._h))
+
+    def redo(self):
+        _check(self.L.cbq_editable_redo(self._h))
+
+    def fill_sphere(self, x, y, z, radius, material):
+        _check(self.L.cbq_editable_fill_sphere(self._h, float(x), float(y), float(z), float(radius), int(material)))
+
+    def nodes(self):
+        """A VIEW of the current array (valid until the next edit), shape (n, 8)."""
+        n = C.c_uint64()
+        p = self.L.cbq_editable_nodes(self._h, C.byref(n))
+        return np.ctypeslib.as_array(p, shape=(int(n.value), 8))
+
+    def root(self):
+        return int(self.L.cbq_editable_root(self._h))
+
+    def shared_end(self):
+        return int(self.L.cbq_editable_shared_end(self._h))
+
+    def sync(self, ctx, first_upload=False, colours=None):
+        if colours is not None:
+            colours = np.ascontiguousarray(colours, dtype=np.float32).reshape(256, 3)
+        _check(self.L.cbq_editable_sync(self._h, ctx._h, int(bool(first_upload)), _ptr(colours)))
 
 
 class Context:

@@ -204,6 +204,24 @@ int cbq_get_option(cbq_context* ctx, const char* key, int64_t* value);
 int cbq_get_counter(cbq_context* ctx, const char* key, uint64_t* value);
 int cbq_reset_counters(cbq_context* ctx);
 
+/* ---- host-side copy-on-write edits (the viewer's pick -> checkpoint -> brush -> re-sync loop) ---- */
+
+/* A growable copy of a node array with the reference's edit history. Restates Volume::checkpoint /
+ * undo / redo (storage.cpp:358-385), NodeStore::setNodeChild (storage.cpp:152-167) and fillBrush with a
+ * SphereBrush (voxelization.cpp:825-915) so that the resulting array is word for word the reference's. */
+typedef struct cbq_editable cbq_editable;
+int  cbq_editable_create(const uint32_t* nodes, uint64_t node_count, uint32_t root_index, cbq_editable** out);
+void cbq_editable_destroy(cbq_editable* e);
+int  cbq_editable_checkpoint(cbq_editable* e);
+int  cbq_editable_undo(cbq_editable* e);
+int  cbq_editable_redo(cbq_editable* e);
+int  cbq_editable_fill_sphere(cbq_editable* e, float x, float y, float z, float radius, uint8_t material);
+const uint32_t* cbq_editable_nodes(const cbq_editable* e, uint64_t* node_count);
+uint32_t cbq_editable_root(const cbq_editable* e);
+uint64_t cbq_editable_shared_end(const cbq_editable* e);
+/* first_upload != 0: cbq_upload; otherwise cbq_update with the tail that changed since the last sync. */
+int  cbq_editable_sync(cbq_editable* e, cbq_context* ctx, int first_upload, const float* colours_rgb);
+
 /* ---- procedural scenes (inputs for tests and benchmarks; host only) --------------------- */
 
 typedef struct cbq_scene cbq_scene;
