@@ -197,6 +197,7 @@ def pathtrace_workload(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    t_start = time.time()
     if args.config == 4:
         args.scene, args.scene_log2, args.spp, args.bounces = args.scene or "soup", 14, 64, 4
     elif args.config == 5:
@@ -217,6 +218,10 @@ def pathtrace_workload(args):
         lower, upper, colours = meta[:3].cpu().numpy(), meta[3:].cpu().numpy(), col.cpu().numpy()
     else:
         nodes, root, lower, upper, colours = scene.nodes, scene.root, scene.lower, scene.upper, scene.colours
+    def log(msg):
+        if rank == 0:
+            sys.stderr.write("[bench pathtrace %.1fs] %s\n" % (time.time() - t_start, msg)); sys.stderr.flush()
+    log("scene %s 2^%d: %d nodes, built in %.1f s" % (kind, log2, len(nodes), t_build))
     ctx = api.Context(local)
     for kv in args.option:
         k, v = kv.split("=")
@@ -278,9 +283,11 @@ def pathtrace_workload(args):
         if world > 1:
             sharding.reduce_image(dist, accum, dst=0)
 
+    log("uploaded; warming up")
     for i in range(max(args.warmup, 3)):
         step(i)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        log("warm-up frame %d done" % i)
     if world > 1:
         dist.barrier()
     ctx.reset_counters()
@@ -293,6 +300,7 @@ def pathtrace_workload(args):
         torch.cuda.synchronize()
     launches = ctx.counter("kernel_launches")
     total_ms = float(np.sum([a.elapsed_time(b) for a, b in zip(starts, stops)]))
+    log("timed region done: %.1f ms per frame, %d abandoned rays" % (total_ms / args.steps, ctx.counter("abandoned_rays")))
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
