@@ -62,7 +62,7 @@ EXPORTS = [
     "cbq_download_nodes", "cbq_node_count",
     "cbq_trace", "cbq_trace_device", "cbq_camera_from_pose", "cbq_primary_rays_device", "cbq_primary_rays_tiled_device", "cbq_random_rays_device",
     "cbq_raycast_frame_device",
-    "cbq_render", "cbq_render_device",
+    "cbq_render", "cbq_render_device", "cbq_rng_points_device",
     "cbq_host_alloc", "cbq_host_free", "cbq_set_option", "cbq_get_option", "cbq_get_counter", "cbq_reset_counters",
     "cbq_editable_create", "cbq_editable_destroy", "cbq_editable_checkpoint", "cbq_editable_undo", "cbq_editable_redo",
     "cbq_editable_fill_sphere", "cbq_editable_nodes", "cbq_editable_root", "cbq_editable_shared_end", "cbq_editable_sync",
@@ -108,6 +108,7 @@ def load_library():
     L.cbq_raycast_frame_device.argtypes = [vp, C.POINTER(Camera), u32, u32, u32, f32, vp, vp]
     L.cbq_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(PtParams), vp]
     L.cbq_render_device.argtypes = [vp, C.POINTER(Camera), C.POINTER(PtParams), vp, vp]
+    L.cbq_rng_points_device.argtypes = [vp, vp, u64, i32, vp, vp, vp]
     L.cbq_host_alloc.argtypes = [C.POINTER(vp), u64]
     L.cbq_host_free.argtypes = [vp]
     L.cbq_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
@@ -413,6 +414,10 @@ class Context:
     def render_device(self, cam, params, d_accum, stream=None):
         _check(self.L.cbq_render_device(self._h, C.byref(cam), C.byref(params), C.c_void_p(int(d_accum)),
                                         _stream(stream)))
+
+    def rng_points_device(self, d_seeds, n, draws, d_points, d_states, stream=None):
+        _check(self.L.cbq_rng_points_device(self._h, C.c_void_p(int(d_seeds)), int(n), int(draws), C.c_void_p(int(d_points)),
+                                            C.c_void_p(int(d_states)), _stream(stream)))
 
     # -- misc --------------------------------------------------------------------------------
     def synchronize(self):

@@ -631,6 +631,17 @@ int cbq_render(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_params* p, 
 	return CBQ_OK;
 }
 
+int cbq_rng_points_device(cbq_context* ctx, const uint32_t* d_seeds, uint64_t n, int draws, float* d_points, uint32_t* d_states, void* stream)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if ((n && (!d_seeds || !d_points || !d_states)) || draws < 0) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad argument");
+	if (n == 0 || draws == 0) return CBQ_OK;
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	CBQ_CUDA(cbq::launchRngPoints(d_seeds, n, draws, d_points, d_states, s));
+	ctx->launches++;
+	return CBQ_OK;
+}
+
 int cbq_host_alloc(void** out, uint64_t bytes)
 {
 	if (!out) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");

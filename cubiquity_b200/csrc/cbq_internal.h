@@ -108,6 +108,7 @@ struct WavefrontBuffers {
 	float* radiance = nullptr;     // finished radiance of each path, SoA [3][pixels]
 	unsigned long long* counters = nullptr;     // live paths per depth             [8]
 };
+cudaError_t launchRngPoints(const uint32_t* seeds, uint64_t n, int draws, float* points, uint32_t* states, cudaStream_t stream);
 int wavefrontReserve(WavefrontBuffers& b, size_t paths);       // cudaError_t as int
 void wavefrontRelease(WavefrontBuffers& b);
 // nextQueue hands out zeroed ticket counters for the trace launches.

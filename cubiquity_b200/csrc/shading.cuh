@@ -61,14 +61,19 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
 	return ((0.0f + ax * bx) + ay * by) + az * bz;   // linalg sum(a*b): fold from 0, left to right
 }
 
-// randomPointInUnitSphere, pathtracing_demo.cpp:62-79
+// randomPointInUnitSphere, pathtracing_demo.cpp:62-79. The try cap is quirk Q8: the 32-bit
+// truncation of the 64-bit mixer is not a bijection, a stream can fall into a cycle of rejected points
+// (about one seed in 4e8) and the reference's loop would then spin for ever; after kMaxBallTries
+// rejected candidates the last one is returned as it is. Same rule as the CPU checker.
+constexpr int kMaxBallTries = 64;
 __device__ __forceinline__ void unitBallPoint(uint32_t& rng, float& x, float& y, float& z)
 {
+	int tries = 0;
 	do {
 		rng = (uint32_t)bitMix64((uint64_t)rng);
 		x = (float)(rng & 0x3FFu); y = (float)((rng >> 10) & 0x3FFu); z = (float)((rng >> 20) & 0x3FFu);
 		x = (x - 511.5f) / 511.5f; y = (y - 511.5f) / 511.5f; z = (z - 511.5f) / 511.5f;
-	} while (dot3(x, y, z, x, y, z) >= 1.0f);
+	} while (dot3(x, y, z, x, y, z) >= 1.0f && ++tries < kMaxBallTries);
 }
 
 // surfaceColour + positionBasedNoise, pathtracing_demo.cpp:36-60

@@ -208,6 +208,22 @@ lightKernel(WaveParams w, const unsigned long long* __restrict__ liveCount, cons
 	}
 }
 
+// Self-test hook (cbq_rng_points_device): the path tracer's RNG for caller-chosen seeds.
+__global__ void __launch_bounds__(256)
+rngPointsKernel(const uint32_t* __restrict__ seeds, uint64_t n, int draws, float* __restrict__ points, uint32_t* __restrict__ states)
+{
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint32_t rng = seeds[i];
+		for (int d = 0; d < draws; d++) {
+			float x, y, z;
+			unitBallPoint(rng, x, y, z);
+			float* p = points + 3 * (i * (uint64_t)draws + d);
+			p[0] = x; p[1] = y; p[2] = z;
+		}
+		states[i] = rng;
+	}
+}
+
 template <typename T>
 cudaError_t grow(T*& p, size_t count)
 {
@@ -217,6 +233,15 @@ cudaError_t grow(T*& p, size_t count)
 }
 
 } // namespace
+
+cudaError_t launchRngPoints(const uint32_t* seeds, uint64_t n, int draws, float* points, uint32_t* states, cudaStream_t stream)
+{
+	uint64_t blocks = (n + 255) / 256;
+	if (blocks > 148u * 8u) blocks = 148u * 8u;
+	if (blocks == 0) blocks = 1;
+	rngPointsKernel<<<(int)blocks, 256, 0, stream>>>(seeds, n, draws, points, states);
+	return cudaGetLastError();
+}
 
 int wavefrontReserve(WavefrontBuffers& b, size_t pixels /* paths */)
 {

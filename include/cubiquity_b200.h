@@ -188,6 +188,11 @@ int cbq_render(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_params* p, 
 int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_params* p, float* d_accum,
                       void* stream);
 
+/* Self-test hook: `draws` successive randomPointInUnitSphere results (pathtracing_demo.cpp:62-79) of the
+ * stream that starts at each seed: d_points is n x draws x 3 floats, d_states the n final states. */
+int cbq_rng_points_device(cbq_context* ctx, const uint32_t* d_seeds, uint64_t n, int draws, float* d_points,
+                          uint32_t* d_states, void* stream);
+
 /* ---- pinned host memory, tuning, counters ---------------------------------------------- */
 
 int cbq_host_alloc(void** out, uint64_t bytes);

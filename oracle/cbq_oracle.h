@@ -91,6 +91,7 @@ void cbqo_camera_from_pose(const double position[3], double pitch, double yaw, d
 void cbqo_camera_ray(const cbqo_camera* cam, int x, int y, int width, int height, cbqo_ray* out);
 void cbqo_camera_rays(const cbqo_camera* cam, int width, int height, cbqo_ray* out);
 
+void cbqo_unit_ball_points(uint32_t* state, int draws, float* out /* draws x 3 */);
 uint32_t cbqo_pixel_seed(const cbqo_ray* primary, uint32_t sample_index);
 
 /* accum: width*height*3 floats, row-major, ADDED to (like mImage += pixel, pathtracing_demo.cpp:224).

@@ -93,8 +93,15 @@ class Port:
         L.cbqo_fnv1a.argtypes = [C.c_char_p, C.c_int64]
         L.cbqo_fmix32.restype = C.c_uint32
         L.cbqo_fmix32.argtypes = [C.c_uint32]
+        L.cbqo_unit_ball_points.argtypes = [C.POINTER(C.c_uint32), C.c_int, C.c_void_p]
         L.cbqo_pixel_seed.restype = C.c_uint32
         L.cbqo_pixel_seed.argtypes = [C.c_void_p, C.c_uint32]
+
+    def unit_ball_points(self, seed, draws):
+        state = C.c_uint32(int(seed))
+        out = np.zeros((draws, 3), dtype=np.float32)
+        self.lib.cbqo_unit_ball_points(C.byref(state), int(draws), _ptr(out))
+        return out, int(state.value)
 
     def find_subdags(self, nodes, root):
         nodes = np.ascontiguousarray(nodes, dtype=np.uint32)
