@@ -66,7 +66,7 @@ def render_sweep(ctx, scene, dev, stream):
 
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "primary"
-    scene = api.Scene("terrain", 12, 1)
+    scene = api.Scene(os.environ.get("CBQ_SWEEP_SCENE", "terrain"), int(os.environ.get("CBQ_SWEEP_LOG2", "12")), 1)
     ctx = api.Context(0)
     ctx.upload(scene.nodes, scene.root, scene.colours)
     dev = torch.device("cuda", 0)

@@ -59,3 +59,40 @@ def test_single_ray_call_matches_oracle(exe, port):
     assert int(got[0]) == int(want["hit"][0]) == 1
     assert np.float32(float(got[1])) == want["distance"][0] and int(got[2]) == int(want["material"][0])
     assert [np.float32(float(v)) for v in got[3:6]] == list(want["position"][0])
+
+
+@pytest.fixture(scope="module")
+def render_exe(api):
+    out = os.path.join(ROOT, "tests", "_build", "render_dag")
+    libdir = os.path.dirname(api.library_path())
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", os.path.join(ROOT, "examples", "render_dag.cpp"), "-I" + os.path.join(ROOT, "include"),
+                    "-o", out, "-L" + libdir, "-lcubiquity_b200", "-Wl,-rpath," + libdir], check=True)
+    return out
+
+
+def test_example_program_builds_and_fails_loudly_without_a_gpu(render_exe, api, tmp_path):
+    if api.device_count() > 0:
+        pytest.skip("a GPU is present")
+    p = subprocess.run([render_exe, GOLD, str(tmp_path / "o.ppm")], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 1 and "fallback" in p.stderr
+
+
+@pytest.mark.gpu
+def test_example_program_renders_what_the_library_renders(render_exe, gpu, api, ref, tmp_path):
+    """The C++ example (file in, PPM out) against the same frame rendered through the Python binding, with the
+    camera placed from the REFERENCE's bounds (cubiquity_estimate_bounds) -- byte-identical images."""
+    from cubiquity_b200 import dagfile
+    out = tmp_path / "o.ppm"
+    p = subprocess.run([render_exe, GOLD, str(out), "96", "64", "3", "2"], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    data = out.read_bytes()
+    header = b"P6\n96 64\n255\n"
+    assert data.startswith(header)
+    got = np.frombuffer(data[len(header):], dtype=np.uint8).reshape(64, 96, 3)
+    nodes, root = dagfile.read_dag(GOLD)
+    _, lo, hi = ref.volume().load(GOLD).bounds()
+    gpu.upload(nodes, root)                                     # purple default colours, like the example
+    img = gpu.render(api.default_camera(lo, hi), api.pt_params(96, 64, spp=3, bounces=2, variant=api.VARIANT_RECURSIVE))
+    want = np.clip(img * np.float32(255.0 / 3.0), 0, 255).astype(np.uint8)
+    assert np.array_equal(got, want)
+    assert got.std() > 10
