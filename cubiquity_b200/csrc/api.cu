@@ -287,6 +287,7 @@ int cbq_create(int device, cbq_context** out)
 	ctx->cfg.blocksPerSm = 4;
 	ctx->cfg.smCount = ctx->prop.multiProcessorCount;
 	ctx->cfg.refillThreshold = 8;    // robust default: +68 % on incoherent rays, -7 % on coherent ones (profiles/r01_sweeps.md)
+	ctx->cfg.refillQuantum = 1;
 	ctx->cfg.kernel = 0;
 	ctx->cfg.stackLevels = 33;
 	ctx->cfg.sampleGroup = 0;    // auto; 1080p, 4 bounces: 512 / 734 / 789 / 812 M spp/s for groups of 1 / 4 / 8 / 16 (profiles/r01_analysis.md)
@@ -669,6 +670,9 @@ int cbq_set_option(cbq_context* ctx, const char* key, int64_t value)
 	} else if (k == "refill_threshold") {
 		if (value < 1 || value > 32) return fail(CBQ_ERROR_INVALID_ARGUMENT, "refill_threshold must be in [1, 32]");
 		ctx->cfg.refillThreshold = (int)value;
+	} else if (k == "refill_quantum") {
+		if (value < 1 || value > 32 || (value & (value - 1)) != 0) return fail(CBQ_ERROR_INVALID_ARGUMENT, "refill_quantum must be a power of two in [1, 32]");
+		ctx->cfg.refillQuantum = (int)value;
 	} else if (k == "kernel") {
 		if (value < 0 || value > 1) return fail(CBQ_ERROR_INVALID_ARGUMENT, "kernel must be 0 or 1");
 		ctx->cfg.kernel = (int)value;
@@ -695,6 +699,7 @@ int cbq_get_option(cbq_context* ctx, const char* key, int64_t* value)
 	else if (k == "blocks_per_sm") *value = ctx->cfg.blocksPerSm;
 	else if (k == "refill_threshold") *value = ctx->cfg.refillThreshold;
 	else if (k == "kernel") *value = ctx->cfg.kernel;
+	else if (k == "refill_quantum") *value = ctx->cfg.refillQuantum;
 	else if (k == "l2_persist") *value = ctx->l2Persist;
 	else if (k == "render_mode") *value = ctx->renderMode;
 	else if (k == "sample_group") *value = ctx->cfg.sampleGroup;

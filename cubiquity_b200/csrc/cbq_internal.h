@@ -51,6 +51,7 @@ struct LaunchConfig {
 	int blocksPerSm;       // resident CTAs per SM the grid is sized for
 	int smCount;
 	int refillThreshold;   // idle lanes in a warp that trigger a refill from the ray queue (1..32)
+	int refillQuantum;     // tickets are dealt in whole groups of this many (1, 2, 4, 8, 16 or 32)
 	int kernel;            // 0 persistent queue kernel, 1 one-thread-per-ray
 	int stackLevels;       // entries per lane in the shared-memory stack (max sub-DAG height + 1)
 	int sampleGroup;       // wavefront path tracer: samples of a pixel traced together (1..16)

@@ -172,7 +172,7 @@ template <bool kSurface, bool kLodOff, bool kDeviceCount, typename Source, typen
 __global__ void __launch_bounds__(256, CBQ_TRACE_MIN_BLOCKS)
 tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict__ subdagsGlobal, Source source,
 	Sink sink, const uint64_t hostCount, const unsigned long long* __restrict__ countPtr, uint32_t countScale,
-	float maxFootprint, int refillThreshold,
+	float maxFootprint, int refillThreshold, int refillQuantum,
 	unsigned long long* __restrict__ queue, unsigned long long* __restrict__ abandoned)
 {
 	// The batch size may live on the device (wavefront path tracer: the number of surviving paths is
@@ -199,7 +199,10 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 	for (;;) {
 		const unsigned idle = __ballot_sync(kFullMask, s.phase == kPhaseIdle);
 		if (idle != 0u && !drained && (__popc(idle) >= refillThreshold || idle == kFullMask)) {
-			int want = __popc(idle);
+			// Only whole groups of `refillQuantum` tickets are dealt (a power of two <= 32): with tile-ordered
+			// rays a quantum of 16 keeps every refill an aligned 8x2-pixel half tile, so the warp's ticket
+			// window never drifts off the tile grid.
+			int want = __popc(idle) & ~(refillQuantum - 1);
 			int myRank = __popc(idle & lowerLanes);
 			// Deal from the current chunk, claiming a new one when it runs dry.
 			while (want > 0) {
@@ -373,7 +376,7 @@ cudaError_t launchKernel(Kernel kernel, const TraceArgs& a, const Source& src, c
 	const uint64_t needed = (tickets + (uint64_t)cfg.blockThreads - 1) / (uint64_t)cfg.blockThreads;
 	if (!a.countPtr && (uint64_t)grid > needed) grid = (int)(needed ? needed : 1);
 	kernel<<<grid, cfg.blockThreads, smem, stream>>>(a.nodes, a.subdags, src, sink, tickets, a.countPtr, a.countScale, a.maxFootprint,
-		cfg.refillThreshold, a.queue, a.abandoned);
+		cfg.refillThreshold, cfg.refillQuantum > 0 ? cfg.refillQuantum : 1, a.queue, a.abandoned);
 	return cudaGetLastError();
 }
 

@@ -81,11 +81,12 @@ def main():
         ctx.primary_rays_tiled_device(cam, W, H, d_tiled.data_ptr(), None, stream)
         d_hits = torch.zeros(n * 10, dtype=torch.int32, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        for thr in (32, 28, 24, 16, 8, 32):
+        for thr, q in ((32, 1), (16, 16), (24, 16), (16, 8), (8, 8), (24, 8), (32, 32)):
             ctx.set_option("refill_threshold", thr)
+            ctx.set_option("refill_quantum", q)
             for mf in (-1.0, 0.0035):
                 cold, warm = time_config(ctx, d_tiled, n, d_hits, flush, stream, mf=mf)
-                print(json.dumps({"workload": "tiled_refill", "refill_threshold": thr, "max_footprint": mf, "cold_ms": round(cold, 4), "cold_grays": round(n / cold / 1e6, 3)}), flush=True)
+                print(json.dumps({"workload": "tiled_refill", "refill_threshold": thr, "refill_quantum": q, "max_footprint": mf, "cold_ms": round(cold, 4), "cold_grays": round(n / cold / 1e6, 3)}), flush=True)
         return
     if what == "frame":
         # fused camera path (8x4-pixel tiles per warp) vs the row-major ray buffer, and the L2 window on/off
