@@ -465,6 +465,8 @@ def main():
     pt = None
     if args.workload == "primary":
         d_accum = torch.zeros(HEIGHT * WIDTH * 3, dtype=torch.float32, device=dev)
+        saved_threshold = ctx.get_option("refill_threshold")
+        ctx.set_option("refill_threshold", 8)      # the library default: secondary rays are incoherent
         p = api.pt_params(WIDTH, HEIGHT, spp=args.spp, bounces=args.bounces, variant=api.VARIANT_RECURSIVE, frame_id=0)
         ctx.render_device(cam, p, d_accum.data_ptr(), stream)     # warm-up with the same shape (buffers get sized here)
         torch.cuda.synchronize()
@@ -479,6 +481,7 @@ def main():
             torch.cuda.synchronize()
             pt_times.append(a.elapsed_time(b2))
         pt_ms = float(np.median(pt_times))
+        ctx.set_option("refill_threshold", saved_threshold)
         if world > 1:
             t = torch.tensor([pt_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
