@@ -58,7 +58,7 @@ def pt_params(width, height, spp=1, bounces=1, variant=VARIANT_ONE_BOUNCE, inclu
 
 EXPORTS = [
     "cbq_create", "cbq_destroy", "cbq_last_error", "cbq_device_count", "cbq_synchronize",
-    "cbq_upload", "cbq_update", "cbq_set_colours", "cbq_get_subdags", "cbq_find_subdags",
+    "cbq_upload", "cbq_update", "cbq_bake", "cbq_set_colours", "cbq_get_subdags", "cbq_find_subdags",
     "cbq_download_nodes", "cbq_node_count",
     "cbq_trace", "cbq_trace_device", "cbq_camera_from_pose", "cbq_primary_rays_device", "cbq_primary_rays_tiled_device", "cbq_random_rays_device",
     "cbq_raycast_frame_device",
@@ -94,6 +94,7 @@ def load_library():
     L.cbq_synchronize.argtypes = [vp]
     L.cbq_upload.argtypes = [vp, vp, u64, u32, vp]
     L.cbq_update.argtypes = [vp, vp, u64, u64, u32]
+    L.cbq_bake.argtypes = [vp, C.POINTER(u64), C.POINTER(u32)]
     L.cbq_set_colours.argtypes = [vp, vp]
     L.cbq_get_subdags.argtypes = [vp, vp]
     L.cbq_find_subdags.argtypes = [vp, u64, u32, vp]
@@ -349,6 +350,14 @@ class Context:
     def update(self, nodes, dirty_begin, root):
         nodes = np.ascontiguousarray(nodes, dtype=np.uint32).reshape(-1, 8)
         _check(self.L.cbq_update(self._h, _ptr(nodes), int(dirty_begin), len(nodes), int(root)))
+
+    def bake(self):
+        """Volume::bake (reference storage.cpp:388-395) on the device copy; returns (node_count, root) of the merged
+        array (download_nodes() reads it back). Same canonical DAG as the reference's merge, different node order."""
+        n = C.c_uint64()
+        root = C.c_uint32()
+        _check(self.L.cbq_bake(self._h, C.byref(n), C.byref(root)))
+        return int(n.value), int(root.value)
 
     def subdags(self):
         out = np.zeros(8, dtype=SUBDAG_DTYPE)

@@ -103,6 +103,10 @@ struct cbq_context {
 	cudaStream_t copyIn = nullptr, copyOut = nullptr;
 	cudaEvent_t evIn[kStages]{}, evKernel[kStages]{}, evOut[kStages]{};
 
+	// Volume buffers and bake work space come from a private stream-ordered pool that keeps what is freed
+	// (release threshold = max): a re-upload or a bake of a multi-GB DAG does not pay cudaMalloc/cudaFree each time.
+	cudaMemPool_t pool = nullptr;
+
 	// The volume: one linear device buffer.
 	uint8_t* volume = nullptr;
 	size_t volumeBytes = 0;
@@ -136,6 +140,7 @@ struct cbq_context {
 
 	// Counters
 	uint64_t launches = 0, raysTraced = 0, bytesH2D = 0, bytesD2H = 0;
+	uint64_t bakeReachable = 0;   // nodes the root reached in the last cbq_bake, before merging
 
 	const uint32_t* nodesPtr() const { return reinterpret_cast<const uint32_t*>(volume + cbq::kNodeOffset); }
 	const cbq::SubDag* subdagsPtr() const { return reinterpret_cast<const cbq::SubDag*>(volume + cbq::kSubDagOffset); }
@@ -150,6 +155,16 @@ int bind(cbq_context* ctx)
 	if (!ctx) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null context");
 	CBQ_CUDA(cudaSetDevice(ctx->device));
 	return CBQ_OK;
+}
+
+cudaError_t poolAlloc(cbq_context* ctx, uint8_t** out, size_t bytes)
+{
+	return cudaMallocFromPoolAsync(reinterpret_cast<void**>(out), bytes, ctx->pool, ctx->stream);
+}
+
+void poolFree(cbq_context* ctx, void* p)
+{
+	if (p) cudaFreeAsync(p, ctx->stream);
 }
 
 // Hand out a zeroed ticket counter. The ring is re-zeroed (stream ordered) each time it wraps.
@@ -281,6 +296,17 @@ int cbq_create(int device, cbq_context** out)
 		CBQ_CUDA(cudaEventCreateWithFlags(&ctx->evKernel[i], cudaEventDisableTiming));
 		CBQ_CUDA(cudaEventCreateWithFlags(&ctx->evOut[i], cudaEventDisableTiming));
 	}
+	{
+		cudaMemPoolProps props;
+		std::memset(&props, 0, sizeof(props));
+		props.allocType = cudaMemAllocationTypePinned;
+		props.handleTypes = cudaMemHandleTypeNone;
+		props.location.type = cudaMemLocationTypeDevice;
+		props.location.id = device;
+		CBQ_CUDA(cudaMemPoolCreate(&ctx->pool, &props));
+		uint64_t keep = ~0ull;
+		CBQ_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+	}
 	CBQ_CUDA(cudaMalloc(&ctx->queues, sizeof(unsigned long long) * (kQueueSlots + 1)));
 	CBQ_CUDA(cudaMemset(ctx->queues, 0, sizeof(unsigned long long) * (kQueueSlots + 1)));
 	ctx->cfg.blockThreads = 256;
@@ -310,7 +336,9 @@ void cbq_destroy(cbq_context* ctx)
 	cudaFree(ctx->frameRays);
 	cbq::wavefrontRelease(ctx->wavefront);
 	cudaFree(ctx->queues);
-	cudaFree(ctx->volume);
+	poolFree(ctx, ctx->volume);
+	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+	if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
 	if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
@@ -347,8 +375,8 @@ int cbq_upload(cbq_context* ctx, const uint32_t* nodes, uint64_t node_count, uin
 	const size_t bytes = cbq::kNodeOffset + (size_t)capacity * 32;
 	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
 	if (bytes > ctx->volumeBytes) {
-		if (ctx->volume) { CBQ_CUDA(cudaDeviceSynchronize()); CBQ_CUDA(cudaFree(ctx->volume)); ctx->volume = nullptr; ctx->volumeBytes = 0; }
-		CBQ_CUDA(cudaMalloc(&ctx->volume, bytes));
+		if (ctx->volume) { CBQ_CUDA(cudaDeviceSynchronize()); poolFree(ctx, ctx->volume); ctx->volume = nullptr; ctx->volumeBytes = 0; }
+		CBQ_CUDA(poolAlloc(ctx, &ctx->volume, bytes));
 		ctx->volumeBytes = bytes;
 	}
 	ctx->nodeCapacity = (ctx->volumeBytes - cbq::kNodeOffset) / 32;
@@ -378,9 +406,9 @@ int cbq_update(cbq_context* ctx, const uint32_t* nodes, uint64_t dirty_begin, ui
 		const size_t bytes = cbq::kNodeOffset + (size_t)capacity * 32;
 		uint8_t* bigger = nullptr;
 		CBQ_CUDA(cudaDeviceSynchronize());
-		CBQ_CUDA(cudaMalloc(&bigger, bytes));
-		CBQ_CUDA(cudaMemcpy(bigger, ctx->volume, cbq::kNodeOffset + (size_t)dirty_begin * 32, cudaMemcpyDeviceToDevice));
-		CBQ_CUDA(cudaFree(ctx->volume));
+		CBQ_CUDA(poolAlloc(ctx, &bigger, bytes));
+		CBQ_CUDA(cudaMemcpyAsync(bigger, ctx->volume, cbq::kNodeOffset + (size_t)dirty_begin * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+		poolFree(ctx, ctx->volume);
 		ctx->volume = bigger; ctx->volumeBytes = bytes; ctx->nodeCapacity = capacity;
 	}
 	const uint64_t tail = node_count - dirty_begin;
@@ -392,6 +420,62 @@ int cbq_update(cbq_context* ctx, const uint32_t* nodes, uint64_t dirty_begin, ui
 	ctx->nodeCount = node_count;
 	ctx->root = root_index;
 	ctx->generation++;
+	return writeHeaderAndSubdags(ctx);
+}
+
+int cbq_bake(cbq_context* ctx, uint64_t* node_count, uint32_t* root_index)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "cbq_bake before cbq_upload");
+	const uint64_t n = ctx->nodeCount;
+	uint64_t slots = 0;
+	const size_t scratchBytes = cbq::bakeScratchBytes(n, &slots);
+	const size_t tailBytes = 4 * sizeof(unsigned long long) + 8 * sizeof(cbq::SubDag) + 64;   // results, sub-DAGs, status
+	const size_t newBytes = cbq::kNodeOffset + (size_t)n * 32;     // the merged array is never longer than the input
+	uint8_t* scratch = nullptr;
+	uint8_t* baked = nullptr;
+	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	CBQ_CUDA(poolAlloc(ctx, &scratch, scratchBytes + tailBytes));
+	if (poolAlloc(ctx, &baked, newBytes) != cudaSuccess) { cudaGetLastError(); poolFree(ctx, scratch); return fail(CBQ_ERROR_OUT_OF_MEMORY, "cbq_bake: no room for a second copy of the volume (%zu bytes)", newBytes); }
+	unsigned long long* dResults = reinterpret_cast<unsigned long long*>(scratch + scratchBytes);
+	cbq::SubDag* dSubdags = reinterpret_cast<cbq::SubDag*>(dResults + 4);
+	uint32_t* dStatus = reinterpret_cast<uint32_t*>(dSubdags + 8);
+	uint32_t* outNodes = reinterpret_cast<uint32_t*>(baked + cbq::kNodeOffset);
+
+	struct { unsigned long long results[4]; cbq::SubDag subdags[8]; uint32_t status; } host;
+	cudaError_t e = cudaMemsetAsync(dStatus, 0, 64, ctx->stream);
+	if (e == cudaSuccess) e = cbq::launchBake(ctx->nodesPtr(), n, ctx->root, scratch, slots, outNodes, dResults, ctx->cfg.smCount, ctx->stream, &ctx->launches);
+	if (e == cudaSuccess) e = cbq::launchSubdags(outNodes, (uint32_t)n, 0, dResults + 2, dSubdags, dStatus, ctx->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(baked + cbq::kColourOffset, ctx->volume + cbq::kColourOffset, cbq::kNodeOffset - cbq::kColourOffset, cudaMemcpyDeviceToDevice, ctx->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(&host, dResults, sizeof(host.results) + sizeof(host.subdags) + sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	poolFree(ctx, scratch);
+	if (e != cudaSuccess) { poolFree(ctx, baked); return fail(CBQ_ERROR_CUDA, "cbq_bake failed: %s", cudaGetErrorString(e)); }
+	ctx->launches += 1;
+	ctx->bytesD2H += sizeof(host);
+	if (host.results[0] != 0) {
+		poolFree(ctx, baked);
+		return fail(CBQ_ERROR_CORRUPT_VOLUME, "cbq_bake: %llu reachable nodes never resolved (a cycle, or a DAG deeper than 32 levels); the volume is unchanged",
+			host.results[0]);
+	}
+	if (host.status != 0) { poolFree(ctx, baked); return fail(CBQ_ERROR_CORRUPT_VOLUME, "cbq_bake: the merged array has no valid sub-DAGs; the volume is unchanged"); }
+
+	CBQ_CUDA(cudaDeviceSynchronize());           // nobody may still be reading the old copy
+	poolFree(ctx, ctx->volume);
+	ctx->volume = baked;
+	ctx->volumeBytes = newBytes;
+	ctx->nodeCapacity = n;
+	ctx->nodeCount = cbq::kMaterialCount + host.results[1];
+	ctx->root = (uint32_t)host.results[2];
+	ctx->generation++;
+	ctx->bakeReachable = host.results[3];
+	std::memcpy(ctx->subdags, host.subdags, sizeof(host.subdags));
+	int maxH = 0;
+	for (int i = 0; i < 8; i++) if (ctx->subdags[i].node > 0) maxH = std::max(maxH, ctx->subdags[i].height);
+	ctx->maxSubDagHeight = maxH;
+	ctx->cfg.stackLevels = maxH + 1;
+	if (node_count) *node_count = ctx->nodeCount;
+	if (root_index) *root_index = ctx->root;
 	return writeHeaderAndSubdags(ctx);
 }
 
@@ -720,6 +804,7 @@ int cbq_get_counter(cbq_context* ctx, const char* key, uint64_t* value)
 	else if (k == "rays_traced") *value = ctx->raysTraced;
 	else if (k == "bytes_h2d") *value = ctx->bytesH2D;
 	else if (k == "bytes_d2h") *value = ctx->bytesD2H;
+	else if (k == "bake_reachable") *value = ctx->bakeReachable;
 	else if (k == "abandoned_rays") {
 		unsigned long long v = 0;
 		CBQ_CUDA(cudaDeviceSynchronize());

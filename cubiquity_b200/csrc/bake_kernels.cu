@@ -1,0 +1,428 @@
+// Device-side `bake`: hash-cons merge of a node array that is already resident in HBM.
+//
+// What the reference does on one CPU thread (Volume::bake -> NodeStore::merge / merge_node, reference
+// src/library/storage.cpp:208-290, 388-395): walk the DAG depth first from the root; replace every child by its
+// merged index; a node whose eight (merged) children are the same material BECOMES that material
+// (isMaterialNode(const Node&), storage.cpp:69-75); otherwise look the node up by CONTENT in an open-addressing
+// table and append it if absent; finally compact the table and rewrite the child indices. The result is the
+// canonical minimal DAG of everything reachable from the root; which slot a node lands in is an artefact of the
+// reference's hash function and visiting order and is NOT part of the format (children are absolute indices).
+//
+// Here the same canonical DAG is produced level-synchronously, bottom-up by rank (a node can be finished once
+// all its children are), one thread per node:
+//   1. reachKernel, <= 33 passes: mark what the root reaches (the DAG is at most 32 levels deep).
+//   2. resolveKernel + insertKernel, <= 33 passes: a node whose children all have final ids writes its canonical
+//      content (children replaced by ids) and is hash-consed into a table of OWNER indices with one atomicCAS;
+//      keys are compared exactly against the owner's canonical content (no reliance on hash uniqueness).
+//      The id of a distinct node is the owner's ORIGINAL index; duplicates record the smallest original index of
+//      their class with atomicMin, which makes the final order independent of who won the CAS races.
+//   3. flag the representative (smallest original index) of every class, exclusive scan, emit: distinct nodes
+//      keep the relative order their first occurrence had in the input, so the output is deterministic and
+//      baking a baked array is the identity.
+// All of it is integer gather/scatter work bound by HBM sectors (DESIGN.md section 4.7 has the bytes per node).
+#include "cbq_internal.h"
+
+namespace cbq {
+
+namespace {
+
+constexpr uint32_t kUnresolved = 0xffffffffu;
+constexpr uint32_t kPending = 0xfffffffeu;
+constexpr uint32_t kEmptySlot = 0xffffffffu;
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;                        // per thread
+constexpr uint32_t kScanTile = kScanThreads * kScanItems;
+
+struct NodeWords {
+	uint32_t w[8];
+};
+
+__device__ __forceinline__ NodeWords loadNode(const uint32_t* nodes, uint32_t i)
+{
+	const uint4* p = reinterpret_cast<const uint4*>(nodes) + (size_t)i * 2;
+	const uint4 a = p[0], b = p[1];
+	NodeWords n;
+	n.w[0] = a.x; n.w[1] = a.y; n.w[2] = a.z; n.w[3] = a.w;
+	n.w[4] = b.x; n.w[5] = b.y; n.w[6] = b.z; n.w[7] = b.w;
+	return n;
+}
+
+__device__ __forceinline__ void storeNode(uint32_t* nodes, uint32_t i, const NodeWords& n)
+{
+	uint4* p = reinterpret_cast<uint4*>(nodes) + (size_t)i * 2;
+	p[0] = make_uint4(n.w[0], n.w[1], n.w[2], n.w[3]);
+	p[1] = make_uint4(n.w[4], n.w[5], n.w[6], n.w[7]);
+}
+
+__device__ __forceinline__ uint64_t hashNode(const NodeWords& n)
+{
+	uint64_t h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+	for (int k = 0; k < 8; k += 2) {
+		h ^= (uint64_t)n.w[k] | ((uint64_t)n.w[k + 1] << 32);
+		h *= 0xff51afd7ed558ccdull;
+		h ^= h >> 29;
+	}
+	h *= 0xc4ceb9fe1a85ec53ull;
+	h ^= h >> 32;
+	return h;
+}
+
+__global__ void bakeInit(uint32_t n, uint32_t root, uint8_t* mark, uint32_t* newIndex, uint32_t* rep, uint32_t* flags, unsigned long long* frontier)
+{
+	if (blockIdx.x == 0 && threadIdx.x == 0) frontier[1] = 1;   // the root is the frontier of depth 1
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		mark[i] = (i == root) ? 1 : 0;
+		newIndex[i] = i < kMaterialCount ? i : kUnresolved;
+		rep[i] = 0xffffffffu;
+		flags[i] = 0;
+	}
+}
+
+// Pass `depth` (1-based): expand the nodes first reached at that depth. frontier[d] != 0 iff something was first reached at depth d.
+__global__ void bakeReach(const uint32_t* __restrict__ nodes, uint32_t n, uint32_t depth, uint8_t* mark, unsigned long long* frontier)
+{
+	if (frontier[depth] == 0) return;            // nothing was reached at this depth: the walk is over
+	bool found = false;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		if (mark[i] != depth) continue;
+		const NodeWords node = loadNode(nodes, i);
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			const uint32_t c = node.w[k];
+			if (c < kMaterialCount || c >= n) continue;
+			// Parents racing for the same child all store the same byte.
+			if (mark[c] == 0) { mark[c] = (uint8_t)(depth + 1u); found = true; }
+		}
+	}
+	if (__any_sync(0xffffffffu, found) && (threadIdx.x & 31) == 0) frontier[depth + 1] = 1;
+}
+
+// counters[0] = results[3] = non-material nodes the root reaches.
+__global__ void bakeCountReached(uint32_t n, const uint8_t* __restrict__ mark, unsigned long long* counters, unsigned long long* results)
+{
+	unsigned long long c = 0;
+	for (uint32_t i = kMaterialCount + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += mark[i] != 0;
+	for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+	if ((threadIdx.x & 31) == 0 && c) { atomicAdd(&counters[0], c); atomicAdd(&results[3], c); }
+}
+
+// A reachable node whose children all have final ids becomes either a material (all eight the same material) or
+// a pending hash-cons candidate with its canonical content written out.
+__global__ void bakeResolve(const uint32_t* __restrict__ nodes, uint32_t n, const uint8_t* __restrict__ mark,
+	uint32_t* newIndex, uint32_t* canon, unsigned long long* counters)
+{
+	if (counters[0] == 0) return;                // counters[0] = reachable nodes still without an id
+	unsigned long long collapsed = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		if (mark[i] == 0 || newIndex[i] != kUnresolved) continue;
+		NodeWords node = loadNode(nodes, i);
+		bool ready = true;
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			uint32_t c = node.w[k];
+			if (c >= kMaterialCount) c = (c < n) ? __ldcg(&newIndex[c]) : kUnresolved;
+			ready = ready && (c < kPending);
+			node.w[k] = c;
+		}
+		if (!ready) continue;
+		bool uniform = node.w[0] < kMaterialCount;
+#pragma unroll
+		for (int k = 1; k < 8; k++) uniform = uniform && (node.w[k] == node.w[0]);
+		if (uniform) {
+			newIndex[i] = node.w[0];             // the whole cube is one material (storage.cpp:261-263)
+			collapsed++;
+		} else {
+			storeNode(canon, i, node);
+			newIndex[i] = kPending;
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) collapsed += __shfl_down_sync(0xffffffffu, collapsed, o);
+	if ((threadIdx.x & 31) == 0 && collapsed) atomicAdd(&counters[2], collapsed);   // folded into counters[0] by bakeInsert
+}
+
+// Hash-cons the pending nodes. table[slot] = original index of the node that owns the slot.
+__global__ void bakeInsert(uint32_t n, uint32_t* newIndex, const uint32_t* __restrict__ canon, uint32_t* table, uint32_t tableMask,
+	uint32_t* rep, unsigned long long* counters)
+{
+	if (counters[0] == 0) return;
+	unsigned long long resolved = 0, distinct = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		if (newIndex[i] != kPending) continue;
+		const NodeWords key = loadNode(canon, i);
+		uint32_t slot = (uint32_t)hashNode(key) & tableMask;
+		uint32_t owner;
+		for (;;) {
+			owner = table[slot];
+			if (owner == kEmptySlot) {
+				owner = atomicCAS(&table[slot], kEmptySlot, i);
+				if (owner == kEmptySlot) { owner = i; distinct++; break; }
+			}
+			// canon[owner] was written by bakeResolve, i.e. before this kernel started: plain loads see it.
+			const NodeWords other = loadNode(canon, owner);
+			bool same = true;
+#pragma unroll
+			for (int k = 0; k < 8; k++) same = same && (other.w[k] == key.w[k]);
+			if (same) break;
+			slot = (slot + 1u) & tableMask;
+		}
+		newIndex[i] = owner;
+		atomicMin(&rep[owner], i);
+		resolved++;
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		resolved += __shfl_down_sync(0xffffffffu, resolved, o);
+		distinct += __shfl_down_sync(0xffffffffu, distinct, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		if (resolved) atomicAdd(&counters[3], resolved);
+		if (distinct) atomicAdd(&counters[1], distinct);
+	}
+}
+
+// Between passes: remaining -= collapsed + resolved of the pass just finished (single thread, keeps the early-outs exact).
+__global__ void bakeSettle(unsigned long long* counters)
+{
+	counters[0] -= counters[2] + counters[3];
+	counters[2] = 0;
+	counters[3] = 0;
+}
+
+__global__ void bakeFlag(uint32_t n, const uint8_t* __restrict__ mark, const uint32_t* __restrict__ newIndex, const uint32_t* __restrict__ rep, uint32_t* flags)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		if (i >= kMaterialCount && mark[i] != 0 && newIndex[i] == i) flags[rep[i]] = 1;   // i owns a class; rep[i] <= i is its first occurrence
+	}
+}
+
+// ---- exclusive scan of 32-bit flags/counts: tile reduce -> scan of tile sums (recursive) -> tile scan ----
+__global__ void scanTileSums(const uint32_t* __restrict__ in, uint64_t n, uint32_t* sums)
+{
+	__shared__ uint32_t warpSums[kScanThreads / 32];
+	const uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+	uint32_t s = 0;
+#pragma unroll
+	for (int k = 0; k < kScanItems; k++) {
+		const uint64_t i = base + (uint64_t)k * kScanThreads + threadIdx.x;
+		if (i < n) s += in[i];
+	}
+	for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+	if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = s;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t t = 0;
+		for (int w = 0; w < kScanThreads / 32; w++) t += warpSums[w];
+		sums[blockIdx.x] = t;
+	}
+}
+
+// out[i] = offsets[tile] + exclusive prefix of in[] within the tile (in == out allowed). offsets == nullptr: 0.
+__global__ void scanTiles(const uint32_t* in, uint64_t n, const uint32_t* __restrict__ offsets, uint32_t* out)
+{
+	__shared__ uint32_t warpSums[kScanThreads / 32];
+	const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;   // blocked arrangement
+	uint32_t v[kScanItems];
+	uint32_t s = 0;
+#pragma unroll
+	for (int k = 0; k < kScanItems; k++) {
+		v[k] = (base + k < n) ? in[base + k] : 0u;
+		s += v[k];
+	}
+	uint32_t incl = s;
+	const int lane = threadIdx.x & 31;
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl += t;
+	}
+	if (lane == 31) warpSums[threadIdx.x >> 5] = incl;
+	__syncthreads();
+	uint32_t before = offsets ? offsets[blockIdx.x] : 0u;
+	for (int w = 0; w < (int)(threadIdx.x >> 5); w++) before += warpSums[w];
+	uint32_t run = before + incl - s;
+#pragma unroll
+	for (int k = 0; k < kScanItems; k++) {
+		if (base + k < n) out[base + k] = run;
+		run += v[k];
+	}
+}
+
+cudaError_t exclusiveScan(uint32_t* data, uint64_t n, uint32_t* scratch, cudaStream_t stream, uint64_t* launches)
+{
+	// scratch holds the tile sums of every level back to back: n/2048 + n/2048^2 + ... + 1 words.
+	const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
+	if (tiles <= 1) {
+		scanTiles<<<1, kScanThreads, 0, stream>>>(data, n, nullptr, data);
+		*launches += 1;
+		return cudaGetLastError();
+	}
+	scanTileSums<<<(unsigned)tiles, kScanThreads, 0, stream>>>(data, n, scratch);
+	cudaError_t e = exclusiveScan(scratch, tiles, scratch + tiles, stream, launches);
+	if (e != cudaSuccess) return e;
+	scanTiles<<<(unsigned)tiles, kScanThreads, 0, stream>>>(data, n, scratch, data);
+	*launches += 2;
+	return cudaGetLastError();
+}
+
+// Emit the distinct nodes in first-occurrence order with their children renumbered; the 256 material nodes first.
+__global__ void bakeEmit(uint32_t n, const uint8_t* __restrict__ mark, const uint32_t* __restrict__ newIndex, const uint32_t* __restrict__ rep,
+	const uint32_t* __restrict__ position, const uint32_t* __restrict__ canon, uint32_t* out)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		if (i < kMaterialCount) {
+			NodeWords self;
+#pragma unroll
+			for (int k = 0; k < 8; k++) self.w[k] = i;
+			storeNode(out, i, self);
+			continue;
+		}
+		if (mark[i] == 0 || newIndex[i] != i) continue;
+		NodeWords node = loadNode(canon, i);
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			const uint32_t c = node.w[k];
+			node.w[k] = c < kMaterialCount ? c : kMaterialCount + position[rep[c]];
+		}
+		storeNode(out, kMaterialCount + position[rep[i]], node);
+	}
+}
+
+// result[0] = new root index
+__global__ void bakeRoot(uint32_t root, const uint32_t* newIndex, const uint32_t* rep, const uint32_t* position, uint32_t* result)
+{
+	const uint32_t r = newIndex[root];
+	result[0] = r < kMaterialCount ? r : (r >= kPending ? 0u : kMaterialCount + position[rep[r]]);   // unresolved: the caller reports the cycle
+}
+
+// findSubDAG (reference src/library/raytracing.cpp:43-87) on the device copy: one thread per root octant.
+__global__ void subdagKernel(const uint32_t* __restrict__ nodes, uint32_t nodeCount, uint32_t root, const unsigned long long* rootPtr, SubDag* out, uint32_t* status)
+{
+	const uint32_t octant = threadIdx.x;
+	if (octant >= 8) return;
+	if (rootPtr) root = (uint32_t)*rootPtr;
+	int height = 32;
+	uint32_t lower[3] = { 0x80000000u, 0x80000000u, 0x80000000u };
+	uint32_t only = octant;
+	SubDag sd;
+	sd.lower[0] = sd.lower[1] = sd.lower[2] = 0; sd.height = 0; sd.pad0 = 0; sd.node = 0; sd.pad1 = 0; sd.pad2 = 0;
+	bool ok = root < nodeCount;
+	uint32_t next = ok ? nodes[(size_t)root * 8 + only] : 0;
+	uint32_t node = 0, occupied = 1;
+	while (ok && occupied == 1) {
+		height--;
+		if (height < 0) { ok = false; break; }
+		node = next;
+		if (node >= nodeCount) { ok = false; break; }
+		for (int a = 0; a < 3; a++) lower[a] ^= ((only >> a) & 1u) << height;
+		occupied = 0;
+		for (uint32_t c = 0; c < 8; c++) {
+			const uint32_t child = nodes[(size_t)node * 8 + c];
+			if (child > 0) { next = child; occupied++; only = c; }
+		}
+	}
+	if (ok) {
+		for (int a = 0; a < 3; a++) sd.lower[a] = (int32_t)lower[a];
+		sd.height = height;
+		sd.node = node;
+	} else {
+		atomicOr(status, 1u);
+	}
+	out[octant] = sd;
+}
+
+__global__ void bakeResults(const unsigned long long* counters, const uint32_t* rootOut, unsigned long long* results)
+{
+	results[0] = counters[0];
+	results[1] = counters[1];
+	results[2] = rootOut[0];
+}
+
+int gridFor(uint64_t n, int smCount)
+{
+	const uint64_t want = (n + 255) / 256;
+	const uint64_t cap = (uint64_t)smCount * 8;     // 8 x 256 threads = every resident lane of an SM
+	return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+} // namespace
+
+// The scratch buffer, carved into 256-byte aligned sections.
+struct BakeScratch {
+	uint32_t* canon; uint32_t* newIndex; uint32_t* rep; uint32_t* flags; uint8_t* mark; uint32_t* table; uint32_t* scan;
+	unsigned long long* counters; uint32_t* rootOut;
+	size_t bytes;
+};
+
+static BakeScratch carve(uint8_t* base, uint64_t n, uint64_t tableSlots)
+{
+	size_t at = 0;
+	auto take = [&](size_t bytes) { uint8_t* p = base + at; at += (bytes + 255) & ~(size_t)255; return p; };
+	uint64_t scanWords = 0;
+	for (uint64_t t = (n + kScanTile - 1) / kScanTile; ; t = (t + kScanTile - 1) / kScanTile) { scanWords += t; if (t <= 1) break; }
+	BakeScratch s;
+	s.canon = reinterpret_cast<uint32_t*>(take(n * 32));
+	s.newIndex = reinterpret_cast<uint32_t*>(take(n * 4));
+	s.rep = reinterpret_cast<uint32_t*>(take(n * 4));
+	s.flags = reinterpret_cast<uint32_t*>(take(n * 4));
+	s.mark = take(n);
+	s.table = reinterpret_cast<uint32_t*>(take(tableSlots * 4));
+	s.scan = reinterpret_cast<uint32_t*>(take((scanWords + 8) * 4));
+	s.counters = reinterpret_cast<unsigned long long*>(take(64 * 8));   // [0..3] counters, [8 + d] frontier of depth d
+	s.rootOut = reinterpret_cast<uint32_t*>(take(256));
+	s.bytes = at;
+	return s;
+}
+
+size_t bakeScratchBytes(uint64_t n, uint64_t* tableSlots)
+{
+	uint64_t slots = 1024;
+	while (slots < 2 * n) slots <<= 1;
+	if (slots > 0x80000000ull) slots = 0x80000000ull;
+	*tableSlots = slots;
+	return carve(nullptr, n, slots).bytes;
+}
+
+cudaError_t launchSubdags(const uint32_t* nodes, uint32_t nodeCount, uint32_t root, const unsigned long long* rootPtr, SubDag* out, uint32_t* status, cudaStream_t stream)
+{
+	subdagKernel<<<1, 32, 0, stream>>>(nodes, nodeCount, root, rootPtr, out, status);
+	return cudaGetLastError();
+}
+
+// Enqueue the whole bake on `stream`. `scratch` is bakeScratchBytes(n) bytes; `out` has room for n nodes.
+// Afterwards (stream order) results[0] = reachable nodes left without an id (0 unless the array has a cycle or is
+// deeper than 32 levels), results[1] = distinct non-material nodes, results[2] = new root index,
+// results[3] = nodes reachable from the root before merging.
+cudaError_t launchBake(const uint32_t* nodes, uint64_t n64, uint32_t root, uint8_t* scratch, uint64_t tableSlots, uint32_t* out,
+	unsigned long long* results, int smCount, cudaStream_t stream, uint64_t* launches)
+{
+	const uint32_t n = (uint32_t)n64;
+	const BakeScratch sc = carve(scratch, n64, tableSlots);
+	uint32_t* canon = sc.canon; uint32_t* newIndex = sc.newIndex; uint32_t* rep = sc.rep; uint32_t* flags = sc.flags;
+	uint8_t* mark = sc.mark; uint32_t* table = sc.table; uint32_t* scanScratch = sc.scan;
+	unsigned long long* counters = sc.counters; uint32_t* rootOut = sc.rootOut;
+
+	const int grid = gridFor(n64, smCount);
+	uint64_t count = 0;
+	cudaError_t e;
+	if ((e = cudaMemsetAsync(counters, 0, 64 * 8, stream)) != cudaSuccess) return e;
+	if ((e = cudaMemsetAsync(table, 0xff, tableSlots * 4, stream)) != cudaSuccess) return e;
+	unsigned long long* frontier = counters + 8;
+	bakeInit<<<grid, 256, 0, stream>>>(n, root, mark, newIndex, rep, flags, frontier); count++;
+	for (uint32_t depth = 1; depth <= 33; depth++) { bakeReach<<<grid, 256, 0, stream>>>(nodes, n, depth, mark, frontier); count++; }
+	if ((e = cudaMemsetAsync(results, 0, 4 * sizeof(unsigned long long), stream)) != cudaSuccess) return e;
+	bakeCountReached<<<grid, 256, 0, stream>>>(n, mark, counters, results); count++;
+	for (int pass = 0; pass < 33; pass++) {
+		bakeResolve<<<grid, 256, 0, stream>>>(nodes, n, mark, newIndex, canon, counters);
+		bakeInsert<<<grid, 256, 0, stream>>>(n, newIndex, canon, table, (uint32_t)(tableSlots - 1), rep, counters);
+		bakeSettle<<<1, 1, 0, stream>>>(counters);
+		count += 3;
+	}
+	bakeFlag<<<grid, 256, 0, stream>>>(n, mark, newIndex, rep, flags); count++;
+	if ((e = exclusiveScan(flags, n64, scanScratch, stream, &count)) != cudaSuccess) return e;
+	bakeEmit<<<grid, 256, 0, stream>>>(n, mark, newIndex, rep, flags, canon, out); count++;
+	bakeRoot<<<1, 1, 0, stream>>>(root, newIndex, rep, flags, rootOut); count++;
+	bakeResults<<<1, 1, 0, stream>>>(counters, rootOut, results); count++;
+	if (launches) *launches += count;
+	return cudaGetLastError();
+}
+
+} // namespace cbq

@@ -117,4 +117,11 @@ typedef int (*QueueFn)(void* user, cudaStream_t stream, unsigned long long** out
 cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, const LaunchConfig& cfg, cudaStream_t stream,
 	QueueFn nextQueue, void* user, uint64_t* launches);
 
+// Device-side bake (bake_kernels.cu).
+size_t bakeScratchBytes(uint64_t nodeCount, uint64_t* tableSlots);
+cudaError_t launchBake(const uint32_t* nodes, uint64_t nodeCount, uint32_t root, uint8_t* scratch, uint64_t tableSlots, uint32_t* out,
+	unsigned long long* results, int smCount, cudaStream_t stream, uint64_t* launches);
+// findSubDAGs on a device array; root is read from *rootPtr when rootPtr != nullptr. *status |= 1 on a runaway chain.
+cudaError_t launchSubdags(const uint32_t* nodes, uint32_t nodeCount, uint32_t root, const unsigned long long* rootPtr, SubDag* out, uint32_t* status, cudaStream_t stream);
+
 } // namespace cbq

@@ -73,6 +73,16 @@ public:
 		return cbq_update(mCtx, static_cast<const uint32_t*>(nodes), sharedNodesEndAtLastSync, nodeCount, root) == CBQ_OK;
 	}
 
+	// Volume::bake() (storage.cpp:388-395) on the device copy. On success the device holds the merged DAG;
+	// nodeCount/root describe it and download() reads it back, e.g. into a fresh Volume via the .dag layout.
+	bool bake(uint64_t& nodeCount, uint32_t& root)
+	{
+		const bool ok = cbq_bake(mCtx, &nodeCount, &root) == CBQ_OK;
+		if (ok) mSynced = nodeCount;
+		return ok;
+	}
+	bool download(uint64_t begin, uint64_t count, void* nodesOut) { return cbq_download_nodes(mCtx, begin, count, static_cast<uint32_t*>(nodesOut)) == CBQ_OK; }
+
 	SubDAGArray subDAGs() const
 	{
 		SubDAGArray a{};

@@ -130,6 +130,18 @@ int cbq_upload(cbq_context* ctx, const uint32_t* nodes, uint64_t node_count, uin
 int cbq_update(cbq_context* ctx, const uint32_t* nodes, uint64_t dirty_begin, uint64_t node_count,
                uint32_t root_index);
 
+/* Volume::bake() (reference src/library/storage.cpp:388-395 -> NodeStore::merge / merge_node, :208-290) on the
+ * DEVICE copy, without a host round trip: everything the root reaches is hash-consed bottom-up, a node whose eight
+ * merged children are one material becomes that material (isMaterialNode(const Node&), :69-75), unreachable nodes
+ * (undo history, copy-on-write garbage) are dropped and the children are renumbered. The result is the same
+ * canonical minimal DAG the reference produces -- same node count, same voxels, isomorphic -- but not the same
+ * array ORDER (the reference's order is its hash-table slot order; here distinct nodes keep the relative order
+ * of their first occurrence in the input, so the output is deterministic and baking twice is the identity).
+ * The device volume is replaced in place, sub-DAGs are refreshed on the device. *node_count (including the 256
+ * material nodes) and *root_index describe the new array; read it back with cbq_download_nodes. Host-side
+ * editors (cbq_editable) holding the old array must be re-created from the download: every index moved. */
+int cbq_bake(cbq_context* ctx, uint64_t* node_count, uint32_t* root_index);
+
 int cbq_set_colours(cbq_context* ctx, const float* colours_rgb);
 int cbq_get_subdags(cbq_context* ctx, cbq_subdag out[8]);
 

@@ -309,3 +309,42 @@ class RefVolume:
         hits = np.zeros(len(rays), dtype=HIT_DTYPE)
         self.L.ref_trace_ray_ref(self.h, _ptr(rays), len(rays), _ptr(hits))
         return hits
+
+
+def dag_signature(nodes, root):
+    """Checker for bake parity: the canonical form of the DAG below `root`, independent of node order.
+
+    Follows NodeStore::merge_node (reference storage.cpp:243-290): children first, a node whose eight merged
+    children are one material IS that material, otherwise nodes are identified by content. Returns
+    (signature of the root, number of distinct non-material nodes); two arrays describe the same volume with the
+    same sharing iff both values agree. Iterative post-order, hashlib digests as content ids."""
+    import hashlib
+    nodes = np.ascontiguousarray(nodes, dtype=np.uint32).reshape(-1, 8)
+    sig = {}
+    distinct = set()
+
+    def mat(m):
+        return b"m" + int(m).to_bytes(4, "little")
+
+    if root < 256:
+        return mat(root), 0
+    stack = [(int(root), False)]
+    while stack:
+        i, expanded = stack.pop()
+        if i in sig:
+            continue
+        kids = [int(c) for c in nodes[i]]
+        if not expanded:
+            stack.append((i, True))
+            for c in kids:
+                if c >= 256 and c not in sig:
+                    stack.append((c, False))
+            continue
+        parts = [mat(c) if c < 256 else sig[c] for c in kids]
+        if parts[0][:1] == b"m" and all(p == parts[0] for p in parts):
+            sig[i] = parts[0]
+        else:
+            d = hashlib.blake2b(b"".join(parts), digest_size=16).digest()
+            sig[i] = b"n" + d
+            distinct.add(d)
+    return sig[int(root)], len(distinct)

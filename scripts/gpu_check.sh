@@ -18,6 +18,14 @@ launches) echo "== ncu launch list"
   grep -c . $OUT/launches.csv;;
 ncu) echo "== ncu full capture"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:tracePersistent -s 4 -c 1 -o $OUT/prof_trace -f python bench.py --steps 3 --warmup 3 > $OUT/ncu_full.log 2>&1; tail -2 $OUT/ncu_full.log | cut -c1-300;;
+baketests) echo "== bake tests"; timeout 900 python -m pytest tests/test_gpu_bake.py -q --timeout 600 2>&1 | tee $OUT/pytest_bake.log | tail -25;;
+bakesan) echo "== bake under compute-sanitizer"
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_bake.py -q --timeout 800 -k "unbaked or cycles or uniform or deterministic" > $OUT/bake_memcheck.log 2>&1; echo "exit $?"; tail -8 $OUT/bake_memcheck.log
+  timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_bake.py -q --timeout 800 -k "unbaked" > $OUT/bake_racecheck.log 2>&1; echo "exit $?"; tail -5 $OUT/bake_racecheck.log;;
+bake) echo "== bake bench"
+  timeout 600 python scripts/bake_bench.py --scene terrain --log2 12 --edits 200 --out $OUT/bake.jsonl 2>&1 | tail -3
+  timeout 600 python scripts/bake_bench.py --scene city --log2 16 --edits 200 --out $OUT/bake.jsonl 2>&1 | tail -3
+  timeout 600 python scripts/bake_bench.py --scene soup --log2 14 --edits 50 --out $OUT/bake.jsonl 2>&1 | tail -3;;
 sweep) echo "== sweep"; timeout 900 python scripts/sweep.py primary 2>&1 | tee $OUT/sweep_primary.jsonl;;
 sweeprandom) echo "== sweep random"; timeout 900 python scripts/sweep.py random 2>&1 | tee $OUT/sweep_random.jsonl;;
 esac
