@@ -58,7 +58,7 @@ def pt_params(width, height, spp=1, bounces=1, variant=VARIANT_ONE_BOUNCE, inclu
 
 EXPORTS = [
     "cbq_create", "cbq_destroy", "cbq_last_error", "cbq_device_count", "cbq_synchronize",
-    "cbq_upload", "cbq_update", "cbq_bake", "cbq_set_colours", "cbq_get_subdags", "cbq_find_subdags",
+    "cbq_upload", "cbq_update", "cbq_bake", "cbq_build_dense", "cbq_build_dense_device", "cbq_set_colours", "cbq_get_subdags", "cbq_find_subdags",
     "cbq_download_nodes", "cbq_node_count",
     "cbq_trace", "cbq_trace_device", "cbq_camera_from_pose", "cbq_primary_rays_device", "cbq_primary_rays_tiled_device", "cbq_random_rays_device",
     "cbq_raycast_frame_device",
@@ -95,6 +95,8 @@ def load_library():
     L.cbq_upload.argtypes = [vp, vp, u64, u32, vp]
     L.cbq_update.argtypes = [vp, vp, u64, u64, u32]
     L.cbq_bake.argtypes = [vp, C.POINTER(u64), C.POINTER(u32)]
+    L.cbq_build_dense.argtypes = [vp, vp, u32, C.POINTER(C.c_int32), vp, C.POINTER(u64), C.POINTER(u32)]
+    L.cbq_build_dense_device.argtypes = [vp, vp, u32, C.POINTER(C.c_int32), vp, C.POINTER(u64), C.POINTER(u32)]
     L.cbq_set_colours.argtypes = [vp, vp]
     L.cbq_get_subdags.argtypes = [vp, vp]
     L.cbq_find_subdags.argtypes = [vp, u64, u32, vp]
@@ -357,6 +359,27 @@ class Context:
         n = C.c_uint64()
         root = C.c_uint32()
         _check(self.L.cbq_bake(self._h, C.byref(n), C.byref(root)))
+        return int(n.value), int(root.value)
+
+    def build_dense(self, voxels, origin=(0, 0, 0), colours=None, device_ptr=None, size_log2=None):
+        """setVoxel for every voxel + bake (reference storage.cpp:388-438), on the device. voxels: uint8 array
+        [z, y, x] with side 2^k, or a device pointer (device_ptr, size_log2). Returns (node_count, root)."""
+        n = C.c_uint64()
+        root = C.c_uint32()
+        org = (C.c_int32 * 3)(*[int(v) for v in origin])
+        col = None
+        if colours is not None:
+            col = np.ascontiguousarray(colours, dtype=np.float32).reshape(256, 3)
+        if device_ptr is not None:
+            _check(self.L.cbq_build_dense_device(self._h, C.c_void_p(int(device_ptr)), int(size_log2), org, _ptr(col) if col is not None else None,
+                                                 C.byref(n), C.byref(root)))
+        else:
+            voxels = np.ascontiguousarray(voxels, dtype=np.uint8)
+            side = voxels.shape[0]
+            k = int(side).bit_length() - 1
+            if voxels.shape != (side, side, side) or (1 << k) != side:
+                raise ValueError("voxels must be a cube with a power-of-two side")
+            _check(self.L.cbq_build_dense(self._h, _ptr(voxels), k, org, _ptr(col) if col is not None else None, C.byref(n), C.byref(root)))
         return int(n.value), int(root.value)
 
     def subdags(self):

@@ -262,6 +262,72 @@ int traceDevice(cbq_context* ctx, const cbq::Ray* dRays, uint64_t n, uint32_t fl
 	return CBQ_OK;
 }
 
+// Hash-cons merge of the device array `dNodes` (cbq::launchBake) and installation of the result as the context's
+// volume: new buffer from the pool, colours carried over, sub-DAGs recomputed on the device.
+int bakeAndInstall(cbq_context* ctx, const uint32_t* dNodes, uint64_t n, uint32_t root, const char* what)
+{
+	uint64_t slots = 0;
+	const size_t scratchBytes = cbq::bakeScratchBytes(n, &slots);
+	const size_t tailBytes = 4 * sizeof(unsigned long long) + 8 * sizeof(cbq::SubDag) + 64;   // results, sub-DAGs, status
+	size_t newBytes = cbq::kNodeOffset + (size_t)n * 32;     // the merged array is never longer than the input
+	uint8_t* scratch = nullptr;
+	uint8_t* baked = nullptr;
+	CBQ_CUDA(poolAlloc(ctx, &scratch, scratchBytes + tailBytes));
+	if (poolAlloc(ctx, &baked, newBytes) != cudaSuccess) { cudaGetLastError(); poolFree(ctx, scratch); return fail(CBQ_ERROR_OUT_OF_MEMORY, "%s: no room for the merged copy of the volume (%zu bytes)", what, newBytes); }
+	unsigned long long* dResults = reinterpret_cast<unsigned long long*>(scratch + scratchBytes);
+	cbq::SubDag* dSubdags = reinterpret_cast<cbq::SubDag*>(dResults + 4);
+	uint32_t* dStatus = reinterpret_cast<uint32_t*>(dSubdags + 8);
+	uint32_t* outNodes = reinterpret_cast<uint32_t*>(baked + cbq::kNodeOffset);
+
+	struct { unsigned long long results[4]; cbq::SubDag subdags[8]; uint32_t status; } host;
+	cudaError_t e = cudaMemsetAsync(dStatus, 0, 64, ctx->stream);
+	if (e == cudaSuccess) e = cbq::launchBake(dNodes, n, root, scratch, slots, outNodes, dResults, ctx->cfg.smCount, ctx->stream, &ctx->launches);
+	if (e == cudaSuccess) e = cbq::launchSubdags(outNodes, (uint32_t)n, 0, dResults + 2, dSubdags, dStatus, ctx->stream);
+	if (e == cudaSuccess && ctx->volume) e = cudaMemcpyAsync(baked + cbq::kColourOffset, ctx->volume + cbq::kColourOffset, cbq::kNodeOffset - cbq::kColourOffset, cudaMemcpyDeviceToDevice, ctx->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(&host, dResults, sizeof(host.results) + sizeof(host.subdags) + sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	poolFree(ctx, scratch);
+	if (e != cudaSuccess) { poolFree(ctx, baked); return fail(CBQ_ERROR_CUDA, "%s failed: %s", what, cudaGetErrorString(e)); }
+	ctx->launches += 1;
+	ctx->bytesD2H += sizeof(host);
+	if (host.results[0] != 0) {
+		poolFree(ctx, baked);
+		return fail(CBQ_ERROR_CORRUPT_VOLUME, "%s: %llu reachable nodes never resolved (a cycle, or a DAG deeper than 32 levels); the volume is unchanged",
+			what, host.results[0]);
+	}
+	if (host.status != 0) { poolFree(ctx, baked); return fail(CBQ_ERROR_CORRUPT_VOLUME, "%s: the merged array has no valid sub-DAGs; the volume is unchanged", what); }
+
+	const uint64_t count = cbq::kMaterialCount + host.results[1];
+	uint64_t capacity = n;
+	const uint64_t wanted = count + std::max<uint64_t>(count / 4, 1u << 16);     // the head-room cbq_upload gives
+	if (capacity > 2 * wanted) {
+		// Mostly merged away (a dense grid, a long edit session): move into a buffer of the usual size.
+		uint8_t* snug = nullptr;
+		const size_t snugBytes = cbq::kNodeOffset + (size_t)wanted * 32;
+		if (poolAlloc(ctx, &snug, snugBytes) == cudaSuccess) {
+			CBQ_CUDA(cudaMemcpyAsync(snug, baked, cbq::kNodeOffset + (size_t)count * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+			poolFree(ctx, baked);
+			baked = snug; newBytes = snugBytes; capacity = wanted;
+		} else cudaGetLastError();
+	}
+
+	CBQ_CUDA(cudaDeviceSynchronize());           // nobody may still be reading the old copy
+	poolFree(ctx, ctx->volume);
+	ctx->volume = baked;
+	ctx->volumeBytes = newBytes;
+	ctx->nodeCapacity = capacity;
+	ctx->nodeCount = count;
+	ctx->root = (uint32_t)host.results[2];
+	ctx->generation++;
+	ctx->bakeReachable = host.results[3];
+	std::memcpy(ctx->subdags, host.subdags, sizeof(host.subdags));
+	int maxH = 0;
+	for (int i = 0; i < 8; i++) if (ctx->subdags[i].node > 0) maxH = std::max(maxH, ctx->subdags[i].height);
+	ctx->maxSubDagHeight = maxH;
+	ctx->cfg.stackLevels = maxH + 1;
+	return writeHeaderAndSubdags(ctx);
+}
+
 } // namespace
 
 extern "C" {
@@ -427,56 +493,56 @@ int cbq_bake(cbq_context* ctx, uint64_t* node_count, uint32_t* root_index)
 {
 	int rc = bind(ctx); if (rc) return rc;
 	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "cbq_bake before cbq_upload");
-	const uint64_t n = ctx->nodeCount;
-	uint64_t slots = 0;
-	const size_t scratchBytes = cbq::bakeScratchBytes(n, &slots);
-	const size_t tailBytes = 4 * sizeof(unsigned long long) + 8 * sizeof(cbq::SubDag) + 64;   // results, sub-DAGs, status
-	const size_t newBytes = cbq::kNodeOffset + (size_t)n * 32;     // the merged array is never longer than the input
-	uint8_t* scratch = nullptr;
-	uint8_t* baked = nullptr;
 	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
-	CBQ_CUDA(poolAlloc(ctx, &scratch, scratchBytes + tailBytes));
-	if (poolAlloc(ctx, &baked, newBytes) != cudaSuccess) { cudaGetLastError(); poolFree(ctx, scratch); return fail(CBQ_ERROR_OUT_OF_MEMORY, "cbq_bake: no room for a second copy of the volume (%zu bytes)", newBytes); }
-	unsigned long long* dResults = reinterpret_cast<unsigned long long*>(scratch + scratchBytes);
-	cbq::SubDag* dSubdags = reinterpret_cast<cbq::SubDag*>(dResults + 4);
-	uint32_t* dStatus = reinterpret_cast<uint32_t*>(dSubdags + 8);
-	uint32_t* outNodes = reinterpret_cast<uint32_t*>(baked + cbq::kNodeOffset);
-
-	struct { unsigned long long results[4]; cbq::SubDag subdags[8]; uint32_t status; } host;
-	cudaError_t e = cudaMemsetAsync(dStatus, 0, 64, ctx->stream);
-	if (e == cudaSuccess) e = cbq::launchBake(ctx->nodesPtr(), n, ctx->root, scratch, slots, outNodes, dResults, ctx->cfg.smCount, ctx->stream, &ctx->launches);
-	if (e == cudaSuccess) e = cbq::launchSubdags(outNodes, (uint32_t)n, 0, dResults + 2, dSubdags, dStatus, ctx->stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(baked + cbq::kColourOffset, ctx->volume + cbq::kColourOffset, cbq::kNodeOffset - cbq::kColourOffset, cudaMemcpyDeviceToDevice, ctx->stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(&host, dResults, sizeof(host.results) + sizeof(host.subdags) + sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-	poolFree(ctx, scratch);
-	if (e != cudaSuccess) { poolFree(ctx, baked); return fail(CBQ_ERROR_CUDA, "cbq_bake failed: %s", cudaGetErrorString(e)); }
-	ctx->launches += 1;
-	ctx->bytesD2H += sizeof(host);
-	if (host.results[0] != 0) {
-		poolFree(ctx, baked);
-		return fail(CBQ_ERROR_CORRUPT_VOLUME, "cbq_bake: %llu reachable nodes never resolved (a cycle, or a DAG deeper than 32 levels); the volume is unchanged",
-			host.results[0]);
-	}
-	if (host.status != 0) { poolFree(ctx, baked); return fail(CBQ_ERROR_CORRUPT_VOLUME, "cbq_bake: the merged array has no valid sub-DAGs; the volume is unchanged"); }
-
-	CBQ_CUDA(cudaDeviceSynchronize());           // nobody may still be reading the old copy
-	poolFree(ctx, ctx->volume);
-	ctx->volume = baked;
-	ctx->volumeBytes = newBytes;
-	ctx->nodeCapacity = n;
-	ctx->nodeCount = cbq::kMaterialCount + host.results[1];
-	ctx->root = (uint32_t)host.results[2];
-	ctx->generation++;
-	ctx->bakeReachable = host.results[3];
-	std::memcpy(ctx->subdags, host.subdags, sizeof(host.subdags));
-	int maxH = 0;
-	for (int i = 0; i < 8; i++) if (ctx->subdags[i].node > 0) maxH = std::max(maxH, ctx->subdags[i].height);
-	ctx->maxSubDagHeight = maxH;
-	ctx->cfg.stackLevels = maxH + 1;
+	rc = bakeAndInstall(ctx, ctx->nodesPtr(), ctx->nodeCount, ctx->root, "cbq_bake"); if (rc) return rc;
 	if (node_count) *node_count = ctx->nodeCount;
 	if (root_index) *root_index = ctx->root;
-	return writeHeaderAndSubdags(ctx);
+	return CBQ_OK;
+}
+
+int cbq_build_dense_device(cbq_context* ctx, const uint8_t* d_voxels, uint32_t size_log2, const int32_t origin[3],
+	const float* colours_rgb, uint64_t* node_count, uint32_t* root_index)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!d_voxels || !origin) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");
+	if (size_log2 < 2 || size_log2 > 10) return fail(CBQ_ERROR_INVALID_ARGUMENT, "size_log2 %u out of range (2..10: 4^3 .. 1024^3 voxels)", size_log2);
+	const uint32_t side = 1u << size_log2;
+	for (int a = 0; a < 3; a++) {
+		if (((uint32_t)origin[a] & (side / 2 - 1u)) != 0) return fail(CBQ_ERROR_INVALID_ARGUMENT, "origin[%d] = %d is not a multiple of half the grid side (%u)", a, origin[a], side / 2);
+		if ((int64_t)origin[a] + (int64_t)side > 0x80000000ll) return fail(CBQ_ERROR_INVALID_ARGUMENT, "the grid leaves the volume along axis %d", a);
+	}
+	uint64_t n = cbq::denseNodeCount(size_log2);
+	uint8_t* tree = nullptr;
+	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	CBQ_CUDA(poolAlloc(ctx, &tree, (size_t)n * 32));
+	uint32_t root = 0;
+	cudaError_t e = cbq::launchBuildDense(d_voxels, size_log2, origin, reinterpret_cast<uint32_t*>(tree), &root, &n, ctx->cfg.smCount, ctx->stream, &ctx->launches);
+	if (e != cudaSuccess) { poolFree(ctx, tree); return fail(CBQ_ERROR_CUDA, "cbq_build_dense: %s", cudaGetErrorString(e)); }
+	const bool hadVolume = ctx->volume != nullptr;
+	rc = bakeAndInstall(ctx, reinterpret_cast<const uint32_t*>(tree), n, root, "cbq_build_dense");
+	poolFree(ctx, tree);
+	if (rc) return rc;
+	if (colours_rgb || !hadVolume) { rc = cbq_set_colours(ctx, colours_rgb); if (rc) return rc; }
+	if (node_count) *node_count = ctx->nodeCount;
+	if (root_index) *root_index = ctx->root;
+	return CBQ_OK;
+}
+
+int cbq_build_dense(cbq_context* ctx, const uint8_t* voxels, uint32_t size_log2, const int32_t origin[3],
+	const float* colours_rgb, uint64_t* node_count, uint32_t* root_index)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!voxels) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");
+	if (size_log2 < 2 || size_log2 > 10) return fail(CBQ_ERROR_INVALID_ARGUMENT, "size_log2 %u out of range (2..10)", size_log2);
+	const size_t bytes = (size_t)1 << (3 * size_log2);
+	uint8_t* d = nullptr;
+	CBQ_CUDA(poolAlloc(ctx, &d, bytes));
+	cudaError_t e = cudaMemcpyAsync(d, voxels, bytes, cudaMemcpyHostToDevice, ctx->stream);
+	if (e != cudaSuccess) { poolFree(ctx, d); return fail(CBQ_ERROR_CUDA, "cbq_build_dense: %s", cudaGetErrorString(e)); }
+	ctx->bytesH2D += bytes;
+	rc = cbq_build_dense_device(ctx, d, size_log2, origin, colours_rgb, node_count, root_index);
+	poolFree(ctx, d);
+	return rc;
 }
 
 int cbq_set_colours(cbq_context* ctx, const float* colours_rgb)

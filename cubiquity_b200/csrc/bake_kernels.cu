@@ -22,6 +22,8 @@
 // All of it is integer gather/scatter work bound by HBM sectors (DESIGN.md section 4.7 has the bytes per node).
 #include "cbq_internal.h"
 
+#include <vector>
+
 namespace cbq {
 
 namespace {
@@ -379,6 +381,111 @@ size_t bakeScratchBytes(uint64_t n, uint64_t* tableSlots)
 	if (slots > 0x80000000ull) slots = 0x80000000ull;
 	*tableSlots = slots;
 	return carve(nullptr, n, slots).bytes;
+}
+
+// ---- dense grid -> octree ------------------------------------------------------------------------------------
+// Height-1 nodes: the eight voxels of a 2x2x2 cell, child slot x | y << 1 | z << 2 (storage.cpp:57-67).
+__global__ void denseLeafKernel(const uint8_t* __restrict__ voxels, uint32_t k, uint32_t* nodes)
+{
+	const uint32_t half = k - 1;                          // log2 of cells per side
+	const uint64_t cells = 1ull << (3 * half);
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t X = i & ((1ull << half) - 1), Y = (i >> half) & ((1ull << half) - 1), Z = i >> (2 * half);
+		NodeWords n;
+#pragma unroll
+		for (int z = 0; z < 2; z++)
+#pragma unroll
+			for (int y = 0; y < 2; y++) {
+				const uint64_t at = ((2 * Z + z) << (2 * k)) + ((2 * Y + y) << k) + 2 * X;
+				const uint16_t pair = *reinterpret_cast<const uint16_t*>(voxels + at);
+				n.w[z * 4 + y * 2 + 0] = pair & 0xffu;
+				n.w[z * 4 + y * 2 + 1] = pair >> 8;
+			}
+		storeNode(nodes, (uint32_t)(kMaterialCount + i), n);
+	}
+}
+
+// Height-j nodes (j >= 2) point at the eight height-(j-1) nodes of their cell: pure index arithmetic.
+__global__ void denseInnerKernel(uint32_t cellsLog2, uint32_t base, uint32_t childBase, uint32_t* nodes)
+{
+	const uint64_t cells = 1ull << (3 * cellsLog2);
+	const uint32_t childSide = cellsLog2 + 1;             // log2 of child cells per side
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t X = i & ((1ull << cellsLog2) - 1), Y = (i >> cellsLog2) & ((1ull << cellsLog2) - 1), Z = i >> (2 * cellsLog2);
+		NodeWords n;
+#pragma unroll
+		for (int c = 0; c < 8; c++) {
+			const uint64_t x = 2 * X + (c & 1), y = 2 * Y + ((c >> 1) & 1), z = 2 * Z + (c >> 2);
+			n.w[c] = childBase + (uint32_t)((z << (2 * childSide)) + (y << childSide) + x);
+		}
+		storeNode(nodes, (uint32_t)(base + i), n);
+	}
+}
+
+uint64_t denseNodeCount(uint32_t k)
+{
+	uint64_t n = kMaterialCount;
+	for (uint32_t j = 1; j + 1 <= k; j++) n += 1ull << (3 * (k - j));
+	return n + 8 * (33 - k);                                  // room for the host-built top of the tree
+}
+
+// Levels 1 .. k-1 are written on the device; what is left are the eight height-(k-1) cubes the grid consists of.
+// Their ancestors up to the height-32 root (at most 8 chains of 33 - k nodes, shared where the cubes share a
+// parent: one chain when the origin is a multiple of the side, up to eight when the grid straddles 0) are a tiny
+// trie built here on the host, slot = next bit of the unsigned position (make_position_unsigned /
+// extract_next_child_id, storage.cpp:45-67).
+cudaError_t launchBuildDense(const uint8_t* voxels, uint32_t k, const int32_t origin[3], uint32_t* nodes, uint32_t* root, uint64_t* nodeCount,
+	int smCount, cudaStream_t stream, uint64_t* launches)
+{
+	// Material nodes are written by launchBake into ITS output; the input copy of them is never read (children < 256
+	// are ids, not indices), so [0, 256) of `nodes` stays untouched.
+	uint32_t base = kMaterialCount;
+	const uint64_t leaves = 1ull << (3 * (k - 1));
+	denseLeafKernel<<<gridFor(leaves, smCount), 256, 0, stream>>>(voxels, k, nodes);
+	uint64_t count = 1;
+	uint32_t childBase = base;
+	base += (uint32_t)leaves;
+	for (uint32_t j = 2; j + 1 <= k; j++) {
+		const uint32_t cellsLog2 = k - j;
+		const uint64_t cells = 1ull << (3 * cellsLog2);
+		denseInnerKernel<<<gridFor(cells, smCount), 256, 0, stream>>>(cellsLog2, base, childBase, nodes);
+		count++;
+		childBase = base;
+		base += (uint32_t)cells;
+	}
+	// childBase .. childBase + 8: the height-(k-1) cubes, index (z * 2 + y) * 2 + x within the grid.
+	struct Top { int h; uint64_t x, y, z; uint32_t child[8]; };
+	std::vector<Top> top;
+	auto nodeFor = [&](int h, uint64_t x, uint64_t y, uint64_t z) -> uint32_t {
+		for (size_t i = 0; i < top.size(); i++) if (top[i].h == h && top[i].x == x && top[i].y == y && top[i].z == z) return (uint32_t)i;
+		Top t; t.h = h; t.x = x; t.y = y; t.z = z;
+		for (int c = 0; c < 8; c++) t.child[c] = 0;
+		top.push_back(t);
+		return (uint32_t)(top.size() - 1);
+	};
+	const uint64_t u[3] = { (uint64_t)((uint32_t)origin[0] + 0x80000000u), (uint64_t)((uint32_t)origin[1] + 0x80000000u), (uint64_t)((uint32_t)origin[2] + 0x80000000u) };
+	const uint32_t rootAt = nodeFor(32, 0, 0, 0);
+	for (uint32_t c = 0; c < 8; c++) {
+		const uint64_t U[3] = { (u[0] >> (k - 1)) + (c & 1u), (u[1] >> (k - 1)) + ((c >> 1) & 1u), (u[2] >> (k - 1)) + (c >> 2) };
+		uint32_t cur = rootAt;
+		for (int h = 32; h >= (int)k; h--) {
+			const int bit = h - (int)k;
+			const uint32_t slot = (uint32_t)((U[0] >> bit) & 1u) | (uint32_t)(((U[1] >> bit) & 1u) << 1) | (uint32_t)(((U[2] >> bit) & 1u) << 2);
+			if (h == (int)k) { top[cur].child[slot] = childBase + c; break; }
+			const uint32_t next = nodeFor(h - 1, U[0] >> bit, U[1] >> bit, U[2] >> bit);
+			top[cur].child[slot] = base + next;
+			cur = next;
+		}
+	}
+	std::vector<uint32_t> words(top.size() * 8);
+	for (size_t i = 0; i < top.size(); i++) for (int c = 0; c < 8; c++) words[i * 8 + c] = top[i].child[c];
+	cudaError_t e = cudaMemcpyAsync(nodes + (size_t)base * 8, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream);
+	if (e != cudaSuccess) return e;
+	if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;     // `words` is on our stack frame
+	*root = base + rootAt;
+	*nodeCount = (uint64_t)base + top.size();
+	if (launches) *launches += count;
+	return cudaGetLastError();
 }
 
 cudaError_t launchSubdags(const uint32_t* nodes, uint32_t nodeCount, uint32_t root, const unsigned long long* rootPtr, SubDag* out, uint32_t* status, cudaStream_t stream)

@@ -124,4 +124,9 @@ cudaError_t launchBake(const uint32_t* nodes, uint64_t nodeCount, uint32_t root,
 // findSubDAGs on a device array; root is read from *rootPtr when rootPtr != nullptr. *status |= 1 on a runaway chain.
 cudaError_t launchSubdags(const uint32_t* nodes, uint32_t nodeCount, uint32_t root, const unsigned long long* rootPtr, SubDag* out, uint32_t* status, cudaStream_t stream);
 
+// Dense voxel grid -> complete (un-merged) octree below a height-32 root; launchBake then merges it.
+uint64_t denseNodeCount(uint32_t sizeLog2);   // upper bound: what to allocate
+cudaError_t launchBuildDense(const uint8_t* voxels, uint32_t sizeLog2, const int32_t origin[3], uint32_t* nodes, uint32_t* root, uint64_t* nodeCount,
+	int smCount, cudaStream_t stream, uint64_t* launches);
+
 } // namespace cbq

@@ -142,6 +142,19 @@ int cbq_update(cbq_context* ctx, const uint32_t* nodes, uint64_t dirty_begin, ui
  * editors (cbq_editable) holding the old array must be re-created from the download: every index moved. */
 int cbq_bake(cbq_context* ctx, uint64_t* node_count, uint32_t* root_index);
 
+/* Build the volume from a dense grid of material ids ON THE DEVICE: what the reference does one voxel at a time
+ * with Volume::setVoxel (storage.cpp:396-438) followed by Volume::bake (:388-395). voxels[(z * S + y) * S + x],
+ * S = 2^size_log2 (2 <= size_log2 <= 10), is the material of voxel origin + (x, y, z); origin must be a multiple
+ * of S / 2 per axis (so a grid centred on 0 is fine); everything outside the grid is empty (material 0). The complete octree over the grid is written
+ * level by level (no per-voxel inserts), chained up to the height-32 root and hash-consed with the same kernels
+ * as cbq_bake; the result -- the canonical DAG, i.e. the same node count and content as the reference's bake of
+ * the same voxels -- becomes the context's volume (read it back with cbq_download_nodes). colours_rgb as in
+ * cbq_upload. The _device variant takes a device pointer to the grid. */
+int cbq_build_dense(cbq_context* ctx, const uint8_t* voxels, uint32_t size_log2, const int32_t origin[3],
+                    const float* colours_rgb, uint64_t* node_count, uint32_t* root_index);
+int cbq_build_dense_device(cbq_context* ctx, const uint8_t* d_voxels, uint32_t size_log2, const int32_t origin[3],
+                           const float* colours_rgb, uint64_t* node_count, uint32_t* root_index);
+
 int cbq_set_colours(cbq_context* ctx, const float* colours_rgb);
 int cbq_get_subdags(cbq_context* ctx, cbq_subdag out[8]);
 
