@@ -49,7 +49,7 @@ def main():
         count, new_root = ctx.bake()
         times.append(time.perf_counter() - t0)
     reachable = ctx.counter("bake_reachable")
-    gpu_s = float(np.median(times[1:]))
+    gpu_s = float(np.median(times[1:] if len(times) > 1 else times))
     line = {"scene": "%s 2^%d + %d brush edits" % (args.scene, args.log2, args.edits), "nodes_in": int(len(nodes)), "reachable": int(reachable),
             "nodes_out": int(count), "gpu_bake_ms": gpu_s * 1e3, "gpu_bake_ms_all": [round(t * 1e3, 3) for t in times],
             "gpu_Mnodes_per_s": len(nodes) / gpu_s / 1e6}
