@@ -58,7 +58,7 @@ def pt_params(width, height, spp=1, bounces=1, variant=VARIANT_ONE_BOUNCE, inclu
 
 EXPORTS = [
     "cbq_create", "cbq_destroy", "cbq_last_error", "cbq_device_count", "cbq_synchronize",
-    "cbq_upload", "cbq_update", "cbq_bake", "cbq_build_dense", "cbq_build_dense_device", "cbq_set_colours", "cbq_get_subdags", "cbq_find_subdags",
+    "cbq_upload", "cbq_update", "cbq_bake", "cbq_build_dense", "cbq_build_dense_device", "cbq_fill_sphere", "cbq_set_root", "cbq_set_colours", "cbq_get_subdags", "cbq_find_subdags",
     "cbq_download_nodes", "cbq_node_count",
     "cbq_trace", "cbq_trace_device", "cbq_camera_from_pose", "cbq_primary_rays_device", "cbq_primary_rays_tiled_device", "cbq_random_rays_device",
     "cbq_raycast_frame_device",
@@ -95,6 +95,8 @@ def load_library():
     L.cbq_upload.argtypes = [vp, vp, u64, u32, vp]
     L.cbq_update.argtypes = [vp, vp, u64, u64, u32]
     L.cbq_bake.argtypes = [vp, C.POINTER(u64), C.POINTER(u32)]
+    L.cbq_fill_sphere.argtypes = [vp, f32, f32, f32, f32, C.c_uint8, C.POINTER(u32), C.POINTER(u64)]
+    L.cbq_set_root.argtypes = [vp, u32]
     L.cbq_build_dense.argtypes = [vp, vp, u32, C.POINTER(C.c_int32), vp, C.POINTER(u64), C.POINTER(u32)]
     L.cbq_build_dense_device.argtypes = [vp, vp, u32, C.POINTER(C.c_int32), vp, C.POINTER(u64), C.POINTER(u32)]
     L.cbq_set_colours.argtypes = [vp, vp]
@@ -360,6 +362,17 @@ class Context:
         root = C.c_uint32()
         _check(self.L.cbq_bake(self._h, C.byref(n), C.byref(root)))
         return int(n.value), int(root.value)
+
+    def fill_sphere(self, x, y, z, radius, material):
+        """checkpoint() + fillBrush(SphereBrush) (reference viewer.cpp:165-168) on the device copy; returns
+        (new_root, node_count). Earlier roots stay valid: set_root() is undo / redo."""
+        root = C.c_uint32()
+        n = C.c_uint64()
+        _check(self.L.cbq_fill_sphere(self._h, float(x), float(y), float(z), float(radius), int(material), C.byref(root), C.byref(n)))
+        return int(root.value), int(n.value)
+
+    def set_root(self, root):
+        _check(self.L.cbq_set_root(self._h, int(root)))
 
     def build_dense(self, voxels, origin=(0, 0, 0), colours=None, device_ptr=None, size_log2=None):
         """setVoxel for every voxel + bake (reference storage.cpp:388-438), on the device. voxels: uint8 array

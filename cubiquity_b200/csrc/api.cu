@@ -328,6 +328,40 @@ int bakeAndInstall(cbq_context* ctx, const uint32_t* dNodes, uint64_t n, uint32_
 	return writeHeaderAndSubdags(ctx);
 }
 
+// findSubDAGs on the device copy for `root` (read from *dRoot when dRoot != nullptr), result adopted by the context.
+int refreshSubdagsOnDevice(cbq_context* ctx, uint32_t root, const unsigned long long* dRoot, uint8_t* dScratch /* >= 512 bytes */, const char* what)
+{
+	cbq::SubDag* dSubdags = reinterpret_cast<cbq::SubDag*>(dScratch);
+	uint32_t* dStatus = reinterpret_cast<uint32_t*>(dScratch + 256);
+	struct { cbq::SubDag subdags[8]; uint32_t status; } host;
+	CBQ_CUDA(cudaMemsetAsync(dStatus, 0, 64, ctx->stream));
+	CBQ_CUDA(cbq::launchSubdags(ctx->nodesPtr(), (uint32_t)ctx->nodeCapacity, root, dRoot, dSubdags, dStatus, ctx->stream));
+	CBQ_CUDA(cudaMemcpyAsync(&host, dSubdags, sizeof(host.subdags) + sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->launches += 1;
+	ctx->bytesD2H += sizeof(host);
+	if (host.status != 0) return fail(CBQ_ERROR_CORRUPT_VOLUME, "%s: no valid sub-DAGs below the root", what);
+	std::memcpy(ctx->subdags, host.subdags, sizeof(host.subdags));
+	int maxH = 0;
+	for (int i = 0; i < 8; i++) if (ctx->subdags[i].node > 0) maxH = std::max(maxH, ctx->subdags[i].height);
+	ctx->maxSubDagHeight = maxH;
+	ctx->cfg.stackLevels = maxH + 1;
+	return CBQ_OK;
+}
+
+// More room for nodes, keeping what is there.
+int growVolume(cbq_context* ctx, uint64_t capacity)
+{
+	const size_t bytes = cbq::kNodeOffset + (size_t)capacity * 32;
+	uint8_t* bigger = nullptr;
+	CBQ_CUDA(cudaDeviceSynchronize());
+	CBQ_CUDA(poolAlloc(ctx, &bigger, bytes));
+	CBQ_CUDA(cudaMemcpyAsync(bigger, ctx->volume, cbq::kNodeOffset + (size_t)ctx->nodeCount * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+	poolFree(ctx, ctx->volume);
+	ctx->volume = bigger; ctx->volumeBytes = bytes; ctx->nodeCapacity = capacity;
+	return CBQ_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -543,6 +577,72 @@ int cbq_build_dense(cbq_context* ctx, const uint8_t* voxels, uint32_t size_log2,
 	rc = cbq_build_dense_device(ctx, d, size_log2, origin, colours_rgb, node_count, root_index);
 	poolFree(ctx, d);
 	return rc;
+}
+
+int cbq_fill_sphere(cbq_context* ctx, float x, float y, float z, float radius, uint8_t material, uint32_t* root_index, uint64_t* node_count)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "cbq_fill_sphere before cbq_upload");
+	if (!(radius >= 0.0f)) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad radius");
+	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	uint32_t listCapacity = 1u << 16;
+	for (int attempt = 0; attempt < 8; attempt++) {
+		if (ctx->nodeCapacity < ctx->nodeCount + 4096) { rc = growVolume(ctx, ctx->nodeCount + std::max<uint64_t>(ctx->nodeCount / 4, 1u << 16)); if (rc) return rc; }
+		const size_t listBytes = (size_t)listCapacity * 32;
+		uint8_t* work = nullptr;
+		CBQ_CUDA(poolAlloc(ctx, &work, listBytes + 1024));
+		unsigned int* dState = reinterpret_cast<unsigned int*>(work + listBytes);
+		unsigned int state[8] = { (unsigned int)ctx->nodeCount, 0, 0, 0, 0, 0, 0, 0 };
+		cudaError_t e = cudaMemsetAsync(dState, 0, cbq::fillSphereStateBytes(), ctx->stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(dState, state, sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream);
+		uint32_t* nodes = reinterpret_cast<uint32_t*>(ctx->volume + cbq::kNodeOffset);
+		const uint32_t capacity = (uint32_t)std::min<uint64_t>(ctx->nodeCapacity, 0xfffffff0ull);
+		if (e == cudaSuccess) e = cbq::launchFillSphere(nodes, capacity, ctx->root, x, y, z, radius, material, work, listCapacity, dState,
+			ctx->cfg.smCount, ctx->stream, &ctx->launches);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(state, dState, sizeof(state), cudaMemcpyDeviceToHost, ctx->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+		if (e != cudaSuccess) { poolFree(ctx, work); return fail(CBQ_ERROR_CUDA, "cbq_fill_sphere failed: %s", cudaGetErrorString(e)); }
+		ctx->bytesD2H += sizeof(state);
+		if (state[2] != 0) {
+			// Nothing that existed was written: forget the attempt, make room, start over from the same root.
+			poolFree(ctx, work);
+			if (state[2] & 2u) { if (listCapacity >= (1u << 25)) return fail(CBQ_ERROR_OUT_OF_MEMORY, "cbq_fill_sphere: the brush touches too many nodes"); listCapacity <<= 3; }
+			if (state[2] & 1u) {
+				if (ctx->nodeCapacity >= 0xfffffff0ull) return fail(CBQ_ERROR_OUT_OF_MEMORY, "cbq_fill_sphere: node indices are 32-bit");
+				rc = growVolume(ctx, std::min<uint64_t>(ctx->nodeCapacity * 2, 0xfffffff0ull)); if (rc) return rc;
+			}
+			continue;
+		}
+		const uint64_t oldCount = ctx->nodeCount;
+		const uint32_t oldRoot = ctx->root;
+		ctx->nodeCount = state[0];
+		ctx->root = state[4];
+		rc = refreshSubdagsOnDevice(ctx, ctx->root, nullptr, work, "cbq_fill_sphere");
+		poolFree(ctx, work);
+		if (rc) { ctx->nodeCount = oldCount; ctx->root = oldRoot; return rc; }
+		ctx->generation++;
+		if (root_index) *root_index = ctx->root;
+		if (node_count) *node_count = ctx->nodeCount;
+		return writeHeaderAndSubdags(ctx);
+	}
+	return fail(CBQ_ERROR_OUT_OF_MEMORY, "cbq_fill_sphere: could not make room for the edit");
+}
+
+int cbq_set_root(cbq_context* ctx, uint32_t root_index)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "cbq_set_root before cbq_upload");
+	if (root_index >= ctx->nodeCount) return fail(CBQ_ERROR_INVALID_ARGUMENT, "root %u is past the %llu nodes on the device", root_index, (unsigned long long)ctx->nodeCount);
+	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	uint8_t* work = nullptr;
+	CBQ_CUDA(poolAlloc(ctx, &work, 1024));
+	const uint32_t oldRoot = ctx->root;
+	ctx->root = root_index;
+	rc = refreshSubdagsOnDevice(ctx, root_index, nullptr, work, "cbq_set_root");
+	poolFree(ctx, work);
+	if (rc) { ctx->root = oldRoot; return rc; }
+	ctx->generation++;
+	return writeHeaderAndSubdags(ctx);
 }
 
 int cbq_set_colours(cbq_context* ctx, const float* colours_rgb)

@@ -129,4 +129,9 @@ uint64_t denseNodeCount(uint32_t sizeLog2);   // upper bound: what to allocate
 cudaError_t launchBuildDense(const uint8_t* voxels, uint32_t sizeLog2, const int32_t origin[3], uint32_t* nodes, uint32_t* root, uint64_t* nodeCount,
 	int smCount, cudaStream_t stream, uint64_t* launches);
 
+// Device-side sphere brush (edit_kernels.cu). Work-list entries are 32 bytes; state is fillSphereStateBytes() bytes.
+cudaError_t launchFillSphere(uint32_t* nodes, uint32_t capacity, uint32_t root, float x, float y, float z, float radius, uint32_t material,
+	void* itemList, uint32_t itemCapacity, unsigned int* state, int smCount, cudaStream_t stream, uint64_t* launches);
+size_t fillSphereStateBytes();
+
 } // namespace cbq

@@ -155,6 +155,17 @@ int cbq_build_dense(cbq_context* ctx, const uint8_t* voxels, uint32_t size_log2,
 int cbq_build_dense_device(cbq_context* ctx, const uint8_t* d_voxels, uint32_t size_log2, const int32_t origin[3],
                            const float* colours_rgb, uint64_t* node_count, uint32_t* root_index);
 
+/* The reference's runtime edit -- Volume::checkpoint() + fillBrush(volume, SphereBrush(centre, radius), material)
+ * (viewer.cpp:165-168; voxelization.cpp:825-915, voxelization.h:91-127) -- applied to the DEVICE copy: no host
+ * editor, no PCIe transfer of a dirty tail. Same voxels change as in the reference (same contains() arithmetic and
+ * box-overlap pruning); new nodes are appended copy-on-write, nothing that existed is written, so every earlier
+ * root stays valid: *root_index is the new root, and cbq_set_root switches between roots (undo / redo,
+ * storage.cpp:373-385). The appended tail is not word-for-word the reference's (breadth-first, copies made before
+ * it is known that something below changes); the volume and its canonical DAG after a bake are. */
+int cbq_fill_sphere(cbq_context* ctx, float x, float y, float z, float radius, uint8_t material,
+                    uint32_t* root_index, uint64_t* node_count);
+int cbq_set_root(cbq_context* ctx, uint32_t root_index);
+
 int cbq_set_colours(cbq_context* ctx, const float* colours_rgb);
 int cbq_get_subdags(cbq_context* ctx, cbq_subdag out[8]);
 

@@ -311,13 +311,15 @@ class RefVolume:
         return hits
 
 
-def dag_signature(nodes, root):
+def dag_signature(nodes, root, collapse=True):
     """Checker for bake parity: the canonical form of the DAG below `root`, independent of node order.
 
     Follows NodeStore::merge_node (reference storage.cpp:243-290): children first, a node whose eight merged
     children are one material IS that material, otherwise nodes are identified by content. Returns
     (signature of the root, number of distinct non-material nodes); two arrays describe the same volume with the
-    same sharing iff both values agree. Iterative post-order, hashlib digests as content ids."""
+    same sharing iff both values agree. Iterative post-order, hashlib digests as content ids.
+    collapse=False skips the material rule: the signature then identifies the UNFOLDED TREE exactly as stored (an
+    un-merged internal node with eight equal material children stays a node), which is what ray traversal sees."""
     import hashlib
     nodes = np.ascontiguousarray(nodes, dtype=np.uint32).reshape(-1, 8)
     sig = {}
@@ -341,7 +343,7 @@ def dag_signature(nodes, root):
                     stack.append((c, False))
             continue
         parts = [mat(c) if c < 256 else sig[c] for c in kids]
-        if parts[0][:1] == b"m" and all(p == parts[0] for p in parts):
+        if collapse and parts[0][:1] == b"m" and all(p == parts[0] for p in parts):
             sig[i] = parts[0]
         else:
             d = hashlib.blake2b(b"".join(parts), digest_size=16).digest()
