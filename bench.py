@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--scene", default=None, choices=[None, "terrain", "soup", "city", "sphere_noise"])
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--device-edits", action="store_true", help="pathtrace --edits: apply the brush on every GPU with cbq_fill_sphere instead of on the host + delta upload/broadcast")
     ap.add_argument("--edits", action="store_true", help="pathtrace: carve a radius-30 sphere and delta re-upload before every frame")
     return ap.parse_args()
 
@@ -236,8 +237,9 @@ def pathtrace_workload(args):
     # Runtime edits (config 5): rank 0 owns the editable copy (csrc/edit.cpp restates the reference's checkpoint +
     # sphere brush); every frame it carves a radius-30 sphere, ships the dirty tail to the other ranks, and every rank
     # applies it with cbq_update -- the delta, not the DAG, crosses PCIe and NVLink.
-    editable = api.Editable(nodes, root) if (args.edits and rank == 0) else None
-    replica = np.array(nodes, dtype=np.uint32, copy=True) if (args.edits and rank != 0) else None
+    host_edits = args.edits and not args.device_edits
+    editable = api.Editable(nodes, root) if (host_edits and rank == 0) else None
+    replica = np.array(nodes, dtype=np.uint32, copy=True) if (host_edits and rank != 0) else None
     synced = len(nodes)
     edit_stats = {"tail_bytes": [], "edit_ms": [], "sync_ms": []}
 
@@ -247,6 +249,15 @@ def pathtrace_workload(args):
             return
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        if args.device_edits:
+            # Every rank replays the same stroke on its own replica (cbq_fill_sphere): nothing crosses PCIe or NVLink.
+            rng = np.random.default_rng(frame)
+            before = ctx.node_count()
+            ctx.fill_sphere(float(rng.uniform(-1200, 1200)), float(rng.uniform(-1200, 1200)), float(rng.uniform(0, 400)), 30.0, 0)
+            edit_stats["tail_bytes"].append((ctx.node_count() - before) * 32)
+            edit_stats["edit_ms"].append(1e3 * (time.perf_counter() - t0))
+            edit_stats["sync_ms"].append(0.0)
+            return
         if rank == 0:
             editable.checkpoint()
             rng = np.random.default_rng(frame)
@@ -323,7 +334,7 @@ def pathtrace_workload(args):
         line = {"metric": "%dp path-traced spp/s" % H, "value": value, "unit": "spp/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32+i32", "data": "synthetic",
-                "config": {"workload": "path tracing %dx%d, %d spp, %d bounces (traceSingleRayRecurse), sun+sky+noise, maxFootprint 0.0035, procedural %s 2^%d SVDAG%s" % (W, H, args.spp, args.bounces, kind, log2, ", radius-30 sphere edit + delta re-upload before every frame" if args.edits else ""),
+                "config": {"workload": "path tracing %dx%d, %d spp, %d bounces (traceSingleRayRecurse), sun+sky+noise, maxFootprint 0.0035, procedural %s 2^%d SVDAG%s" % (W, H, args.spp, args.bounces, kind, log2, (", radius-30 sphere edit on the device before every frame" if args.device_edits else ", radius-30 sphere edit + delta re-upload before every frame") if args.edits else ""),
                            "dag_mb": round(len(nodes) * 32 / 1e6, 1), "scene_build_s": round(t_build, 2),
                            "nodes": int(len(nodes)), "l2": "flushed between steps", "options": args.option,
                            "parallelism": "replicated DAG, 64-row tile bands round-robin over %d GPU(s) (one render call per GPU), one NCCL reduce per frame" % world},

@@ -70,124 +70,165 @@ __device__ __forceinline__ uint64_t hashNode(const NodeWords& n)
 	return h;
 }
 
-__global__ void bakeInit(uint32_t n, uint32_t root, uint8_t* mark, uint32_t* newIndex, uint32_t* rep, uint32_t* flags, unsigned long long* frontier)
+// The passes below walk the array in INDEX order, 256 consecutive nodes (one chunk) per block iteration, because
+// that is where the locality is: children sit near their siblings, so the 4-byte gathers of a chunk share
+// sectors (a version driven by compacted work lists in breadth-first order was 1.7x SLOWER: 9.3 GB instead of
+// 4.8 GB of DRAM reads in the resolve passes, profiles/r01_analysis.md). What makes the <= 33 passes cheap is a
+// per-chunk activity word: a block fetches the words of its next 256 chunks with one coalesced load and only
+// touches chunks that still have work.
+constexpr uint32_t kChunk = 256;
+
+// Calls body(chunk, word) for every chunk of this block whose activity word is non-zero. Block-uniform control flow.
+template <typename Word, typename F>
+__device__ __forceinline__ void forActiveChunks(const Word* activity, uint32_t chunks, F body)
 {
-	if (blockIdx.x == 0 && threadIdx.x == 0) frontier[1] = 1;   // the root is the frontier of depth 1
+	__shared__ uint32_t activeChunk[kChunk], activeWord[kChunk];
+	__shared__ unsigned int activeCount;
+	for (uint32_t first = blockIdx.x; first < chunks; first += gridDim.x * kChunk) {
+		const uint32_t mine = first + threadIdx.x * gridDim.x;
+		__syncthreads();                                  // the previous batch is done with the lists
+		if (threadIdx.x == 0) activeCount = 0;
+		__syncthreads();
+		const uint32_t word = mine < chunks ? (uint32_t)activity[mine] : 0u;
+		if (word != 0) {                                  // order within the batch does not matter
+			const unsigned int at = atomicAdd(&activeCount, 1u);
+			activeChunk[at] = mine;
+			activeWord[at] = word;
+		}
+		__syncthreads();
+		const unsigned int count = activeCount;
+		for (unsigned int k = 0; k < count; k++) body(activeChunk[k], activeWord[k]);
+	}
+}
+
+__global__ void bakeInit(uint32_t n, uint32_t root, uint8_t* mark, uint32_t* newIndex, uint32_t* rep, uint32_t* flags,
+	uint8_t* frontierA, uint8_t* frontierB, uint32_t* chunkRemaining, uint32_t* chunkPending, uint32_t chunks)
+{
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		mark[i] = (i == root) ? 1 : 0;
 		newIndex[i] = i < kMaterialCount ? i : kUnresolved;
 		rep[i] = 0xffffffffu;
 		flags[i] = 0;
-	}
-}
-
-// Pass `depth` (1-based): expand the nodes first reached at that depth. frontier[d] != 0 iff something was first reached at depth d.
-__global__ void bakeReach(const uint32_t* __restrict__ nodes, uint32_t n, uint32_t depth, uint8_t* mark, unsigned long long* frontier)
-{
-	if (frontier[depth] == 0) return;            // nothing was reached at this depth: the walk is over
-	bool found = false;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		if (mark[i] != depth) continue;
-		const NodeWords node = loadNode(nodes, i);
-#pragma unroll
-		for (int k = 0; k < 8; k++) {
-			const uint32_t c = node.w[k];
-			if (c < kMaterialCount || c >= n) continue;
-			// Parents racing for the same child all store the same byte.
-			if (mark[c] == 0) { mark[c] = (uint8_t)(depth + 1u); found = true; }
+		if (i < chunks) {
+			frontierA[i] = 0;
+			frontierB[i] = (i == root / kChunk) ? 1 : 0;     // depth 1 (odd) reads B: the root is its frontier
+			chunkRemaining[i] = 0;
+			chunkPending[i] = 0;
 		}
 	}
-	if (__any_sync(0xffffffffu, found) && (threadIdx.x & 31) == 0) frontier[depth + 1] = 1;
 }
 
-// counters[0] = results[3] = non-material nodes the root reaches.
-__global__ void bakeCountReached(uint32_t n, const uint8_t* __restrict__ mark, unsigned long long* counters, unsigned long long* results)
+// Pass `depth` (1-based): expand the nodes first reached at that depth; `cur` flags the chunks that hold some.
+__global__ void bakeReach(const uint32_t* __restrict__ nodes, uint32_t n, uint32_t depth, uint8_t* mark, uint8_t* cur, uint8_t* next, uint32_t chunks)
 {
-	unsigned long long c = 0;
-	for (uint32_t i = kMaterialCount + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += mark[i] != 0;
-	for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
-	if ((threadIdx.x & 31) == 0 && c) { atomicAdd(&counters[0], c); atomicAdd(&results[3], c); }
+	forActiveChunks(cur, chunks, [&](uint32_t chunk, uint32_t) {
+		const uint32_t i = chunk * kChunk + threadIdx.x;
+		if (i < n && mark[i] == depth) {
+			const NodeWords node = loadNode(nodes, i);
+#pragma unroll
+			for (int k = 0; k < 8; k++) {
+				const uint32_t c = node.w[k];
+				if (c < kMaterialCount || c >= n) continue;
+				// Parents racing for the same child all store the same bytes.
+				if (mark[c] == 0) { mark[c] = (uint8_t)(depth + 1u); next[c / kChunk] = 1; }
+			}
+		}
+		if (threadIdx.x == 0) cur[chunk] = 0;             // clean for its next turn as `next`
+	});
+}
+
+// chunkRemaining[chunk] = non-material nodes of the chunk the root reaches; counters[0] = results[3] = their total.
+__global__ void bakeCountReached(uint32_t n, const uint8_t* __restrict__ mark, uint32_t* chunkRemaining, uint32_t chunks,
+	unsigned long long* counters, unsigned long long* results)
+{
+	for (uint32_t chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
+		const uint32_t i = chunk * kChunk + threadIdx.x;
+		const int c = __syncthreads_count(i >= kMaterialCount && i < n && mark[i] != 0);
+		if (threadIdx.x == 0 && c) {
+			chunkRemaining[chunk] = (uint32_t)c;
+			atomicAdd(&counters[0], (unsigned long long)c);
+			atomicAdd(&results[3], (unsigned long long)c);
+		}
+	}
 }
 
 // A reachable node whose children all have final ids becomes either a material (all eight the same material) or
 // a pending hash-cons candidate with its canonical content written out.
 __global__ void bakeResolve(const uint32_t* __restrict__ nodes, uint32_t n, const uint8_t* __restrict__ mark,
-	uint32_t* newIndex, uint32_t* canon, unsigned long long* counters)
+	uint32_t* newIndex, uint32_t* canon, uint32_t* chunkRemaining, uint32_t* chunkPending, uint32_t chunks, unsigned long long* counters)
 {
-	if (counters[0] == 0) return;                // counters[0] = reachable nodes still without an id
-	unsigned long long collapsed = 0;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		if (mark[i] == 0 || newIndex[i] != kUnresolved) continue;
-		NodeWords node = loadNode(nodes, i);
-		bool ready = true;
+	forActiveChunks(chunkRemaining, chunks, [&](uint32_t chunk, uint32_t remaining) {
+		const uint32_t i = chunk * kChunk + threadIdx.x;
+		bool collapsed = false, pending = false;
+		if (i < n && mark[i] != 0 && newIndex[i] == kUnresolved) {
+			NodeWords node = loadNode(nodes, i);
+			bool ready = true;
 #pragma unroll
-		for (int k = 0; k < 8; k++) {
-			uint32_t c = node.w[k];
-			if (c >= kMaterialCount) c = (c < n) ? __ldcg(&newIndex[c]) : kUnresolved;
-			ready = ready && (c < kPending);
-			node.w[k] = c;
-		}
-		if (!ready) continue;
-		bool uniform = node.w[0] < kMaterialCount;
+			for (int k = 0; k < 8; k++) {
+				uint32_t c = node.w[k];
+				if (c >= kMaterialCount) c = (c < n) ? __ldcg(&newIndex[c]) : kUnresolved;
+				ready = ready && (c < kPending);
+				node.w[k] = c;
+			}
+			if (ready) {
+				bool uniform = node.w[0] < kMaterialCount;
 #pragma unroll
-		for (int k = 1; k < 8; k++) uniform = uniform && (node.w[k] == node.w[0]);
-		if (uniform) {
-			newIndex[i] = node.w[0];             // the whole cube is one material (storage.cpp:261-263)
-			collapsed++;
-		} else {
-			storeNode(canon, i, node);
-			newIndex[i] = kPending;
+				for (int k = 1; k < 8; k++) uniform = uniform && (node.w[k] == node.w[0]);
+				if (uniform) {
+					newIndex[i] = node.w[0];         // the whole cube is one material (storage.cpp:261-263)
+					collapsed = true;
+				} else {
+					storeNode(canon, i, node);
+					newIndex[i] = kPending;
+					pending = true;
+				}
+			}
 		}
-	}
-	for (int o = 16; o > 0; o >>= 1) collapsed += __shfl_down_sync(0xffffffffu, collapsed, o);
-	if ((threadIdx.x & 31) == 0 && collapsed) atomicAdd(&counters[2], collapsed);   // folded into counters[0] by bakeInsert
+		const int nCollapsed = __syncthreads_count(collapsed);
+		const int nPending = __syncthreads_count(pending);
+		if (threadIdx.x == 0) {
+			if (nCollapsed) { chunkRemaining[chunk] = remaining - (uint32_t)nCollapsed; atomicAdd(&counters[0], ~(unsigned long long)nCollapsed + 1ull); }
+			if (nPending) chunkPending[chunk] = (uint32_t)nPending;
+		}
+	});
 }
 
 // Hash-cons the pending nodes. table[slot] = original index of the node that owns the slot.
 __global__ void bakeInsert(uint32_t n, uint32_t* newIndex, const uint32_t* __restrict__ canon, uint32_t* table, uint32_t tableMask,
-	uint32_t* rep, unsigned long long* counters)
+	uint32_t* rep, uint32_t* chunkRemaining, uint32_t* chunkPending, uint32_t chunks, unsigned long long* counters)
 {
-	if (counters[0] == 0) return;
-	unsigned long long resolved = 0, distinct = 0;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		if (newIndex[i] != kPending) continue;
-		const NodeWords key = loadNode(canon, i);
-		uint32_t slot = (uint32_t)hashNode(key) & tableMask;
-		uint32_t owner;
-		for (;;) {
-			owner = table[slot];
-			if (owner == kEmptySlot) {
-				owner = atomicCAS(&table[slot], kEmptySlot, i);
-				if (owner == kEmptySlot) { owner = i; distinct++; break; }
-			}
-			// canon[owner] was written by bakeResolve, i.e. before this kernel started: plain loads see it.
-			const NodeWords other = loadNode(canon, owner);
-			bool same = true;
+	forActiveChunks(chunkPending, chunks, [&](uint32_t chunk, uint32_t pending) {
+		const uint32_t i = chunk * kChunk + threadIdx.x;
+		bool won = false;
+		if (i < n && newIndex[i] == kPending) {
+			const NodeWords key = loadNode(canon, i);
+			uint32_t slot = (uint32_t)hashNode(key) & tableMask;
+			uint32_t owner;
+			for (;;) {
+				owner = table[slot];
+				if (owner == kEmptySlot) {
+					owner = atomicCAS(&table[slot], kEmptySlot, i);
+					if (owner == kEmptySlot) { owner = i; won = true; break; }
+				}
+				// canon[owner] was written by bakeResolve, i.e. before this kernel started: plain loads see it.
+				const NodeWords other = loadNode(canon, owner);
+				bool same = true;
 #pragma unroll
-			for (int k = 0; k < 8; k++) same = same && (other.w[k] == key.w[k]);
-			if (same) break;
-			slot = (slot + 1u) & tableMask;
+				for (int k = 0; k < 8; k++) same = same && (other.w[k] == key.w[k]);
+				if (same) break;
+				slot = (slot + 1u) & tableMask;
+			}
+			newIndex[i] = owner;
+			atomicMin(&rep[owner], i);
 		}
-		newIndex[i] = owner;
-		atomicMin(&rep[owner], i);
-		resolved++;
-	}
-	for (int o = 16; o > 0; o >>= 1) {
-		resolved += __shfl_down_sync(0xffffffffu, resolved, o);
-		distinct += __shfl_down_sync(0xffffffffu, distinct, o);
-	}
-	if ((threadIdx.x & 31) == 0) {
-		if (resolved) atomicAdd(&counters[3], resolved);
-		if (distinct) atomicAdd(&counters[1], distinct);
-	}
-}
-
-// Between passes: remaining -= collapsed + resolved of the pass just finished (single thread, keeps the early-outs exact).
-__global__ void bakeSettle(unsigned long long* counters)
-{
-	counters[0] -= counters[2] + counters[3];
-	counters[2] = 0;
-	counters[3] = 0;
+		const int distinct = __syncthreads_count(won);
+		if (threadIdx.x == 0) {
+			chunkPending[chunk] = 0;
+			chunkRemaining[chunk] -= pending;
+			atomicAdd(&counters[0], ~(unsigned long long)pending + 1ull);
+			if (distinct) atomicAdd(&counters[1], (unsigned long long)distinct);
+		}
+	});
 }
 
 __global__ void bakeFlag(uint32_t n, const uint8_t* __restrict__ mark, const uint32_t* __restrict__ newIndex, const uint32_t* __restrict__ rep, uint32_t* flags)
@@ -350,6 +391,7 @@ int gridFor(uint64_t n, int smCount)
 // The scratch buffer, carved into 256-byte aligned sections.
 struct BakeScratch {
 	uint32_t* canon; uint32_t* newIndex; uint32_t* rep; uint32_t* flags; uint8_t* mark; uint32_t* table; uint32_t* scan;
+	uint8_t* frontierA; uint8_t* frontierB; uint32_t* chunkRemaining; uint32_t* chunkPending;
 	unsigned long long* counters; uint32_t* rootOut;
 	size_t bytes;
 };
@@ -366,6 +408,11 @@ static BakeScratch carve(uint8_t* base, uint64_t n, uint64_t tableSlots)
 	s.rep = reinterpret_cast<uint32_t*>(take(n * 4));
 	s.flags = reinterpret_cast<uint32_t*>(take(n * 4));
 	s.mark = take(n);
+	const uint64_t chunks = (n + kChunk - 1) / kChunk;
+	s.frontierA = take(chunks);
+	s.frontierB = take(chunks);
+	s.chunkRemaining = reinterpret_cast<uint32_t*>(take(chunks * 4));
+	s.chunkPending = reinterpret_cast<uint32_t*>(take(chunks * 4));
 	s.table = reinterpret_cast<uint32_t*>(take(tableSlots * 4));
 	s.scan = reinterpret_cast<uint32_t*>(take((scanWords + 8) * 4));
 	s.counters = reinterpret_cast<unsigned long long*>(take(64 * 8));   // [0..3] counters, [8 + d] frontier of depth d
@@ -512,16 +559,19 @@ cudaError_t launchBake(const uint32_t* nodes, uint64_t n64, uint32_t root, uint8
 	cudaError_t e;
 	if ((e = cudaMemsetAsync(counters, 0, 64 * 8, stream)) != cudaSuccess) return e;
 	if ((e = cudaMemsetAsync(table, 0xff, tableSlots * 4, stream)) != cudaSuccess) return e;
-	unsigned long long* frontier = counters + 8;
-	bakeInit<<<grid, 256, 0, stream>>>(n, root, mark, newIndex, rep, flags, frontier); count++;
-	for (uint32_t depth = 1; depth <= 33; depth++) { bakeReach<<<grid, 256, 0, stream>>>(nodes, n, depth, mark, frontier); count++; }
+	const uint32_t chunks = (uint32_t)((n64 + kChunk - 1) / kChunk);
+	bakeInit<<<grid, 256, 0, stream>>>(n, root, mark, newIndex, rep, flags, sc.frontierA, sc.frontierB, sc.chunkRemaining, sc.chunkPending, chunks); count++;
+	for (uint32_t depth = 1; depth <= 33; depth++) {
+		uint8_t* cur = (depth & 1u) ? sc.frontierB : sc.frontierA;
+		uint8_t* next = (depth & 1u) ? sc.frontierA : sc.frontierB;
+		bakeReach<<<grid, 256, 0, stream>>>(nodes, n, depth, mark, cur, next, chunks); count++;
+	}
 	if ((e = cudaMemsetAsync(results, 0, 4 * sizeof(unsigned long long), stream)) != cudaSuccess) return e;
-	bakeCountReached<<<grid, 256, 0, stream>>>(n, mark, counters, results); count++;
+	bakeCountReached<<<grid, 256, 0, stream>>>(n, mark, sc.chunkRemaining, chunks, counters, results); count++;
 	for (int pass = 0; pass < 33; pass++) {
-		bakeResolve<<<grid, 256, 0, stream>>>(nodes, n, mark, newIndex, canon, counters);
-		bakeInsert<<<grid, 256, 0, stream>>>(n, newIndex, canon, table, (uint32_t)(tableSlots - 1), rep, counters);
-		bakeSettle<<<1, 1, 0, stream>>>(counters);
-		count += 3;
+		bakeResolve<<<grid, 256, 0, stream>>>(nodes, n, mark, newIndex, canon, sc.chunkRemaining, sc.chunkPending, chunks, counters);
+		bakeInsert<<<grid, 256, 0, stream>>>(n, newIndex, canon, table, (uint32_t)(tableSlots - 1), rep, sc.chunkRemaining, sc.chunkPending, chunks, counters);
+		count += 2;
 	}
 	bakeFlag<<<grid, 256, 0, stream>>>(n, mark, newIndex, rep, flags); count++;
 	if ((e = exclusiveScan(flags, n64, scanScratch, stream, &count)) != cudaSuccess) return e;

@@ -29,6 +29,10 @@ bake) echo "== bake bench"
 build) echo "== build bench"; timeout 900 python scripts/build_bench.py --out $OUT/build.jsonl 2>&1 | tail -8;;
 bakelaunch) echo "== ncu launch list of the bake kernels (time + DRAM bytes)"
   timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"bake|scan|subdag|dense" --csv --log-file $OUT/bake_launches.csv python scripts/bake_bench.py --scene soup --log2 14 --edits 50 --reps 0 --no-reference > $OUT/ncu_bake.log 2>&1; grep -c . $OUT/bake_launches.csv;;
+edit) echo "== edit bench"
+  timeout 600 python scripts/edit_bench.py --scene city --log2 16 --out $OUT/edit.jsonl 2>&1 | tail -3
+  timeout 600 python scripts/edit_bench.py --scene terrain --log2 12 --out $OUT/edit.jsonl 2>&1 | tail -3
+  timeout 900 python bench.py --workload pathtrace --scene city --scene-log2 16 --width 3840 --height 2160 --spp 16 --edits --device-edits --steps 3 --warmup 3 2> $OUT/config5_device_edits.err | tee $OUT/config5_device_edits.json | cut -c1-900;;
 sweep) echo "== sweep"; timeout 900 python scripts/sweep.py primary 2>&1 | tee $OUT/sweep_primary.jsonl;;
 sweeprandom) echo "== sweep random"; timeout 900 python scripts/sweep.py random 2>&1 | tee $OUT/sweep_random.jsonl;;
 esac
