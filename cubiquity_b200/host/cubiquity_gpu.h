@@ -73,6 +73,17 @@ public:
 		return cbq_update(mCtx, static_cast<const uint32_t*>(nodes), sharedNodesEndAtLastSync, nodeCount, root) == CBQ_OK;
 	}
 
+	// checkpoint() + fillBrush(volume, SphereBrush(centre, radius), material) (viewer.cpp:165-168) applied to the
+	// device copy; root receives the new root (keep the old ones: setRoot(old) is undo, storage.cpp:373-385).
+	bool fillSphere(float x, float y, float z, float radius, uint8_t material, uint32_t& root)
+	{
+		uint64_t count = 0;
+		const bool ok = cbq_fill_sphere(mCtx, x, y, z, radius, material, &root, &count) == CBQ_OK;
+		if (ok) mSynced = count;
+		return ok;
+	}
+	bool setRoot(uint32_t root) { return cbq_set_root(mCtx, root) == CBQ_OK; }
+
 	// Volume::bake() (storage.cpp:388-395) on the device copy. On success the device holds the merged DAG;
 	// nodeCount/root describe it and download() reads it back, e.g. into a fresh Volume via the .dag layout.
 	bool bake(uint64_t& nodeCount, uint32_t& root)
