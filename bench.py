@@ -472,6 +472,21 @@ def main():
     torch.cuda.synchronize()
     warm_ms = e0.elapsed_time(e1) / args.steps
 
+    # the same steps with the cost-feedback ticket order switched off (every launch deals tickets in buffer order)
+    order_off_ms = None
+    if args.workload == "primary" and ctx.get_option("adaptive_order"):
+        ctx.set_option("adaptive_order", 0)
+        off = []
+        for _ in range(min(args.steps, 10)):
+            if not args.no_flush:
+                flush.zero_()
+            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); step(); b2.record()
+            torch.cuda.synchronize()
+            off.append(a.elapsed_time(b2))
+        order_off_ms = float(np.mean(off))
+        ctx.set_option("adaptive_order", 1)
+
     # ---- secondary metric of BASELINE.json: 1080p path-traced samples per second (spp/s) ------------
     pt = None
     if args.workload == "primary":
@@ -582,6 +597,9 @@ def main():
         "extra": {"warm_l2_ms_per_step": warm_ms, "warm_l2_value": world * n_rays / (warm_ms * 1e-3) / 1e9,
                   "step_ms_min": float(np.min(step_ms)), "step_ms_max": float(np.max(step_ms)), "timed_wall_s": wall,
                   "scene_build_s": build_s, "parity_vs_oracle_sample": parity, "e2e_equals_device_path": bool(same),
+                  "ticket_order": "cost feedback: from the 2nd launch over the same ray buffer the 32-ray tickets are dealt longest first (adaptive_order=1; one extra 1-block sort kernel per step, inside the timed region)" if order_off_ms is not None else "buffer order",
+                  "adaptive_order_off_ms_per_step": order_off_ms,
+                  "adaptive_order_off_value": (world * n_rays / (order_off_ms * 1e-3) / 1e9) if order_off_ms else None,
                   "pathtrace": pt},
     }
     print(json.dumps(line), flush=True)

@@ -138,6 +138,19 @@ struct cbq_context {
 	cbq::WavefrontBuffers wavefront;
 	int renderMode = 0;   // 0 wavefront (per-bounce kernels), 1 persistent megakernel
 
+	// Cost feedback for coherent batches (refill threshold 32): the kernel records how long each 32-ray ticket
+	// took; the next launch over the same batch (same ray buffer, size and stream) deals them longest first.
+	int adaptiveOrder = 1;
+	uint32_t* ticketCost = nullptr;
+	uint32_t* ticketHist = nullptr;
+	uint32_t* ticketOrder[2] = { nullptr, nullptr };
+	uint64_t ticketCapacity = 0;
+	int orderWhich = 0;
+	int orderAge = 0;                 // launches since the order was last rebuilt from the recorded costs
+	uint64_t orderTickets = 0;
+	const void* orderRays = nullptr;
+	cudaStream_t orderStream = nullptr;
+
 	// Counters
 	uint64_t launches = 0, raysTraced = 0, bytesH2D = 0, bytesD2H = 0;
 	uint64_t bakeReachable = 0;   // nodes the root reached in the last cbq_bake, before merging
@@ -240,6 +253,42 @@ int ensureStaging(cbq_context* ctx)
 	return CBQ_OK;
 }
 
+// Cost-feedback scheduling: fills a.ticketOrder / a.ticketCost when this launch qualifies. Returns true if the
+// launch must be followed by orderAfterTrace().
+bool orderBeforeTrace(cbq_context* ctx, cbq::TraceArgs& a, const cbq::LaunchConfig& cfg, cudaStream_t stream)
+{
+	const uint64_t tickets = (a.count + 31) / 32;
+	const uint64_t warps = (uint64_t)cfg.smCount * cfg.blocksPerSm * (cfg.blockThreads / 32);
+	// Worth it only when a warp serves a handful of tickets (a tail exists) and one block can sort them.
+	if (!ctx->adaptiveOrder || !a.rays || a.countPtr || cfg.kernel != 0 || cfg.refillThreshold < 32 || tickets < 2 * warps || tickets > (1u << 18)) return false;
+	if (tickets > ctx->ticketCapacity) {
+		if (cudaDeviceSynchronize() != cudaSuccess) return false;
+		cudaFree(ctx->ticketCost); cudaFree(ctx->ticketHist); cudaFree(ctx->ticketOrder[0]); cudaFree(ctx->ticketOrder[1]);
+		ctx->ticketCost = ctx->ticketHist = ctx->ticketOrder[0] = ctx->ticketOrder[1] = nullptr;
+		ctx->ticketCapacity = 0; ctx->orderTickets = 0;
+		if (cudaMalloc(&ctx->ticketCost, tickets * 4) != cudaSuccess || cudaMalloc(&ctx->ticketOrder[0], tickets * 4) != cudaSuccess ||
+			cudaMalloc(&ctx->ticketOrder[1], tickets * 4) != cudaSuccess || cudaMalloc(&ctx->ticketHist, ((tickets + 1023) / 1024) * 256 * 4) != cudaSuccess) { cudaGetLastError(); return false; }
+		ctx->ticketCapacity = tickets;
+	}
+	if (ctx->orderTickets == tickets && ctx->orderRays == a.rays && ctx->orderStream == stream) a.ticketOrder = ctx->ticketOrder[ctx->orderWhich];
+	a.ticketCost = ctx->ticketCost;
+	return true;
+}
+
+int orderAfterTrace(cbq_context* ctx, const cbq::TraceArgs& a, cudaStream_t stream)
+{
+	const uint64_t tickets = (a.count + 31) / 32;
+	// Costs drift slowly from frame to frame: rebuild the order on the first repeat and then every 4th launch.
+	const bool sameBatch = ctx->orderTickets == tickets && ctx->orderRays == a.rays && ctx->orderStream == stream;
+	if (sameBatch && a.ticketOrder && ++ctx->orderAge < 4) return CBQ_OK;
+	ctx->orderAge = 0;
+	const int next = ctx->orderWhich ^ 1;
+	CBQ_CUDA(cbq::launchOrderTickets(ctx->ticketCost, (uint32_t)tickets, ctx->ticketHist, ctx->ticketOrder[next], stream));
+	ctx->orderWhich = next; ctx->orderTickets = tickets; ctx->orderRays = a.rays; ctx->orderStream = stream;
+	ctx->launches += 2;
+	return CBQ_OK;
+}
+
 int traceDevice(cbq_context* ctx, const cbq::Ray* dRays, uint64_t n, uint32_t flags, float maxFootprint,
 	cbq::Hit* dHits, cudaStream_t stream, const cbq_camera* cam, uint32_t width, uint32_t height)
 {
@@ -256,9 +305,11 @@ int traceDevice(cbq_context* ctx, const cbq::Ray* dRays, uint64_t n, uint32_t fl
 	applyL2Window(ctx, stream);
 	cbq::LaunchConfig cfg = ctx->cfg;
 	if (cam) cfg.refillThreshold = 32;   // tile-ordered primary rays are coherent by construction: no mid-flight refill
+	const bool feedback = orderBeforeTrace(ctx, a, cfg, stream);
 	CBQ_CUDA(cbq::launchTrace(a, (flags & CBQ_TRACE_SURFACE) != 0, cfg, stream));
 	ctx->launches++;
 	ctx->raysTraced += n;
+	if (feedback) return orderAfterTrace(ctx, a, stream);
 	return CBQ_OK;
 }
 
@@ -434,6 +485,7 @@ void cbq_destroy(cbq_context* ctx)
 	}
 	cudaFree(ctx->stageAccum);
 	cudaFree(ctx->frameRays);
+	cudaFree(ctx->ticketCost); cudaFree(ctx->ticketHist); cudaFree(ctx->ticketOrder[0]); cudaFree(ctx->ticketOrder[1]);
 	cbq::wavefrontRelease(ctx->wavefront);
 	cudaFree(ctx->queues);
 	poolFree(ctx, ctx->volume);
@@ -816,9 +868,11 @@ int cbq_raycast_frame_device(cbq_context* ctx, const cbq_camera* cam, uint32_t w
 		cbq::LaunchConfig cfg = ctx->cfg;
 		cfg.refillThreshold = 32;
 		cfg.kernel = 0;
+		const bool feedback = orderBeforeTrace(ctx, a, cfg, s);
 		CBQ_CUDA(cbq::launchTrace(a, (flags & CBQ_TRACE_SURFACE) != 0, cfg, s));
 		ctx->launches++;
 		ctx->raysTraced += n;
+		if (feedback) return orderAfterTrace(ctx, a, s);
 		return CBQ_OK;
 	}
 	return traceDevice(ctx, nullptr, (uint64_t)width * height, flags, max_footprint, reinterpret_cast<cbq::Hit*>(d_hits), s, cam, width, height);
@@ -932,6 +986,9 @@ int cbq_set_option(cbq_context* ctx, const char* key, int64_t value)
 	} else if (k == "render_mode") {
 		if (value < 0 || value > 1) return fail(CBQ_ERROR_INVALID_ARGUMENT, "render_mode must be 0 (wavefront) or 1 (megakernel)");
 		ctx->renderMode = (int)value;
+	} else if (k == "adaptive_order") {
+		ctx->adaptiveOrder = value ? 1 : 0;
+		ctx->orderTickets = 0;         // forget what was learnt
 	} else if (k == "l2_persist") {
 		ctx->l2Persist = value ? 1 : 0;
 		ctx->windowGeneration = ~0ull; // re-apply on next launch
@@ -951,6 +1008,7 @@ int cbq_get_option(cbq_context* ctx, const char* key, int64_t* value)
 	else if (k == "kernel") *value = ctx->cfg.kernel;
 	else if (k == "refill_quantum") *value = ctx->cfg.refillQuantum;
 	else if (k == "l2_persist") *value = ctx->l2Persist;
+	else if (k == "adaptive_order") *value = ctx->adaptiveOrder;
 	else if (k == "render_mode") *value = ctx->renderMode;
 	else if (k == "sample_group") *value = ctx->cfg.sampleGroup;
 	else if (k == "sm_count") *value = ctx->cfg.smCount;

@@ -76,9 +76,13 @@ struct TraceArgs {
 	uint32_t countScale;
 	uint8_t* flags;
 	uint32_t untileWidth;            // != 0: rays are in 8x4-tile order of an image this wide; write hits row-major
+	// optional cost feedback (refillThreshold == 32 only): deal the 32-ray tickets in this order / record their cost
+	const uint32_t* ticketOrder;     // permutation of [0, ceil(count / 32)), or nullptr
+	uint32_t* ticketCost;            // [ceil(count / 32)], or nullptr
 };
 
 cudaError_t launchTrace(const TraceArgs& a, bool surface, const LaunchConfig& cfg, cudaStream_t stream);
+cudaError_t launchOrderTickets(const uint32_t* cost, uint32_t tickets, uint32_t* hist /* ceil(tickets / 1024) x 256 words */, uint32_t* order, cudaStream_t stream);
 cudaError_t launchPrimaryRays(const cbq_camera& cam, uint32_t width, uint32_t height, Ray* rays, cudaStream_t stream, int tiled = 0, uint32_t* pixelOf = nullptr);
 cudaError_t launchRandomRays(uint64_t seed, const float lower[3], const float upper[3], uint64_t n, Ray* rays, cudaStream_t stream);
 

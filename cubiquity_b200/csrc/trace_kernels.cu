@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(256, CBQ_TRACE_MIN_BLOCKS)
 tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict__ subdagsGlobal, Source source,
 	Sink sink, const uint64_t hostCount, const unsigned long long* __restrict__ countPtr, uint32_t countScale,
 	float maxFootprint, int refillThreshold, int refillQuantum,
-	unsigned long long* __restrict__ queue, unsigned long long* __restrict__ abandoned)
+	unsigned long long* __restrict__ queue, unsigned long long* __restrict__ abandoned,
+	const uint32_t* __restrict__ ticketOrder, uint32_t* __restrict__ ticketCost)
 {
 	// The batch size may live on the device (wavefront path tracer: the number of surviving paths is
 	// produced by the previous kernel), so no host round trip is needed between bounces. The plain
@@ -195,6 +196,10 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 	// Warp-uniform window of claimed tickets.
 	uint64_t chunkNext = 0, chunkEnd = 0;
 	bool drained = false;
+	// Cost feedback (ticketCost != nullptr, only with refillThreshold == 32, i.e. one 32-ray ticket per warp at a
+	// time): rounds of the loop below this warp spent on each ticket. The next launch over the same batch deals
+	// the tickets longest first (ticketOrder), which removes most of the end-of-kernel tail.
+	uint32_t rounds = 0;      // since the current ticket was claimed
 
 	for (;;) {
 		const unsigned idle = __ballot_sync(kFullMask, s.phase == kPhaseIdle);
@@ -211,6 +216,12 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 					if (lane == 0) base = atomicAdd(queue, (unsigned long long)kChunk);
 					base = __shfl_sync(kFullMask, base, 0);
 					if (base >= count) { drained = true; break; }
+					if (ticketOrder) base = (unsigned long long)ticketOrder[base / kChunk] * kChunk;   // a permutation of the tickets
+					if (ticketCost) {
+						// chunkEnd still describes the ticket this warp has just finished (0 = none yet)
+						if (lane == 0 && chunkEnd != 0) ticketCost[(chunkEnd - 1) / kChunk] = rounds;
+						rounds = 0;
+					}
 					chunkNext = base;
 					chunkEnd = (base + kChunk < count) ? base + kChunk : count;
 				}
@@ -233,6 +244,7 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 			if (drained) break;
 			continue;
 		}
+		rounds++;
 
 #pragma unroll kStepUnroll
 		for (int k = 0; k < kStepsPerRound; k++) {
@@ -271,6 +283,46 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 			}
 		}
 	}
+	if (ticketCost && lane == 0 && chunkEnd != 0) ticketCost[(chunkEnd - 1) / kChunk] = rounds;
+}
+
+// Tickets by descending cost: counting sort on min(cost, 255) over 1024-ticket slices, one block per slice.
+// Pass 1 leaves each slice's histogram in `hist` ([slices][256]); pass 2 turns the histograms into this slice's
+// first output position per bucket and scatters. Order within a bucket is arbitrary: it is a scheduling hint.
+__global__ void __launch_bounds__(1024)
+ticketHistogram(const uint32_t* __restrict__ cost, uint32_t tickets, uint32_t* __restrict__ hist)
+{
+	__shared__ unsigned int bucket[256];
+	if (threadIdx.x < 256) bucket[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t t = blockIdx.x * 1024u + threadIdx.x;
+	if (t < tickets) atomicAdd(&bucket[255u - min(cost[t], 255u)], 1u);
+	__syncthreads();
+	if (threadIdx.x < 256) hist[blockIdx.x * 256u + threadIdx.x] = bucket[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(1024)
+ticketScatter(const uint32_t* __restrict__ cost, uint32_t tickets, const uint32_t* __restrict__ hist, uint32_t slices, uint32_t* __restrict__ order)
+{
+	__shared__ unsigned int total[256], cursor[256];
+	if (threadIdx.x < 256) {
+		unsigned int all = 0, before = 0;
+		for (uint32_t sl = 0; sl < slices; sl++) {
+			const unsigned int c = hist[sl * 256u + threadIdx.x];
+			all += c;
+			if (sl < blockIdx.x) before += c;
+		}
+		total[threadIdx.x] = all;
+		cursor[threadIdx.x] = before;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned int run = 0;
+		for (int b = 0; b < 256; b++) { const unsigned int c = total[b]; cursor[b] += run; run += c; }
+	}
+	__syncthreads();
+	const uint32_t t = blockIdx.x * 1024u + threadIdx.x;
+	if (t < tickets) order[atomicAdd(&cursor[255u - min(cost[t], 255u)], 1u)] = t;
 }
 
 template <bool kSurface>
@@ -376,7 +428,7 @@ cudaError_t launchKernel(Kernel kernel, const TraceArgs& a, const Source& src, c
 	const uint64_t needed = (tickets + (uint64_t)cfg.blockThreads - 1) / (uint64_t)cfg.blockThreads;
 	if (!a.countPtr && (uint64_t)grid > needed) grid = (int)(needed ? needed : 1);
 	kernel<<<grid, cfg.blockThreads, smem, stream>>>(a.nodes, a.subdags, src, sink, tickets, a.countPtr, a.countScale, a.maxFootprint,
-		cfg.refillThreshold, cfg.refillQuantum > 0 ? cfg.refillQuantum : 1, a.queue, a.abandoned);
+		cfg.refillThreshold, cfg.refillQuantum > 0 ? cfg.refillQuantum : 1, a.queue, a.abandoned, a.ticketOrder, a.ticketCost);
 	return cudaGetLastError();
 }
 
@@ -428,6 +480,14 @@ cudaError_t launchTrace(const TraceArgs& a, bool surface, const LaunchConfig& cf
 	}
 	BufferSource src{ a.rays };
 	return launchPersistent(a, surface, src, a.count, cfg, stream);
+}
+
+cudaError_t launchOrderTickets(const uint32_t* cost, uint32_t tickets, uint32_t* hist, uint32_t* order, cudaStream_t stream)
+{
+	const uint32_t slices = (tickets + 1023u) / 1024u;            // hist holds slices x 256 words
+	ticketHistogram<<<slices, 1024, 0, stream>>>(cost, tickets, hist);
+	ticketScatter<<<slices, 1024, 0, stream>>>(cost, tickets, hist, slices, order);
+	return cudaGetLastError();
 }
 
 cudaError_t launchRandomRays(uint64_t seed, const float lower[3], const float upper[3], uint64_t n, Ray* rays, cudaStream_t stream)

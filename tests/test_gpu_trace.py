@@ -314,3 +314,48 @@ def test_tiled_primary_rays_are_a_permutation_of_the_frame(gpu, port, api, scene
     assert set(first % w) == set(range(8)) and set(first // w) == set(range(4))      # one 8x4 tile per 32 rays
     with pytest.raises(api.CubiquityError):
         gpu.primary_rays_tiled_device(cam, 100, 96, d_rays.data_ptr(), None, stream)
+
+
+def test_cost_feedback_order_is_only_a_schedule(gpu, port, api):
+    """adaptive_order: repeated coherent launches over the same buffer deal the 32-ray tickets longest first
+    (learnt from the previous launch). Every launch -- first (identity order), later (learnt permutation), after
+    the batch changed, with the option off -- must return the same bits as the oracle."""
+    torch = pytest.importorskip("torch")
+    sc = api.Scene("terrain", 10, seed=1)
+    gpu.upload(sc.nodes, sc.root)
+    w, h = 1920, 1080                                   # 64 800 tickets: above the threshold where ordering kicks in
+    cam = api.default_camera(sc.lower, sc.upper)
+    ocam = port.camera([cam.position[0], cam.position[1], cam.position[2]], -(float(np.float32(3.14159265358979)) / 4.0), 0.0)
+    rays = port.camera_rays(ocam, w, h)
+    want = oracle_hits(port, sc, rays, True, -1.0)
+    stream = torch.cuda.current_stream().cuda_stream
+    d_hits = torch.zeros(w * h * 10, dtype=torch.int32, device="cuda")
+    for rep in range(4):                                # launch 0 records, launches 1.. use the learnt order
+        d_hits.zero_()
+        gpu.raycast_frame_device(cam, w, h, d_hits.data_ptr(), True, -1.0, stream)
+        torch.cuda.synchronize()
+        assert_hits_identical(d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1), want, "frame, repetition %d" % rep)
+    # an explicit buffer with the coherent setting, a ragged count (last ticket partial), then a different buffer
+    old = gpu.get_option("refill_threshold")
+    gpu.set_option("refill_threshold", 32)
+    try:
+        n = w * h - 13
+        d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1).copy()).cuda()
+        other = torch.from_numpy(rays[::-1].copy().view(np.float32).reshape(-1)).cuda()
+        for rep in range(3):
+            d_hits.zero_()
+            gpu.trace_device(d_rays.data_ptr(), n, d_hits.data_ptr(), True, -1.0, stream)
+            torch.cuda.synchronize()
+            assert_hits_identical(d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)[:n], want[:n], "buffer, repetition %d" % rep)
+        d_hits.zero_()
+        gpu.trace_device(other.data_ptr(), n, d_hits.data_ptr(), True, -1.0, stream)
+        torch.cuda.synchronize()
+        assert_hits_identical(d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)[:n], want[::-1][:n], "other buffer")
+        gpu.set_option("adaptive_order", 0)
+        d_hits.zero_()
+        gpu.trace_device(d_rays.data_ptr(), n, d_hits.data_ptr(), True, -1.0, stream)
+        torch.cuda.synchronize()
+        assert_hits_identical(d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)[:n], want[:n], "feedback off")
+    finally:
+        gpu.set_option("adaptive_order", 1)
+        gpu.set_option("refill_threshold", old)
