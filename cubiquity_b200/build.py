@@ -68,7 +68,10 @@ def build_library(force=False, verbose=False, defines=(), name=None):
             failed = True
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib] + objs + ["-lpthread"], check=True)
+    # link next to the target and rename: a reader (or a repository snapshot) never sees a half-written library
+    tmp = lib + ".partial"
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + objs + ["-lpthread"], check=True)
+    os.replace(tmp, lib)
     return lib
 
 

@@ -760,11 +760,12 @@ int cbq_trace(cbq_context* ctx, const cbq_ray* rays, uint64_t n, uint32_t flags,
 	// Three-stage pipeline over chunks: H2D on copyIn, kernel on stream, D2H on copyOut, kStages
 	// staging buffers in flight. With pinned host memory the three overlap; with pageable memory
 	// the copies degrade to synchronous but the result is the same.
-	const uint64_t chunks = (n + kPipelineChunk - 1) / kPipelineChunk;
-	for (uint64_t c = 0; c < chunks; c++) {
+	// The copy back (40 B/ray) is the longest leg, so the first stages are short -- 2^15, 2^16, 2^17 rays -- to get it
+	// going early; after that every stage is kPipelineChunk rays.
+	uint64_t begin = 0, stage = std::min<uint64_t>(kPipelineChunk, 1u << 15);
+	for (uint64_t c = 0; begin < n; c++) {
 		const int b = (int)(c % kStages);
-		const uint64_t begin = c * kPipelineChunk;
-		const uint64_t len = std::min(kPipelineChunk, n - begin);
+		const uint64_t len = std::min(stage, n - begin);
 		if (c >= (uint64_t)kStages) CBQ_CUDA(cudaStreamWaitEvent(ctx->copyIn, ctx->evOut[b], 0));   // buffer b free again
 		CBQ_CUDA(cudaMemcpyAsync(ctx->stageRays[b], rays + begin, len * sizeof(cbq_ray), cudaMemcpyHostToDevice, ctx->copyIn));
 		CBQ_CUDA(cudaEventRecord(ctx->evIn[b], ctx->copyIn));
@@ -776,6 +777,8 @@ int cbq_trace(cbq_context* ctx, const cbq_ray* rays, uint64_t n, uint32_t flags,
 		CBQ_CUDA(cudaStreamWaitEvent(ctx->copyOut, ctx->evKernel[b], 0));
 		CBQ_CUDA(cudaMemcpyAsync(hits + begin, ctx->stageHits[b], len * sizeof(cbq_hit), cudaMemcpyDeviceToHost, ctx->copyOut));
 		CBQ_CUDA(cudaEventRecord(ctx->evOut[b], ctx->copyOut));
+		begin += len;
+		stage = std::min<uint64_t>(stage * 2, kPipelineChunk);
 	}
 	CBQ_CUDA(cudaStreamSynchronize(ctx->copyOut));
 	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
