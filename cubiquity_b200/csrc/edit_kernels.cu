@@ -42,12 +42,14 @@ __device__ __forceinline__ bool contains(const Sphere& b, float x, float y, floa
 	return (float)distSq < b.radiusSquared;
 }
 
-__global__ void brushLevel(uint32_t* nodes, uint32_t capacity, Sphere b, uint32_t mat, int height, BrushItem* items, uint32_t itemCapacity, unsigned int* state)
+// One tree level: thread-slots first, first + stride, ... each take one (item, child slot) pair.
+__device__ __forceinline__ void brushLevelRange(uint32_t* nodes, uint32_t capacity, const Sphere& b, uint32_t mat, int height, BrushItem* items,
+	uint32_t itemCapacity, unsigned int* state, uint32_t first, uint32_t stride)
 {
 	const uint32_t begin = state[kLevelBegin + height], count = state[kLevelEnd + height] - begin;
 	const uint32_t childHeight = (uint32_t)height - 1u;
 	const uint32_t side = 1u << childHeight;
-	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count * 8u; t += gridDim.x * blockDim.x) {
+	for (uint32_t t = first; t < count * 8u; t += stride) {
 		const BrushItem it = items[begin + (t >> 3)];
 		const uint32_t slot = t & 7u;
 		const uint32_t cx = slot & 1u, cy = (slot >> 1) & 1u, cz = slot >> 2;
@@ -82,20 +84,27 @@ __global__ void brushLevel(uint32_t* nodes, uint32_t capacity, Sphere b, uint32_
 	}
 }
 
-// Between levels: what was queued during the launch is the next level's range.
-__global__ void brushAdvance(unsigned int* state, int height, uint32_t itemCapacity)
+__global__ void brushLevel(uint32_t* nodes, uint32_t capacity, Sphere b, uint32_t mat, int height, BrushItem* items, uint32_t itemCapacity, unsigned int* state)
+{
+	brushLevelRange(nodes, capacity, b, mat, height, items, itemCapacity, state, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+// Between levels: what was queued during the level is the next level's range.
+__device__ __forceinline__ void advanceLevel(unsigned int* state, int height, uint32_t itemCapacity)
 {
 	const uint32_t tail = state[kItemTail] < itemCapacity ? state[kItemTail] : itemCapacity;
 	state[kLevelBegin + height - 1] = state[kLevelEnd + height];
 	state[kLevelEnd + height - 1] = tail;
 }
 
+__global__ void brushAdvance(unsigned int* state, int height, uint32_t itemCapacity) { advanceLevel(state, height, itemCapacity); }
+
 // Bottom-up: a copy that ended up identical to its source was not needed; point the parent back at the original
 // (the reference's `if (fresh != old)`, voxelization.cpp fillBrush / storage.cpp:152-167).
-__global__ void brushRevert(uint32_t* nodes, int height, const BrushItem* items, const unsigned int* state)
+__device__ __forceinline__ void brushRevertRange(uint32_t* nodes, int height, const BrushItem* items, const unsigned int* state, uint32_t first, uint32_t stride)
 {
 	const uint32_t begin = state[kLevelBegin + height], count = state[kLevelEnd + height] - begin;
-	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+	for (uint32_t t = first; t < count; t += stride) {
 		const BrushItem it = items[begin + t];
 		const uint4* mine = reinterpret_cast<const uint4*>(nodes) + (size_t)it.node * 2;
 		const uint4 a = mine[0], c = mine[1];
@@ -107,8 +116,13 @@ __global__ void brushRevert(uint32_t* nodes, int height, const BrushItem* items,
 	}
 }
 
+__global__ void brushRevert(uint32_t* nodes, int height, const BrushItem* items, const unsigned int* state)
+{
+	brushRevertRange(nodes, height, items, state, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
 // The writable copy of the root (Volume::checkpoint / cloneRoot, storage.cpp:298-303, 358-371) and the first item.
-__global__ void brushBegin(uint32_t* nodes, uint32_t capacity, uint32_t root, BrushItem* items, unsigned int* state)
+__device__ __forceinline__ void beginStroke(uint32_t* nodes, uint32_t capacity, uint32_t root, BrushItem* items, unsigned int* state)
 {
 	const uint32_t fresh = atomicAdd(&state[kNodeTail], 1u);
 	state[kLevelBegin + 32] = 0;
@@ -119,6 +133,29 @@ __global__ void brushBegin(uint32_t* nodes, uint32_t capacity, uint32_t root, Br
 	state[kItemTail] = 1;
 	state[kLevelEnd + 32] = 1;
 	state[kRoot] = fresh;
+}
+
+// The top of the tree holds a handful of items per level (the brush box bounds them): heights 32 .. lowest are
+// walked by ONE block, a barrier between levels instead of a launch.
+__global__ void __launch_bounds__(256) brushTop(uint32_t* nodes, uint32_t capacity, uint32_t root, Sphere b, uint32_t mat, int lowest, BrushItem* items,
+	uint32_t itemCapacity, unsigned int* state)
+{
+	if (threadIdx.x == 0) beginStroke(nodes, capacity, root, items, state);
+	__syncthreads();
+	for (int height = 32; height >= lowest; height--) {
+		brushLevelRange(nodes, capacity, b, mat, height, items, itemCapacity, state, threadIdx.x, blockDim.x);
+		__syncthreads();
+		if (threadIdx.x == 0) advanceLevel(state, height, itemCapacity);
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(256) brushRevertTop(uint32_t* nodes, int lowest, const BrushItem* items, const unsigned int* state)
+{
+	for (int height = lowest; height <= 31; height++) {
+		brushRevertRange(nodes, height, items, state, threadIdx.x, blockDim.x);
+		__syncthreads();
+	}
 }
 
 } // namespace
@@ -141,17 +178,25 @@ cudaError_t launchFillSphere(uint32_t* nodes, uint32_t capacity, uint32_t root, 
 		if (blocks > (uint64_t)smCount * 8) blocks = (uint64_t)smCount * 8;
 		return (unsigned)blocks;
 	};
-	brushBegin<<<1, 1, 0, stream>>>(nodes, capacity, root, items, state);
+	// Heights whose cubes are so large that at most ~64 of them can meet the brush box go to the one-block kernels.
+	int lowest = 32;
+	while (lowest > 1) {
+		const double across = 2.0 * radius / (double)(1u << (lowest - 1)) + 2.0;
+		if (across * across * across > 64.0) break;
+		lowest--;
+	}
+	brushTop<<<1, 256, 0, stream>>>(nodes, capacity, root, b, material, lowest, items, itemCapacity, state);
 	uint64_t count = 1;
-	for (int height = 32; height >= 1; height--) {
+	for (int height = lowest - 1; height >= 1; height--) {
 		brushLevel<<<blocksFor(height, 8), 256, 0, stream>>>(nodes, capacity, b, material, height, items, itemCapacity, state);
 		brushAdvance<<<1, 1, 0, stream>>>(state, height, itemCapacity);
 		count += 2;
 	}
-	for (int height = 1; height <= 31; height++) {
+	for (int height = 1; height < lowest && height <= 31; height++) {
 		brushRevert<<<blocksFor(height, 1), 256, 0, stream>>>(nodes, height, items, state);
 		count++;
 	}
+	if (lowest <= 31) { brushRevertTop<<<1, 256, 0, stream>>>(nodes, lowest, items, state); count++; }
 	if (launches) *launches += count;
 	return cudaGetLastError();
 }

@@ -90,3 +90,17 @@ def test_set_root_argument_checks(gpu, api, scenes):
     with pytest.raises(api.CubiquityError):
         gpu.set_root(len(sc.nodes) + 10)
     gpu.set_root(sc.root)
+
+
+@pytest.mark.parametrize("radius", [0.0, 0.6, 1.5, 2.5])
+def test_tiny_brushes_take_the_one_block_path(gpu, port, ref, scenes, radius):
+    """Radii this small are walked entirely by the one-block kernels (no per-level launches)."""
+    sc = scenes("sphere_noise", 6)
+    v = ref.volume().load_arrays(sc.nodes, sc.root)
+    gpu.upload(sc.nodes, sc.root)
+    for k, (x, y, z) in enumerate([(0.0, 0.0, 0.0), (10.0, -3.0, 7.0), (-1.0, -1.0, -1.0), (15.5, 15.5, 15.5)]):
+        m = 0 if k % 2 == 0 else 6
+        v.checkpoint()
+        v.fill_sphere(x, y, z, radius, m)
+        root, count = gpu.fill_sphere(x, y, z, radius, m)
+        same_tree(gpu, v, root)
