@@ -68,9 +68,11 @@ __device__ __forceinline__ void brushLevelRange(uint32_t* nodes, uint32_t capaci
 		const uint32_t old = *cell;
 		if (old == mat) continue;
 		if (height >= 2 && !inside) {
+			// Reserve the queue entry only once the node exists: every entry below the queue's tail must have been
+			// written, or the next level would walk whatever the work space held before.
 			const uint32_t fresh = atomicAdd(&state[kNodeTail], 1u);
-			const uint32_t at = atomicAdd(&state[kItemTail], 1u);
 			if (fresh >= capacity) { atomicOr(&state[kOverflow], 1u); continue; }
+			const uint32_t at = atomicAdd(&state[kItemTail], 1u);
 			if (at >= itemCapacity) { atomicOr(&state[kOverflow], 2u); continue; }
 			uint4* dst = reinterpret_cast<uint4*>(nodes) + (size_t)fresh * 2;
 			if (old < kMaterialCount) { dst[0] = make_uint4(old, old, old, old); dst[1] = dst[0]; }

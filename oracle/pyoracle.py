@@ -324,6 +324,7 @@ def dag_signature(nodes, root, collapse=True):
     nodes = np.ascontiguousarray(nodes, dtype=np.uint32).reshape(-1, 8)
     sig = {}
     distinct = set()
+    open_nodes = set()          # expanded, not finished: meeting one again means the array has a cycle
 
     def mat(m):
         return b"m" + int(m).to_bytes(4, "little")
@@ -337,11 +338,17 @@ def dag_signature(nodes, root, collapse=True):
             continue
         kids = [int(c) for c in nodes[i]]
         if not expanded:
+            if i in open_nodes:
+                raise ValueError("node %d is its own ancestor: not a DAG" % i)
+            open_nodes.add(i)
             stack.append((i, True))
             for c in kids:
+                if c >= len(nodes):
+                    raise ValueError("node %d has child %d past the end of the array (%d)" % (i, c, len(nodes)))
                 if c >= 256 and c not in sig:
                     stack.append((c, False))
             continue
+        open_nodes.discard(i)
         parts = [mat(c) if c < 256 else sig[c] for c in kids]
         if collapse and parts[0][:1] == b"m" and all(p == parts[0] for p in parts):
             sig[i] = parts[0]

@@ -68,7 +68,8 @@ def test_large_brush_grows_the_array_and_the_work_list(gpu, port, ref, scenes):
     v.fill_sphere(10.0, -20.0, -40.0, 220.0, 0)
     root, count = gpu.fill_sphere(10.0, -20.0, -40.0, 220.0, 0)
     assert count - before > (1 << 16)                                        # more than the head-room of the upload
-    same_tree(gpu, v, root)
+    mine = same_tree(gpu, v, root)
+    assert np.array_equal(mine[:len(sc.nodes)], sc.nodes)                    # the attempts that ran out of room wrote nothing that existed
     rays = mixed_rays(sc.lower, sc.upper, 40000, seed=6)
     want, _, _ = port.trace(v.nodes(), port.find_subdags(v.nodes(), v.root()), rays, True, -1.0, threads=8)
     assert_hits_identical(gpu.intersect_volume(rays, True, -1.0), want, "large brush")
