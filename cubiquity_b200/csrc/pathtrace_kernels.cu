@@ -97,7 +97,9 @@ renderPersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict
 	__syncthreads();
 
 	const GlobalNodes nodes{ nodeBase };
-	SharedStack stack{ (uint32_t)__cvta_generic_to_shared(stackMem + threadIdx.x), blockDim.x * 4u, 0u };
+	uint32_t stackColumn = (uint32_t)__cvta_generic_to_shared(stackMem + threadIdx.x), stackStride = blockDim.x * 4u;
+	asm volatile("" : "+r"(stackColumn), "+r"(stackStride));     // keep both in registers (see tracePersistent)
+	SharedStack stack{ stackColumn, stackStride, 0u };
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lowerLanes = (1u << lane) - 1u;
 	uint64_t chunkNext = 0, chunkEnd = 0;   // warp-uniform window of claimed tickets

@@ -186,7 +186,12 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 	__syncthreads();
 
 	const GlobalNodes nodes{ nodeBase };
-	SharedStack stack{ (uint32_t)__cvta_generic_to_shared(stackMem + threadIdx.x), blockDim.x * 4u, 0u };
+	// The two address terms are made opaque so that they stay in registers: left alone, the compiler re-derives them
+	// (tid, shared-window base, blockDim: 9 extra instructions) at every push and pop to save two of the eight
+	// registers the launch bounds leave unused.
+	uint32_t stackColumn = (uint32_t)__cvta_generic_to_shared(stackMem + threadIdx.x), stackStride = blockDim.x * 4u;
+	asm volatile("" : "+r"(stackColumn), "+r"(stackStride));
+	SharedStack stack{ stackColumn, stackStride, 0u };
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lowerLanes = (1u << lane) - 1u;
 
