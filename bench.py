@@ -487,6 +487,29 @@ def main():
         order_off_ms = float(np.mean(off))
         ctx.set_option("adaptive_order", 1)
 
+    # the same frame with the reference path tracer's LOD threshold (maxFootprint 0.0035, pathtracing_demo.h:84); hits land in a scratch buffer
+    lod_ms = None
+    if args.workload == "primary":
+        d_lod = torch.empty_like(d_hits)
+        def lod_step():
+            ctx.trace_device(d_rays.data_ptr(), n_rays, d_lod.data_ptr(), True, 0.0035, stream)
+        for _ in range(3):
+            lod_step()
+        torch.cuda.synchronize()
+        lod = []
+        for _ in range(min(args.steps, 10)):
+            if not args.no_flush:
+                flush.zero_()
+            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); lod_step(); b2.record()
+            torch.cuda.synchronize()
+            lod.append(a.elapsed_time(b2))
+        lod_ms = float(np.mean(lod))
+        del d_lod
+        for _ in range(2):
+            step()                 # hand the cost feedback back to the LOD-off frame before anything else is measured
+        torch.cuda.synchronize()
+
     # ---- secondary metric of BASELINE.json: 1080p path-traced samples per second (spp/s) ------------
     pt = None
     if args.workload == "primary":
@@ -600,6 +623,8 @@ def main():
                   "ticket_order": "cost feedback: from the 2nd launch over the same ray buffer the 32-ray tickets are dealt longest first (adaptive_order=1; one extra 1-block sort kernel per step, inside the timed region)" if order_off_ms is not None else "buffer order",
                   "adaptive_order_off_ms_per_step": order_off_ms,
                   "adaptive_order_off_value": (world * n_rays / (order_off_ms * 1e-3) / 1e9) if order_off_ms else None,
+                  "max_footprint_0.0035_ms_per_step": lod_ms,
+                  "max_footprint_0.0035_value": (world * n_rays / (lod_ms * 1e-3) / 1e9) if lod_ms else None,
                   "pathtrace": pt},
     }
     print(json.dumps(line), flush=True)
