@@ -154,6 +154,7 @@ struct cbq_context {
 	// Counters
 	uint64_t launches = 0, raysTraced = 0, bytesH2D = 0, bytesD2H = 0;
 	uint64_t bakeReachable = 0;   // nodes the root reached in the last cbq_bake, before merging
+	bool deviceDiverged = false;  // a device-side edit / bake / build made the device copy differ from any host array
 
 	const uint32_t* nodesPtr() const { return reinterpret_cast<const uint32_t*>(volume + cbq::kNodeOffset); }
 	const cbq::SubDag* subdagsPtr() const { return reinterpret_cast<const cbq::SubDag*>(volume + cbq::kSubDagOffset); }
@@ -371,6 +372,7 @@ int bakeAndInstall(cbq_context* ctx, const uint32_t* dNodes, uint64_t n, uint32_
 	ctx->root = (uint32_t)host.results[2];
 	ctx->generation++;
 	ctx->bakeReachable = host.results[3];
+	ctx->deviceDiverged = true;
 	std::memcpy(ctx->subdags, host.subdags, sizeof(host.subdags));
 	int maxH = 0;
 	for (int i = 0; i < 8; i++) if (ctx->subdags[i].node > 0) maxH = std::max(maxH, ctx->subdags[i].height);
@@ -535,6 +537,7 @@ int cbq_upload(cbq_context* ctx, const uint32_t* nodes, uint64_t node_count, uin
 	ctx->nodeCount = node_count;
 	ctx->root = root_index;
 	ctx->generation++;
+	ctx->deviceDiverged = false;
 	CBQ_CUDA(cudaMemcpyAsync(ctx->volume + cbq::kNodeOffset, nodes, (size_t)node_count * 32, cudaMemcpyHostToDevice, ctx->stream));
 	ctx->bytesH2D += node_count * 32;
 	rc = cbq_set_colours(ctx, colours_rgb); if (rc) return rc;
@@ -545,6 +548,8 @@ int cbq_update(cbq_context* ctx, const uint32_t* nodes, uint64_t dirty_begin, ui
 {
 	int rc = bind(ctx); if (rc) return rc;
 	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "cbq_update before cbq_upload");
+	if (ctx->deviceDiverged) return fail(CBQ_ERROR_INVALID_ARGUMENT, "the device copy was changed on the device (cbq_fill_sphere / cbq_bake / cbq_build_dense): "
+		"a host array can no longer be applied as a delta; cbq_upload it, or cbq_download_nodes first");
 	if (!nodes || node_count < cbq::kMaterialCount || dirty_begin > node_count) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad dirty range");
 	if (dirty_begin > ctx->nodeCount) return fail(CBQ_ERROR_INVALID_ARGUMENT, "dirty_begin %llu is past the %llu nodes on the device", (unsigned long long)dirty_begin, (unsigned long long)ctx->nodeCount);
 	if (node_count > 0xffffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "node indices are 32-bit");
@@ -673,6 +678,7 @@ int cbq_fill_sphere(cbq_context* ctx, float x, float y, float z, float radius, u
 		poolFree(ctx, work);
 		if (rc) { ctx->nodeCount = oldCount; ctx->root = oldRoot; return rc; }
 		ctx->generation++;
+		ctx->deviceDiverged = true;
 		if (root_index) *root_index = ctx->root;
 		if (node_count) *node_count = ctx->nodeCount;
 		return writeHeaderAndSubdags(ctx);

@@ -126,7 +126,9 @@ int cbq_upload(cbq_context* ctx, const uint32_t* nodes, uint64_t node_count, uin
  * is stale exactly on the tail [dirty_begin, node_count): pass dirty_begin = the
  * sharedNodesEnd() seen at the previous sync (or anything lower), the CURRENT base pointer and
  * node count, and the new root. Sub-DAGs are recomputed (pathtracing_demo.cpp:335-341).
- * After Volume::bake() everything moved: call cbq_upload again. */
+ * After Volume::bake() everything moved: call cbq_upload again. Once the device copy has been changed ON the device
+ * (cbq_fill_sphere, cbq_bake, cbq_build_dense) no host array is a delta of it any more: cbq_update then fails until
+ * the next cbq_upload. */
 int cbq_update(cbq_context* ctx, const uint32_t* nodes, uint64_t dirty_begin, uint64_t node_count,
                uint32_t root_index);
 

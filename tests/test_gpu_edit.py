@@ -105,3 +105,14 @@ def test_tiny_brushes_take_the_one_block_path(gpu, port, ref, scenes, radius):
         v.fill_sphere(x, y, z, radius, m)
         root, count = gpu.fill_sphere(x, y, z, radius, m)
         same_tree(gpu, v, root)
+
+
+def test_host_delta_after_a_device_edit_is_refused(gpu, api, scenes):
+    sc = scenes("sphere_noise", 6)
+    gpu.upload(sc.nodes, sc.root)
+    gpu.update(sc.nodes, len(sc.nodes), sc.root)                            # fine: nothing happened on the device
+    gpu.fill_sphere(0.0, 0.0, 0.0, 4.0, 0)
+    with pytest.raises(api.CubiquityError):
+        gpu.update(sc.nodes, len(sc.nodes), sc.root)                        # the device copy has nodes the host never saw
+    gpu.upload(sc.nodes, sc.root)
+    gpu.update(sc.nodes, len(sc.nodes), sc.root)
