@@ -141,6 +141,22 @@ def orbit_camera(api, scene, rank):
     return api.camera_from_pose(pos, -(PI_F / 4.0), yaw), pos, yaw
 
 
+class OnlyJsonOnStdout:
+    """The driver reads ONE JSON line from stdout; libraries (NCCL prints its version banner there) must not add to it.
+    File descriptor 1 points at stderr until emit() prints the line."""
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        self.saved = None
+        print(json.dumps(line), flush=True)
+
+
 def reference_arm(args):
     """bench.py --impl reference: the reference's own CPU intersectVolume, all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -188,6 +204,7 @@ def pathtrace_workload(args):
     recursive bounce loop, `--bounces` bounces, `--spp` samples, LOD 0.0035). Strong scaling: the frame's
     64-row tile bands are dealt round-robin to the ranks, the DAG is replicated, and ONE collective -- a sum of
     the disjoint partial images onto rank 0 -- ends the frame (inside the timed region)."""
+    out = OnlyJsonOnStdout()
     import torch
     import torch.distributed as dist
     from cubiquity_b200 import api, sharding
@@ -341,7 +358,7 @@ def pathtrace_workload(args):
                 "e2e": {"value": W * H * args.spp / e2e_s, "unit": "spp/s", "h2d_bytes_per_step": H * W * 12,
                         "d2h_bytes_per_step": H * W * 12, "call": "cbq_render (host image in, this rank's bands rendered, host image out)"},
                 "gpu_launches": int(launches), "clocks": clocks.summary(), "extra": {"mean_radiance": mean, "edits": {k: [round(float(x), 3) for x in v] for k, v in edit_stats.items()} if args.edits else None}}
-        print(json.dumps(line), flush=True)
+        out.emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -355,6 +372,7 @@ def main():
         pathtrace_workload(args)
         return
 
+    out = OnlyJsonOnStdout()
     import torch
     import torch.distributed as dist
     from cubiquity_b200 import api, sharding
@@ -627,7 +645,7 @@ def main():
                   "max_footprint_0.0035_value": (world * n_rays / (lod_ms * 1e-3) / 1e9) if lod_ms else None,
                   "pathtrace": pt},
     }
-    print(json.dumps(line), flush=True)
+    out.emit(line)
     if world > 1:
         dist.destroy_process_group()
 
