@@ -28,5 +28,19 @@ int main(int argc, char** argv)
 	CubiquityGPU::RayVolumeIntersection r = CubiquityGPU::intersectVolume(vol, 0.25f, 0.125f, 100.0f, 0.001f, 0.002f, -1.0f, true);
 	std::printf("hit %d %.9g %u %.9g %.9g %.9g %g %g %g\n", (int)r.hit, r.distance, r.material, r.position[0], r.position[1], r.position[2],
 		r.normal[0], r.normal[1], r.normal[2]);
+	// The volume's life cycle on the device through the same mirror: carve where the ray hit, trace again (the hit
+	// moves away), undo by switching back to the old root (the hit is back), bake and read the merged array back.
+	uint32_t carved = 0;
+	if (!vol.fillSphere(r.position[0], r.position[1], r.position[2], 3.0f, 0, carved)) { std::printf("fill failed %s\n", CubiquityGPU::GpuVolume::lastError().c_str()); return 1; }
+	CubiquityGPU::RayVolumeIntersection after = CubiquityGPU::intersectVolume(vol, 0.25f, 0.125f, 100.0f, 0.001f, 0.002f, -1.0f, true);
+	if (!vol.setRoot(root)) return 1;
+	CubiquityGPU::RayVolumeIntersection undone = CubiquityGPU::intersectVolume(vol, 0.25f, 0.125f, 100.0f, 0.001f, 0.002f, -1.0f, true);
+	uint64_t bakedCount = 0; uint32_t bakedRoot = 0;
+	if (!vol.bake(bakedCount, bakedRoot)) { std::printf("bake failed %s\n", CubiquityGPU::GpuVolume::lastError().c_str()); return 1; }
+	std::vector<uint32_t> baked((size_t)bakedCount * 8);
+	if (!vol.download(0, bakedCount, baked.data())) return 1;
+	CubiquityGPU::RayVolumeIntersection rebaked = CubiquityGPU::intersectVolume(vol, 0.25f, 0.125f, 100.0f, 0.001f, 0.002f, -1.0f, true);
+	std::printf("lifecycle %d %.9g %d %.9g %llu %u %d %.9g\n", (int)after.hit, after.distance, (int)undone.hit, undone.distance,
+		(unsigned long long)bakedCount, baked[(size_t)bakedRoot * 8] | baked[(size_t)bakedRoot * 8 + 7], (int)rebaked.hit, rebaked.distance);
 	return 0;
 }

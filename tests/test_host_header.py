@@ -49,6 +49,8 @@ def test_header_reports_missing_gpu_loudly(exe, api):
 def test_single_ray_call_matches_oracle(exe, port):
     from cubiquity_b200 import dagfile
     lines = run(exe)
+    life = lines.pop()
+    assert life[0] == "lifecycle", life
     assert lines[-1][0] == "hit", lines[-1]
     nodes, root = dagfile.read_dag(GOLD)
     ray = np.zeros(1, dtype=[("o", "<f4", 3), ("d", "<f4", 3)])
@@ -59,6 +61,13 @@ def test_single_ray_call_matches_oracle(exe, port):
     assert int(got[0]) == int(want["hit"][0]) == 1
     assert np.float32(float(got[1])) == want["distance"][0] and int(got[2]) == int(want["material"][0])
     assert [np.float32(float(v)) for v in got[3:6]] == list(want["position"][0])
+    # carve at the hit -> the surface recedes; back to the old root -> the same hit again; bake of the un-edited root
+    # keeps the scene's node count (the golden volume is already merged) and the same hit
+    after_hit, after_d, undone_hit, undone_d, baked_count, _, rebaked_hit, rebaked_d = life[1:]
+    assert int(after_hit) == 1 and float(after_d) > float(got[1]) + 1.0
+    assert int(undone_hit) == 1 and np.float32(float(undone_d)) == want["distance"][0]
+    assert int(baked_count) == len(nodes)
+    assert int(rebaked_hit) == 1 and np.float32(float(rebaked_d)) == want["distance"][0]
 
 
 @pytest.fixture(scope="module")
