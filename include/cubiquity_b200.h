@@ -242,7 +242,9 @@ int cbq_host_free(void* p);
  * pixel the wavefront tracer traces together, 1..16; 0 = choose from the size of the rectangle),
  * "adaptive_order" (0/1, default 1: coherent batches -- refill_threshold 32, cbq_raycast_frame_device -- record how
  * long each 32-ray ticket took, and the next launch over the same ray buffer, size and stream deals the tickets
- * longest first; a scheduling hint only, results do not depend on it). */
+ * longest first; a scheduling hint only, results do not depend on it), "order_refresh" (that order is rebuilt from
+ * the recorded costs every this many launches, default 4; cbq_raycast_frame_device also rebuilds it after every
+ * frame whose camera differs from the previous one). */
 int cbq_set_option(cbq_context* ctx, const char* key, int64_t value);
 int cbq_get_option(cbq_context* ctx, const char* key, int64_t* value);
 
