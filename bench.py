@@ -18,7 +18,7 @@ cbq_trace_device over one frame of rays (2 073 600 rays) that already sit in HBM
              GPU box's host cores, same rays. oracle/ is used ONLY here and in --impl reference.
 
 N > 1 (torchrun): the DAG is built on rank 0 and replicated with one NCCL broadcast; every rank then
-traces its own frame (its own camera on an orbit) -- weak scaling, no collective in the data path.
+traces its own copy of the frame -- weak scaling, no collective in the data path.
 """
 import argparse
 import json
@@ -457,7 +457,9 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
 
     # ---- inputs resident in HBM --------------------------------------------------------------
-    cam, pos, yaw = orbit_camera(api, b, rank)
+    # Weak scaling means the SAME work per GPU at every N: every rank casts the frame of BASELINE configs[1] (rank 0's pose).
+    # (Per-rank poses on an orbit made the 8-GPU figure the slowest view's, not a scaling measurement: 38.2 vs 8 x 5.6 Grays/s.)
+    cam, pos, yaw = orbit_camera(api, b, 0)
     if args.workload == "random":
         n_rays = args.random_rays
         ext = (np.asarray(upper, dtype=np.float64) - np.asarray(lower, dtype=np.float64)) * 0.1
@@ -653,7 +655,7 @@ def main():
                    "nodes": int(len(nodes)), "dag_mb": round(len(nodes) * 32 / 1e6, 1), "rays_per_step_per_gpu": n_rays,
                    "l2": "warm (no flush)" if args.no_flush else "flushed between steps (256 MB memset, untimed)",
                    "hit_fraction": round(hit_fraction, 4), "options": options,
-                   "parallelism": "replicated DAG, one frame per GPU" if world > 1 else "single GPU"},
+                   "parallelism": "replicated DAG, one 1080p frame per GPU (the same view on every GPU)" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": "Grays/s", "h2d_bytes_per_step": n_e2e * 24, "d2h_bytes_per_step": n_e2e * 40, "rays_per_step": n_e2e,
                 "ms_per_step": 1e3 * e2e_s, "call": "cbq_trace (pinned host rays -> pinned host hits, 3-stage copy/compute pipeline)"},
         "gpu_launches": int(launches),
