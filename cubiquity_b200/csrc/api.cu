@@ -149,6 +149,8 @@ struct cbq_context {
 	int orderAge = 0;                 // launches since the order was last rebuilt from the recorded costs
 	int orderRefresh = 4;             // rebuild it every this many launches (option "order_refresh")
 	cbq_camera lastFrameCamera{};     // cbq_raycast_frame_device: a frame whose camera moved rebuilds the order at once
+	cudaEvent_t orderEvent = nullptr; // end of the last launch that used the cost / order buffers (they are shared by all streams)
+	bool orderEventSet = false;
 	uint64_t orderTickets = 0;
 	const void* orderRays = nullptr;
 	cudaStream_t orderStream = nullptr;
@@ -273,6 +275,8 @@ bool orderBeforeTrace(cbq_context* ctx, cbq::TraceArgs& a, const cbq::LaunchConf
 			cudaMalloc(&ctx->ticketOrder[1], tickets * 4) != cudaSuccess || cudaMalloc(&ctx->ticketHist, ((tickets + 1023) / 1024) * 256 * 4) != cudaSuccess) { cudaGetLastError(); return false; }
 		ctx->ticketCapacity = tickets;
 	}
+	// One set of buffers serves every stream: a launch on another stream waits for the previous user (trace + sort).
+	if (ctx->orderEventSet && ctx->orderStream != stream && cudaStreamWaitEvent(stream, ctx->orderEvent, 0) != cudaSuccess) { cudaGetLastError(); return false; }
 	if (ctx->orderTickets == tickets && ctx->orderRays == a.rays && ctx->orderStream == stream) a.ticketOrder = ctx->ticketOrder[ctx->orderWhich];
 	a.ticketCost = ctx->ticketCost;
 	return true;
@@ -285,12 +289,17 @@ int orderAfterTrace(cbq_context* ctx, const cbq::TraceArgs& a, cudaStream_t stre
 	// launch (4). The frame call rebuilds after every frame whose camera moved (refreshNow): measured on an orbit at
 	// 0.25 deg per frame, 4.94 Grays/s with a rebuild per frame, 4.76 every 4th, 4.51 without feedback.
 	const bool sameBatch = ctx->orderTickets == tickets && ctx->orderRays == a.rays && ctx->orderStream == stream;
-	if (sameBatch && a.ticketOrder && ++ctx->orderAge < ctx->orderRefresh && !refreshNow) return CBQ_OK;
-	ctx->orderAge = 0;
-	const int next = ctx->orderWhich ^ 1;
-	CBQ_CUDA(cbq::launchOrderTickets(ctx->ticketCost, (uint32_t)tickets, ctx->ticketHist, ctx->ticketOrder[next], stream));
-	ctx->orderWhich = next; ctx->orderTickets = tickets; ctx->orderRays = a.rays; ctx->orderStream = stream;
-	ctx->launches += 2;
+	const bool keep = sameBatch && a.ticketOrder && ++ctx->orderAge < ctx->orderRefresh && !refreshNow;
+	if (!keep) {
+		ctx->orderAge = 0;
+		const int next = ctx->orderWhich ^ 1;
+		CBQ_CUDA(cbq::launchOrderTickets(ctx->ticketCost, (uint32_t)tickets, ctx->ticketHist, ctx->ticketOrder[next], stream));
+		ctx->orderWhich = next; ctx->orderTickets = tickets; ctx->orderRays = a.rays;
+		ctx->launches += 2;
+	}
+	ctx->orderStream = stream;
+	CBQ_CUDA(cudaEventRecord(ctx->orderEvent, stream));
+	ctx->orderEventSet = true;
 	return CBQ_OK;
 }
 
@@ -464,6 +473,7 @@ int cbq_create(int device, cbq_context** out)
 		uint64_t keep = ~0ull;
 		CBQ_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
 	}
+	CBQ_CUDA(cudaEventCreateWithFlags(&ctx->orderEvent, cudaEventDisableTiming));
 	CBQ_CUDA(cudaMalloc(&ctx->queues, sizeof(unsigned long long) * (kQueueSlots + 1)));
 	CBQ_CUDA(cudaMemset(ctx->queues, 0, sizeof(unsigned long long) * (kQueueSlots + 1)));
 	ctx->cfg.blockThreads = 256;
@@ -492,6 +502,7 @@ void cbq_destroy(cbq_context* ctx)
 	cudaFree(ctx->stageAccum);
 	cudaFree(ctx->frameRays);
 	cudaFree(ctx->ticketCost); cudaFree(ctx->ticketHist); cudaFree(ctx->ticketOrder[0]); cudaFree(ctx->ticketOrder[1]);
+	if (ctx->orderEvent) cudaEventDestroy(ctx->orderEvent);
 	cbq::wavefrontRelease(ctx->wavefront);
 	cudaFree(ctx->queues);
 	poolFree(ctx, ctx->volume);

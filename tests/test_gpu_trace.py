@@ -351,6 +351,16 @@ def test_cost_feedback_order_is_only_a_schedule(gpu, port, api):
         gpu.trace_device(other.data_ptr(), n, d_hits.data_ptr(), True, -1.0, stream)
         torch.cuda.synchronize()
         assert_hits_identical(d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)[:n], want[::-1][:n], "other buffer")
+        # two streams taking turns over the same batch share one set of cost / order buffers: launches must not overlap on them
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        outs = [torch.zeros(w * h * 10, dtype=torch.int32, device="cuda") for _ in range(6)]
+        torch.cuda.synchronize()
+        for k, o in enumerate(outs):
+            st = s1 if k % 2 == 0 else s2
+            gpu.trace_device(d_rays.data_ptr(), n, o.data_ptr(), True, -1.0, st.cuda_stream)
+        torch.cuda.synchronize()
+        for k, o in enumerate(outs):
+            assert_hits_identical(o.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)[:n], want[:n], "alternating streams, launch %d" % k)
         gpu.set_option("adaptive_order", 0)
         d_hits.zero_()
         gpu.trace_device(d_rays.data_ptr(), n, d_hits.data_ptr(), True, -1.0, stream)
