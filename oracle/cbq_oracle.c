@@ -90,7 +90,16 @@ void cbqo_find_subdags(const uint32_t* nodes, uint32_t root, cbqo_subdag out[8])
  * 'D' descend, 'A' advance within the parent, 'P' advance that pops, 'H' hit, 'O' sub-DAG entered. */
 static uint8_t* g_events = NULL;
 static uint32_t g_eventCount = 0, g_eventCap = 0;
-static inline void record_event(uint8_t e) { if (g_events && g_eventCount < g_eventCap) g_events[g_eventCount++] = e; }
+static uint64_t* g_heightHist = NULL;   /* [5][34]: events D, A, P, H, O by the height of the node they happen in */
+static int g_eventHeight = 0;
+static inline void record_event(uint8_t e)
+{
+	if (g_events && g_eventCount < g_eventCap) g_events[g_eventCount++] = e;
+	if (g_heightHist && g_eventHeight >= 0 && g_eventHeight < 34) {
+		const int k = e == 'D' ? 0 : e == 'A' ? 1 : e == 'P' ? 2 : e == 'H' ? 3 : 4;
+		g_heightHist[k * 34 + g_eventHeight]++;
+	}
+}
 
 /* ---------------------------------------------------------------- ray cast */
 
@@ -185,6 +194,7 @@ static int esvo_node(const uint32_t* nodes, uint32_t node, const int32_t nodePos
 			const int bigEnough = ((float)childSize / tExit) > maxFootprint;
 			if (internal && bigEnough) {
 				if (st) st->descents++;
+				g_eventHeight = nodeHeight;
 				record_event('D');
 				if (tExit < lastExit) stack[nodeHeight] = node;
 				lastExit = tExit;
@@ -196,6 +206,7 @@ static int esvo_node(const uint32_t* nodes, uint32_t node, const int32_t nodePos
 				for (int a = 0; a < 3; a++) pos[a] = (int32_t)((uint32_t)pos[a] + (uint32_t)(id[a] * childSize));
 			} else {
 				found = 1;
+				g_eventHeight = nodeHeight;
 				record_event('H');
 				hit->hit = 1;
 				hit->distance = tEntry;
@@ -218,6 +229,7 @@ static int esvo_node(const uint32_t* nodes, uint32_t node, const int32_t nodePos
 				pos[a] = (int32_t)((uint32_t)pos[a] + (uint32_t)(flips[a] * childSize));
 				if ((id[a] & flips[a]) != flips[a]) wrapped = 1;
 			}
+			g_eventHeight = nodeHeight;
 			record_event(wrapped ? 'P' : 'A');
 			if (wrapped) {
 				if (st) st->pops++;
@@ -676,6 +688,19 @@ void cbqo_trace_iterations(const uint32_t* nodes, const cbqo_subdag sd[8], const
 	}
 }
 
+
+/* Where in the tree the work happens: events by kind (D, A, P, H, O) and by the height of the node they happen in
+ * (children of a height-h node are 2^(h-1) voxels wide). hist: 5 * 34 counters, accumulated. Diagnostics only. */
+void cbqo_trace_event_heights(const uint32_t* nodes, const cbqo_subdag sd[8], const cbqo_ray* rays, uint64_t n,
+	int surf, float maxFootprint, uint64_t* hist)
+{
+	g_heightHist = hist;
+	for (uint64_t i = 0; i < n; i++) {
+		cbqo_hit h;
+		cbqo_intersect(nodes, sd, &rays[i], surf, maxFootprint, &h, NULL);
+	}
+	g_heightHist = NULL;
+}
 
 /* Event strings per ray, for the warp-scheduling simulations in DESIGN.md. events: n * cap bytes. */
 void cbqo_trace_events(const uint32_t* nodes, const cbqo_subdag sd[8], const cbqo_ray* rays, uint64_t n,

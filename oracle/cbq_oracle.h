@@ -107,4 +107,8 @@ uint32_t cbqo_fmix32(uint32_t h);
 #ifdef __cplusplus
 }
 #endif
+/* Diagnostics: events (D, A, P, H, O) by the height of the node they happen in; hist has 5 * 34 counters. */
+void cbqo_trace_event_heights(const uint32_t* nodes, const cbqo_subdag sd[8], const cbqo_ray* rays, uint64_t n,
+	int surf, float maxFootprint, uint64_t* hist);
+
 #endif
