@@ -90,11 +90,15 @@ void cbqo_find_subdags(const uint32_t* nodes, uint32_t root, cbqo_subdag out[8])
  * 'D' descend, 'A' advance within the parent, 'P' advance that pops, 'H' hit, 'O' sub-DAG entered. */
 static uint8_t* g_events = NULL;
 static uint32_t g_eventCount = 0, g_eventCap = 0;
+static int g_eventsCarryHeight = 0;       /* event byte = kind (0 D, 1 A, 2 P, 3 H, 4 O) + 8 * height instead of the letter */
 static uint64_t* g_heightHist = NULL;   /* [5][34]: events D, A, P, H, O by the height of the node they happen in */
 static int g_eventHeight = 0;
 static inline void record_event(uint8_t e)
 {
-	if (g_events && g_eventCount < g_eventCap) g_events[g_eventCount++] = e;
+	if (g_events && g_eventCount < g_eventCap) {
+		const int kind = e == 'D' ? 0 : e == 'A' ? 1 : e == 'P' ? 2 : e == 'H' ? 3 : 4;
+		g_events[g_eventCount++] = g_eventsCarryHeight ? (uint8_t)(kind + 8 * (g_eventHeight < 0 ? 0 : g_eventHeight > 31 ? 31 : g_eventHeight)) : e;
+	}
 	if (g_heightHist && g_eventHeight >= 0 && g_eventHeight < 34) {
 		const int k = e == 'D' ? 0 : e == 'A' ? 1 : e == 'P' ? 2 : e == 'H' ? 3 : 4;
 		g_heightHist[k * 34 + g_eventHeight]++;
@@ -714,3 +718,12 @@ void cbqo_trace_events(const uint32_t* nodes, const cbqo_subdag sd[8], const cbq
 	}
 	g_events = NULL;
 }
+
+void cbqo_trace_events_with_heights(const uint32_t* nodes, const cbqo_subdag sd[8], const cbqo_ray* rays, uint64_t n,
+	int surf, float maxFootprint, uint8_t* events, uint32_t cap, uint32_t* counts)
+{
+	g_eventsCarryHeight = 1;
+	cbqo_trace_events(nodes, sd, rays, n, surf, maxFootprint, events, cap, counts);
+	g_eventsCarryHeight = 0;
+}
+

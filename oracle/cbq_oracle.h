@@ -107,6 +107,14 @@ uint32_t cbqo_fmix32(uint32_t h);
 #ifdef __cplusplus
 }
 #endif
+/* Event strings per ray ('O' sub-DAG entered, 'D' descend, 'A' advance, 'P' advance + pop, 'H' hit): events is n * cap bytes. */
+void cbqo_trace_events(const uint32_t* nodes, const cbqo_subdag sd[8], const cbqo_ray* rays, uint64_t n,
+	int surf, float maxFootprint, uint8_t* events, uint32_t cap, uint32_t* counts);
+
+/* As cbqo_trace_events, but each event byte is kind (0 D, 1 A, 2 P, 3 H, 4 O) + 8 * height of the node it happens in. */
+void cbqo_trace_events_with_heights(const uint32_t* nodes, const cbqo_subdag sd[8], const cbqo_ray* rays, uint64_t n,
+	int surf, float maxFootprint, uint8_t* events, uint32_t cap, uint32_t* counts);
+
 /* Diagnostics: events (D, A, P, H, O) by the height of the node they happen in; hist has 5 * 34 counters. */
 void cbqo_trace_event_heights(const uint32_t* nodes, const cbqo_subdag sd[8], const cbqo_ray* rays, uint64_t n,
 	int surf, float maxFootprint, uint64_t* hist);
