@@ -107,6 +107,9 @@ uint32_t cbqo_fmix32(uint32_t h);
 #ifdef __cplusplus
 }
 #endif
+/* EXPERIMENT (design study): see cbq_oracle.c. 0 = off (the default; every test runs with it off). */
+void cbqo_experiment_set_brick_height(int h);
+
 /* Event strings per ray ('O' sub-DAG entered, 'D' descend, 'A' advance, 'P' advance + pop, 'H' hit): events is n * cap bytes. */
 void cbqo_trace_events(const uint32_t* nodes, const cbqo_subdag sd[8], const cbqo_ray* rays, uint64_t n,
 	int surf, float maxFootprint, uint8_t* events, uint32_t cap, uint32_t* counts);
