@@ -18,6 +18,7 @@ def main():
     from conftest import mixed_rays
     port = pyoracle.Port()
     port.lib.cbqo_experiment_set_brick_height.restype = None
+    port.lib.cbqo_experiment_set_grid_height.restype = None
     threads = 1                                   # the switch is a process-wide global: keep the comparison single-threaded per call
     for kind, log2 in (("terrain", 12), ("sphere_noise", 8), ("soup", 9), ("city", 12)):
         sc = api.Scene(kind, log2, 1)
@@ -42,6 +43,13 @@ def main():
                 if len(bad) and h == 3:
                     i = bad[0]
                     line += " (first: ray %d want %s got %s)" % (i, want[i], got[i])
+            for g in (5, 6, 7):
+                port.lib.cbqo_experiment_set_grid_height(g)
+                got, _, _ = port.trace(sc.nodes, sub, rays, True, -1.0, threads=threads)
+                port.lib.cbqo_experiment_set_grid_height(0)
+                a = got.view(np.uint32).reshape(len(rays), -1)
+                w = want.view(np.uint32).reshape(len(rays), -1)
+                line += "   top grid of %d-voxel cells: %d differ" % (1 << g, int((a != w).any(axis=1).sum()))
             print(line, flush=True)
 
 
