@@ -43,7 +43,7 @@ int fail(int code, const char* fmt, ...)
 		}                                                                                         \
 	} while (0)
 
-constexpr int kQueueSlots = 4096;      // ring of zeroed ticket counters, one per launch
+constexpr int kQueueSlots = 64;        // ticket counters, one per stream that has launched a trace (the kernel re-arms its own)
 constexpr uint64_t kPipelineChunk = 1u << 18;  // rays per host<->device pipeline stage (6 MB in, 10 MB out); 2^16 was 45 % slower end to end (API overhead per stage)
 constexpr int kStages = 3;                     // staging buffers in flight
 
@@ -115,10 +115,16 @@ struct cbq_context {
 	uint64_t generation = 0;
 	cbq::SubDag subdags[8]{};
 	int maxSubDagHeight = 0;
+	// The packed references the ray cast follows (traverse.cuh), derived from the node array on the device:
+	// nodeCapacity x 8 references of refBits bits, same indexing as the nodes.
+	uint8_t* refs = nullptr;
+	size_t refBytes = 0;
+	int refBits = 32;
 
 	// Launch bookkeeping.
-	unsigned long long* queues = nullptr; // kQueueSlots counters + 1 abandoned counter at the end
-	int queueCursor = 0;
+	unsigned long long* queues = nullptr; // kQueueSlots x {ticket counter, finished CTAs} + 1 abandoned counter at the end
+	cudaStream_t queueStream[kQueueSlots]{};
+	int queueUsed = 0;
 	cbq::LaunchConfig cfg{};
 	int l2Persist = 1;
 	cudaStream_t windowStream = nullptr;  // stream the access-policy window was last applied to
@@ -136,7 +142,6 @@ struct cbq_context {
 	float* stageAccum = nullptr;
 	size_t stageAccumBytes = 0;
 	cbq::WavefrontBuffers wavefront;
-	int renderMode = 0;   // 0 wavefront (per-bounce kernels), 1 persistent megakernel
 
 	// Cost feedback for coherent batches (refill threshold 32): the kernel records how long each 32-ray ticket
 	// took; the next launch over the same batch (same ray buffer, size and stream) deals them longest first.
@@ -163,7 +168,11 @@ struct cbq_context {
 	const uint32_t* nodesPtr() const { return reinterpret_cast<const uint32_t*>(volume + cbq::kNodeOffset); }
 	const cbq::SubDag* subdagsPtr() const { return reinterpret_cast<const cbq::SubDag*>(volume + cbq::kSubDagOffset); }
 	const float4* coloursPtr() const { return reinterpret_cast<const float4*>(volume + cbq::kColourOffset); }
-	unsigned long long* abandonedPtr() const { return queues + kQueueSlots; }
+	unsigned long long* abandonedPtr() const { return queues + 2 * kQueueSlots; }
+	cbq::VolumeView view() const
+	{
+		return cbq::VolumeView{ refs, refBits, subdagsPtr(), reinterpret_cast<const unsigned long long*>(volume + cbq::kRootRefOffset) };
+	}
 };
 
 namespace {
@@ -185,16 +194,18 @@ void poolFree(cbq_context* ctx, void* p)
 	if (p) cudaFreeAsync(p, ctx->stream);
 }
 
-// Hand out a zeroed ticket counter. The ring is re-zeroed (stream ordered) each time it wraps.
+// The ticket counter of `stream`. Launches on one stream are ordered and every trace kernel leaves its counter
+// zeroed again (its last CTA re-arms it), so a stream needs exactly one; different streams never share one.
 int nextQueue(cbq_context* ctx, cudaStream_t stream, unsigned long long** out)
 {
-	if (ctx->queueCursor == kQueueSlots) {
-		// All users of earlier slots were enqueued on streams we synchronise with here.
+	for (int i = 0; i < ctx->queueUsed; i++) if (ctx->queueStream[i] == stream) { *out = ctx->queues + 2 * i; return CBQ_OK; }
+	if (ctx->queueUsed == kQueueSlots) {
+		// More streams than slots (they may have been destroyed since): wait for everything, then start over.
 		CBQ_CUDA(cudaDeviceSynchronize());
-		CBQ_CUDA(cudaMemsetAsync(ctx->queues, 0, sizeof(unsigned long long) * kQueueSlots, stream));
-		ctx->queueCursor = 0;
+		ctx->queueUsed = 0;
 	}
-	*out = ctx->queues + ctx->queueCursor++;
+	ctx->queueStream[ctx->queueUsed] = stream;
+	*out = ctx->queues + 2 * ctx->queueUsed++;
 	return CBQ_OK;
 }
 
@@ -205,24 +216,54 @@ int writeHeaderAndSubdags(cbq_context* ctx)
 	h.magic = 0x31514243u; h.version = CBQ_VERSION;
 	h.nodeCount = ctx->nodeCount; h.nodeCapacity = ctx->nodeCapacity;
 	h.rootIndex = ctx->root; h.maxSubDagHeight = (uint32_t)ctx->maxSubDagHeight; h.generation = ctx->generation;
-	CBQ_CUDA(cudaMemcpyAsync(ctx->volume + cbq::kHeaderOffset, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+	h.refBits = (uint32_t)ctx->refBits;
+	// The root references behind byte 64 are written on the device (publishVolume).
+	CBQ_CUDA(cudaMemcpyAsync(ctx->volume + cbq::kHeaderOffset, &h, cbq::kRootRefOffset, cudaMemcpyHostToDevice, ctx->stream));
 	CBQ_CUDA(cudaMemcpyAsync(ctx->volume + cbq::kSubDagOffset, ctx->subdags, sizeof(ctx->subdags), cudaMemcpyHostToDevice, ctx->stream));
 	CBQ_CUDA(cudaStreamSynchronize(ctx->stream)); // h is on our stack
-	ctx->bytesH2D += sizeof(h) + sizeof(ctx->subdags);
+	ctx->bytesH2D += cbq::kRootRefOffset + sizeof(ctx->subdags);
 	return CBQ_OK;
 }
 
-int refreshSubdags(cbq_context* ctx, const uint32_t* nodes, uint64_t nodeCount, uint32_t root)
+// Header and sub-DAGs to the device, then the packed references of nodes [dirtyBegin, nodeCount) and of the 8
+// sub-DAG roots (pack_kernels.cu). Nodes below dirtyBegin must be unchanged since they were last packed AND must not
+// point into the dirty range -- true for copy-on-write tails (storage.cpp:152-167: a shared node is never written, so it
+// cannot have learnt about a younger node). Everything is re-packed when the buffer moved or the width changed.
+int publishVolume(cbq_context* ctx, uint64_t dirtyBegin)
 {
-	cbq::SubDag sd[8];
+	int rc = writeHeaderAndSubdags(ctx); if (rc) return rc;
+	const int bits = ctx->nodeCapacity <= (1ull << 24) ? 32 : 64;
+	const size_t bytes = (size_t)ctx->nodeCapacity * 8 * (size_t)(bits / 8);
+	if (bits != ctx->refBits || bytes > ctx->refBytes || !ctx->refs) {
+		CBQ_CUDA(cudaDeviceSynchronize());           // nobody may still be reading the old references
+		poolFree(ctx, ctx->refs); ctx->refs = nullptr; ctx->refBytes = 0;
+		CBQ_CUDA(poolAlloc(ctx, &ctx->refs, bytes));
+		ctx->refBytes = bytes; ctx->refBits = bits;
+		dirtyBegin = 0;
+		rc = writeHeaderAndSubdags(ctx); if (rc) return rc;   // refBits changed
+	}
+	CBQ_CUDA(cbq::launchPackNodes(ctx->nodesPtr(), dirtyBegin, ctx->nodeCount, ctx->refs, ctx->refBits, ctx->cfg.smCount, ctx->stream));
+	CBQ_CUDA(cbq::launchPackRoots(ctx->nodesPtr(), ctx->subdagsPtr(), reinterpret_cast<unsigned long long*>(ctx->volume + cbq::kRootRefOffset), ctx->stream));
+	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->launches += 2;
+	return CBQ_OK;
+}
+
+// Sub-DAGs of a host array, not yet adopted: callers commit them with adoptSubdags() once nothing can fail any more.
+int computeSubdags(const uint32_t* nodes, uint64_t nodeCount, uint32_t root, cbq::SubDag sd[8])
+{
 	if (!findSubDags(nodes, nodeCount, root, sd))
 		return fail(CBQ_ERROR_CORRUPT_VOLUME, "node array is not a valid DAG below root %u (child index out of range or runaway chain)", root);
+	return CBQ_OK;
+}
+
+void adoptSubdags(cbq_context* ctx, const cbq::SubDag sd[8])
+{
 	int maxH = 0;
 	for (int i = 0; i < 8; i++) if (sd[i].node > 0) maxH = std::max(maxH, sd[i].height);
-	std::memcpy(ctx->subdags, sd, sizeof(sd));
+	std::memcpy(ctx->subdags, sd, sizeof(ctx->subdags));
 	ctx->maxSubDagHeight = maxH;
 	ctx->cfg.stackLevels = maxH + 1;
-	return CBQ_OK;
 }
 
 // Pin the node array in L2 (persisting access-policy window) for kernels on `stream`.
@@ -265,7 +306,7 @@ bool orderBeforeTrace(cbq_context* ctx, cbq::TraceArgs& a, const cbq::LaunchConf
 	const uint64_t tickets = (a.count + 31) / 32;
 	const uint64_t warps = (uint64_t)cfg.smCount * cfg.blocksPerSm * (cfg.blockThreads / 32);
 	// Worth it only when a warp serves a handful of tickets (a tail exists) and one block can sort them.
-	if (!ctx->adaptiveOrder || !a.rays || a.countPtr || cfg.kernel != 0 || cfg.refillThreshold < 32 || tickets < 2 * warps || tickets > (1u << 18)) return false;
+	if (!ctx->adaptiveOrder || !a.rays || a.countPtr || cfg.refillThreshold < 32 || tickets < 2 * warps || tickets > (1u << 18)) return false;
 	if (tickets > ctx->ticketCapacity) {
 		if (cudaDeviceSynchronize() != cudaSuccess) return false;
 		cudaFree(ctx->ticketCost); cudaFree(ctx->ticketHist); cudaFree(ctx->ticketOrder[0]); cudaFree(ctx->ticketOrder[1]);
@@ -310,7 +351,7 @@ int traceDevice(cbq_context* ctx, const cbq::Ray* dRays, uint64_t n, uint32_t fl
 	if (n == 0) return CBQ_OK;
 	cbq::TraceArgs a;
 	std::memset(&a, 0, sizeof(a));
-	a.nodes = ctx->nodesPtr(); a.subdags = ctx->subdagsPtr();
+	a.volume = ctx->view();
 	a.rays = dRays; a.hits = dHits; a.count = n; a.maxFootprint = maxFootprint;
 	a.abandoned = ctx->abandonedPtr();
 	if (cam) { a.camera = *cam; a.width = width; a.height = height; }
@@ -391,7 +432,7 @@ int bakeAndInstall(cbq_context* ctx, const uint32_t* dNodes, uint64_t n, uint32_
 	for (int i = 0; i < 8; i++) if (ctx->subdags[i].node > 0) maxH = std::max(maxH, ctx->subdags[i].height);
 	ctx->maxSubDagHeight = maxH;
 	ctx->cfg.stackLevels = maxH + 1;
-	return writeHeaderAndSubdags(ctx);
+	return publishVolume(ctx, 0);
 }
 
 // findSubDAGs on the device copy for `root` (read from *dRoot when dRoot != nullptr), result adopted by the context.
@@ -474,14 +515,13 @@ int cbq_create(int device, cbq_context** out)
 		CBQ_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
 	}
 	CBQ_CUDA(cudaEventCreateWithFlags(&ctx->orderEvent, cudaEventDisableTiming));
-	CBQ_CUDA(cudaMalloc(&ctx->queues, sizeof(unsigned long long) * (kQueueSlots + 1)));
-	CBQ_CUDA(cudaMemset(ctx->queues, 0, sizeof(unsigned long long) * (kQueueSlots + 1)));
+	CBQ_CUDA(cudaMalloc(&ctx->queues, sizeof(unsigned long long) * (2 * kQueueSlots + 1)));
+	CBQ_CUDA(cudaMemset(ctx->queues, 0, sizeof(unsigned long long) * (2 * kQueueSlots + 1)));
 	ctx->cfg.blockThreads = 256;
 	ctx->cfg.blocksPerSm = 4;
 	ctx->cfg.smCount = ctx->prop.multiProcessorCount;
 	ctx->cfg.refillThreshold = 8;    // robust default: +68 % on incoherent rays, -7 % on coherent ones (profiles/r01_sweeps.md)
 	ctx->cfg.refillQuantum = 1;
-	ctx->cfg.kernel = 0;
 	ctx->cfg.stackLevels = 33;
 	ctx->cfg.sampleGroup = 0;    // auto; 1080p, 4 bounces: 512 / 734 / 789 / 812 M spp/s for groups of 1 / 4 / 8 / 16 (profiles/r01_analysis.md)
 	*out = ctx;
@@ -505,6 +545,7 @@ void cbq_destroy(cbq_context* ctx)
 	if (ctx->orderEvent) cudaEventDestroy(ctx->orderEvent);
 	cbq::wavefrontRelease(ctx->wavefront);
 	cudaFree(ctx->queues);
+	poolFree(ctx, ctx->refs);
 	poolFree(ctx, ctx->volume);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
@@ -537,26 +578,28 @@ int cbq_upload(cbq_context* ctx, const uint32_t* nodes, uint64_t node_count, uin
 	if (node_count > 0xffffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "node indices are 32-bit");
 	if (!childrenInRange(nodes, 0, node_count, node_count))
 		return fail(CBQ_ERROR_CORRUPT_VOLUME, "a child index is >= the node count %llu", (unsigned long long)node_count);
-	rc = refreshSubdags(ctx, nodes, node_count, root_index); if (rc) return rc;
+	cbq::SubDag sd[8];
+	rc = computeSubdags(nodes, node_count, root_index, sd); if (rc) return rc;
 
 	// Head-room for copy-on-write growth so that edits rarely force a reallocation.
 	const uint64_t capacity = node_count + std::max<uint64_t>(node_count / 4, 1u << 16);
 	const size_t bytes = cbq::kNodeOffset + (size_t)capacity * 32;
-	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	CBQ_CUDA(cudaDeviceSynchronize());   // a kernel on a caller's stream may still be reading the volume
 	if (bytes > ctx->volumeBytes) {
-		if (ctx->volume) { CBQ_CUDA(cudaDeviceSynchronize()); poolFree(ctx, ctx->volume); ctx->volume = nullptr; ctx->volumeBytes = 0; }
+		if (ctx->volume) { poolFree(ctx, ctx->volume); ctx->volume = nullptr; ctx->volumeBytes = 0; ctx->nodeCount = 0; }
 		CBQ_CUDA(poolAlloc(ctx, &ctx->volume, bytes));
 		ctx->volumeBytes = bytes;
 	}
+	CBQ_CUDA(cudaMemcpyAsync(ctx->volume + cbq::kNodeOffset, nodes, (size_t)node_count * 32, cudaMemcpyHostToDevice, ctx->stream));
+	ctx->bytesH2D += node_count * 32;
 	ctx->nodeCapacity = (ctx->volumeBytes - cbq::kNodeOffset) / 32;
 	ctx->nodeCount = node_count;
 	ctx->root = root_index;
 	ctx->generation++;
 	ctx->deviceDiverged = false;
-	CBQ_CUDA(cudaMemcpyAsync(ctx->volume + cbq::kNodeOffset, nodes, (size_t)node_count * 32, cudaMemcpyHostToDevice, ctx->stream));
-	ctx->bytesH2D += node_count * 32;
+	adoptSubdags(ctx, sd);
 	rc = cbq_set_colours(ctx, colours_rgb); if (rc) return rc;
-	return writeHeaderAndSubdags(ctx);
+	return publishVolume(ctx, 0);
 }
 
 int cbq_update(cbq_context* ctx, const uint32_t* nodes, uint64_t dirty_begin, uint64_t node_count, uint32_t root_index)
@@ -570,14 +613,14 @@ int cbq_update(cbq_context* ctx, const uint32_t* nodes, uint64_t dirty_begin, ui
 	if (node_count > 0xffffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "node indices are 32-bit");
 	if (!childrenInRange(nodes, dirty_begin, node_count, node_count))
 		return fail(CBQ_ERROR_CORRUPT_VOLUME, "a child index in the dirty tail is >= the node count %llu", (unsigned long long)node_count);
-	rc = refreshSubdags(ctx, nodes, node_count, root_index); if (rc) return rc;
-	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	cbq::SubDag sd[8];
+	rc = computeSubdags(nodes, node_count, root_index, sd); if (rc) return rc;
+	CBQ_CUDA(cudaDeviceSynchronize());   // a kernel on a caller's stream may still be reading the tail we overwrite
 	if (node_count > ctx->nodeCapacity) {
 		// Out of head-room: grow, keeping the clean prefix that is already on the device.
 		const uint64_t capacity = node_count + std::max<uint64_t>(node_count / 4, 1u << 16);
 		const size_t bytes = cbq::kNodeOffset + (size_t)capacity * 32;
 		uint8_t* bigger = nullptr;
-		CBQ_CUDA(cudaDeviceSynchronize());
 		CBQ_CUDA(poolAlloc(ctx, &bigger, bytes));
 		CBQ_CUDA(cudaMemcpyAsync(bigger, ctx->volume, cbq::kNodeOffset + (size_t)dirty_begin * 32, cudaMemcpyDeviceToDevice, ctx->stream));
 		poolFree(ctx, ctx->volume);
@@ -592,7 +635,8 @@ int cbq_update(cbq_context* ctx, const uint32_t* nodes, uint64_t dirty_begin, ui
 	ctx->nodeCount = node_count;
 	ctx->root = root_index;
 	ctx->generation++;
-	return writeHeaderAndSubdags(ctx);
+	adoptSubdags(ctx, sd);
+	return publishVolume(ctx, dirty_begin);
 }
 
 int cbq_bake(cbq_context* ctx, uint64_t* node_count, uint32_t* root_index)
@@ -656,7 +700,7 @@ int cbq_fill_sphere(cbq_context* ctx, float x, float y, float z, float radius, u
 	int rc = bind(ctx); if (rc) return rc;
 	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "cbq_fill_sphere before cbq_upload");
 	if (!(radius >= 0.0f)) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad radius");
-	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	CBQ_CUDA(cudaDeviceSynchronize());   // header, sub-DAGs and root references change in place
 	uint32_t listCapacity = 1u << 16;
 	for (int attempt = 0; attempt < 8; attempt++) {
 		if (ctx->nodeCapacity < ctx->nodeCount + 4096) { rc = growVolume(ctx, ctx->nodeCount + std::max<uint64_t>(ctx->nodeCount / 4, 1u << 16)); if (rc) return rc; }
@@ -696,7 +740,8 @@ int cbq_fill_sphere(cbq_context* ctx, float x, float y, float z, float radius, u
 		ctx->deviceDiverged = true;
 		if (root_index) *root_index = ctx->root;
 		if (node_count) *node_count = ctx->nodeCount;
-		return writeHeaderAndSubdags(ctx);
+		// The stroke only appended nodes (and re-pointed children inside what it appended).
+		return publishVolume(ctx, oldCount);
 	}
 	return fail(CBQ_ERROR_OUT_OF_MEMORY, "cbq_fill_sphere: could not make room for the edit");
 }
@@ -706,7 +751,7 @@ int cbq_set_root(cbq_context* ctx, uint32_t root_index)
 	int rc = bind(ctx); if (rc) return rc;
 	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "cbq_set_root before cbq_upload");
 	if (root_index >= ctx->nodeCount) return fail(CBQ_ERROR_INVALID_ARGUMENT, "root %u is past the %llu nodes on the device", root_index, (unsigned long long)ctx->nodeCount);
-	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	CBQ_CUDA(cudaDeviceSynchronize());   // sub-DAGs and root references change in place
 	uint8_t* work = nullptr;
 	CBQ_CUDA(poolAlloc(ctx, &work, 1024));
 	const uint32_t oldRoot = ctx->root;
@@ -715,7 +760,7 @@ int cbq_set_root(cbq_context* ctx, uint32_t root_index)
 	poolFree(ctx, work);
 	if (rc) { ctx->root = oldRoot; return rc; }
 	ctx->generation++;
-	return writeHeaderAndSubdags(ctx);
+	return publishVolume(ctx, ctx->nodeCount);
 }
 
 int cbq_set_colours(cbq_context* ctx, const float* colours_rgb)
@@ -884,14 +929,13 @@ int cbq_raycast_frame_device(cbq_context* ctx, const cbq_camera* cam, uint32_t w
 		ctx->launches++;
 		cbq::TraceArgs a;
 		std::memset(&a, 0, sizeof(a));
-		a.nodes = ctx->nodesPtr(); a.subdags = ctx->subdagsPtr();
+		a.volume = ctx->view();
 		a.rays = ctx->frameRays; a.hits = reinterpret_cast<cbq::Hit*>(d_hits); a.count = n; a.maxFootprint = max_footprint;
 		a.abandoned = ctx->abandonedPtr(); a.untileWidth = width;
 		rc = nextQueue(ctx, s, &a.queue); if (rc) return rc;
 		applyL2Window(ctx, s);
 		cbq::LaunchConfig cfg = ctx->cfg;
 		cfg.refillThreshold = 32;
-		cfg.kernel = 0;
 		const bool feedback = orderBeforeTrace(ctx, a, cfg, s);
 		CBQ_CUDA(cbq::launchTrace(a, (flags & CBQ_TRACE_SURFACE) != 0, cfg, s));
 		ctx->launches++;
@@ -917,15 +961,9 @@ int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_para
 	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
 	cbq::RenderArgs a;
 	std::memset(&a, 0, sizeof(a));
-	a.nodes = ctx->nodesPtr(); a.subdags = ctx->subdagsPtr(); a.colours = ctx->coloursPtr();
+	a.volume = ctx->view(); a.colours = ctx->coloursPtr();
 	a.camera = *cam; a.params = *p; a.accum = d_accum; a.abandoned = ctx->abandonedPtr();
 	applyL2Window(ctx, s);
-	if (ctx->renderMode == 1) {
-		rc = nextQueue(ctx, s, &a.queue); if (rc) return rc;
-		CBQ_CUDA(cbq::launchRender(a, ctx->cfg, s));
-		ctx->launches++;
-		return CBQ_OK;
-	}
 	const size_t pixels = (size_t)(p->x1 - p->x0) * cbq::bandedRowCount(p->y1 - p->y0, p->band_count, p->band_index);
 	if (pixels == 0) return CBQ_OK;
 	// Samples traced together. 0 = auto: aim at ~16 M paths per wave (8 samples of a 1080p frame, 16 of a
@@ -1003,15 +1041,9 @@ int cbq_set_option(cbq_context* ctx, const char* key, int64_t value)
 	} else if (k == "refill_quantum") {
 		if (value < 1 || value > 32 || (value & (value - 1)) != 0) return fail(CBQ_ERROR_INVALID_ARGUMENT, "refill_quantum must be a power of two in [1, 32]");
 		ctx->cfg.refillQuantum = (int)value;
-	} else if (k == "kernel") {
-		if (value < 0 || value > 1) return fail(CBQ_ERROR_INVALID_ARGUMENT, "kernel must be 0 or 1");
-		ctx->cfg.kernel = (int)value;
 	} else if (k == "sample_group") {
 		if (value < 0 || value > 16) return fail(CBQ_ERROR_INVALID_ARGUMENT, "sample_group must be 0 (auto) or in [1, 16]");
 		ctx->cfg.sampleGroup = (int)value;
-	} else if (k == "render_mode") {
-		if (value < 0 || value > 1) return fail(CBQ_ERROR_INVALID_ARGUMENT, "render_mode must be 0 (wavefront) or 1 (megakernel)");
-		ctx->renderMode = (int)value;
 	} else if (k == "order_refresh") {
 		if (value < 1 || value > 1024) return fail(CBQ_ERROR_INVALID_ARGUMENT, "order_refresh must be in [1, 1024]");
 		ctx->orderRefresh = (int)value;
@@ -1034,12 +1066,11 @@ int cbq_get_option(cbq_context* ctx, const char* key, int64_t* value)
 	if (k == "block_threads") *value = ctx->cfg.blockThreads;
 	else if (k == "blocks_per_sm") *value = ctx->cfg.blocksPerSm;
 	else if (k == "refill_threshold") *value = ctx->cfg.refillThreshold;
-	else if (k == "kernel") *value = ctx->cfg.kernel;
 	else if (k == "refill_quantum") *value = ctx->cfg.refillQuantum;
 	else if (k == "l2_persist") *value = ctx->l2Persist;
 	else if (k == "adaptive_order") *value = ctx->adaptiveOrder;
 	else if (k == "order_refresh") *value = ctx->orderRefresh;
-	else if (k == "render_mode") *value = ctx->renderMode;
+	else if (k == "ref_bits") *value = ctx->refBits;
 	else if (k == "sample_group") *value = ctx->cfg.sampleGroup;
 	else if (k == "sm_count") *value = ctx->cfg.smCount;
 	else if (k == "stack_levels") *value = ctx->cfg.stackLevels;

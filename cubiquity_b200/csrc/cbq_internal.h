@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/cubiquity_b200.h"
@@ -10,11 +11,14 @@
 namespace cbq {
 
 // Layout of the ONE linear device buffer a volume lives in (cbq_upload):
-//   [0, 256)        VolumeHeader
+//   [0, 256)        VolumeHeader (the packed references of the 8 sub-DAG roots at byte 64)
 //   [256, 512)      SubDag[8]
 //   [512, 4608)     float4 colours[256]   (rgb + pad, so a material colour is one 16-byte load)
-//   [4608, ...)     nodes, 32 bytes each, 128-byte aligned start => every node is one L2 sector
+//   [4608, ...)     nodes, 32 bytes each, 128-byte aligned start => every node is one L2 sector:
+//                   nodeCapacity nodes in the reference's layout (what edits, bake and download work on), then,
+//                   128-byte aligned, nodeCapacity x 8 packed references (traverse.cuh) -- what the ray cast reads
 constexpr size_t kHeaderOffset = 0;
+constexpr size_t kRootRefOffset = 64;
 constexpr size_t kSubDagOffset = 256;
 constexpr size_t kColourOffset = 512;
 constexpr size_t kNodeOffset = 4608;
@@ -27,8 +31,12 @@ struct VolumeHeader {
 	uint32_t rootIndex;
 	uint32_t maxSubDagHeight;
 	uint64_t generation;   // bumped by every upload / update
-	uint8_t pad[256 - 40];
+	uint32_t refBits;      // width of a packed reference: 32 while nodeCapacity <= 2^24, else 64
+	uint8_t pad0[kRootRefOffset - 44];
+	uint64_t rootRefs[8];  // written on the device (packRoots)
+	uint8_t pad1[256 - kRootRefOffset - 64];
 };
+static_assert(offsetof(VolumeHeader, rootRefs) == kRootRefOffset, "root references at byte 64");
 static_assert(sizeof(VolumeHeader) == 256, "header is 256 bytes");
 
 // Row l of a banded rectangle -> image row: bands of 64 rows counted from y0, this share owns every
@@ -52,19 +60,25 @@ struct LaunchConfig {
 	int smCount;
 	int refillThreshold;   // idle lanes in a warp that trigger a refill from the ray queue (1..32)
 	int refillQuantum;     // tickets are dealt in whole groups of this many (1, 2, 4, 8, 16 or 32)
-	int kernel;            // 0 persistent queue kernel, 1 one-thread-per-ray
 	int stackLevels;       // entries per lane in the shared-memory stack (max sub-DAG height + 1)
 	int sampleGroup;       // wavefront path tracer: samples of a pixel traced together (1..16)
 };
 
+// What a kernel needs to know about the uploaded volume (device pointers into the volume buffer).
+struct VolumeView {
+	const void* refs;                      // packed references, 8 per node: uint32_t or uint64_t by refBits
+	int refBits;
+	const SubDag* subdags;
+	const unsigned long long* rootRefs;    // packed references of the 8 sub-DAG roots
+};
+
 struct TraceArgs {
-	const uint32_t* nodes;
-	const SubDag* subdags;       // device pointer into the volume buffer
+	VolumeView volume;
 	const Ray* rays;             // nullptr => generate from the camera
 	Hit* hits;
 	uint64_t count;
 	float maxFootprint;
-	unsigned long long* queue;   // one zeroed 64-bit ticket counter for this launch
+	unsigned long long* queue;   // [0] ticket counter, [1] finished CTAs; both zero, re-armed by the kernel itself
 	unsigned long long* abandoned; // device counter, incremented per abandoned ray
 	// camera source (rays == nullptr): image size and the pixel rectangle to trace (0 = whole image)
 	cbq_camera camera;
@@ -87,16 +101,13 @@ cudaError_t launchPrimaryRays(const cbq_camera& cam, uint32_t width, uint32_t he
 cudaError_t launchRandomRays(uint64_t seed, const float lower[3], const float upper[3], uint64_t n, Ray* rays, cudaStream_t stream);
 
 struct RenderArgs {
-	const uint32_t* nodes;
-	const SubDag* subdags;
+	VolumeView volume;
 	const float4* colours;
 	cbq_camera camera;
 	cbq_pt_params params;
 	float* accum;
-	unsigned long long* queue;
 	unsigned long long* abandoned;
 };
-cudaError_t launchRender(const RenderArgs& a, const LaunchConfig& cfg, cudaStream_t stream);
 
 // Wavefront path tracer (wavefront_kernels.cu): per-bounce kernels around the ray-cast kernel.
 struct WavefrontBuffers {
@@ -120,6 +131,10 @@ void wavefrontRelease(WavefrontBuffers& b);
 typedef int (*QueueFn)(void* user, cudaStream_t stream, unsigned long long** out);
 cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, const LaunchConfig& cfg, cudaStream_t stream,
 	QueueFn nextQueue, void* user, uint64_t* launches);
+
+// Packed references (pack_kernels.cu): refs[begin * 8 .. end * 8) from the reference-layout nodes; the 8 root references.
+cudaError_t launchPackNodes(const uint32_t* nodes, uint64_t begin, uint64_t end, void* refs, int refBits, int smCount, cudaStream_t stream);
+cudaError_t launchPackRoots(const uint32_t* nodes, const SubDag* subdags, unsigned long long* rootRefs, cudaStream_t stream);
 
 // Device-side bake (bake_kernels.cu).
 size_t bakeScratchBytes(uint64_t nodeCount, uint64_t* tableSlots);

@@ -22,8 +22,8 @@
 // The number of survivors never visits the host: shade leaves it in a device counter and the next
 // trace / light kernels read their batch size from there, so a wave is a fixed sequence of launches
 // on one stream. Paths are independent and each pixel has exactly one path per wave, so the order
-// in which compaction packs them cannot change any result: images are bit-identical to the
-// persistent megakernel (pathtrace_kernels.cu) and, for the recursive variant, to the oracle.
+// in which compaction packs them cannot change any result: for the recursive variant images are
+// bit-identical to the oracle.
 //
 // Why no sort of the secondary rays: the ray-cast kernel is issue-bound, not memory-bound, and with
 // mid-flight lane refill it traces incoherent rays as fast as coherent ones (4.5 vs 4.4 Grays/s,
@@ -247,7 +247,8 @@ int wavefrontReserve(WavefrontBuffers& b, size_t pixels /* paths */)
 {
 	if (pixels <= b.pixelCapacity) return (int)cudaSuccess;
 	cudaError_t e;
-#define CBQ_TRY(x) do { e = (x); if (e != cudaSuccess) return (int)e; } while (0)
+	// Every buffer is freed before it is re-allocated: on a failure half-way nothing may be left looking usable.
+#define CBQ_TRY(x) do { e = (x); if (e != cudaSuccess) { wavefrontRelease(b); return (int)e; } } while (0)
 	CBQ_TRY(grow(b.hits, pixels));
 	for (int i = 0; i < 2; i++) { CBQ_TRY(grow(b.rays[i], pixels)); CBQ_TRY(grow(b.pixel[i], pixels)); CBQ_TRY(grow(b.rng[i], pixels)); }
 	CBQ_TRY(grow(b.sunTerm, pixels));
@@ -300,7 +301,7 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 			// ---- surface rays of this depth
 			TraceArgs t;
 			memset(&t, 0, sizeof(t));
-			t.nodes = a.nodes; t.subdags = a.subdags; t.hits = b.hits; t.maxFootprint = p.max_footprint; t.abandoned = a.abandoned;
+			t.volume = a.volume; t.hits = b.hits; t.maxFootprint = p.max_footprint; t.abandoned = a.abandoned;
 			if (nextQueue(user, stream, &t.queue) != 0) return cudaErrorUnknown;
 			if (d == 0) {
 				// one primary ray per PIXEL: the samples of the group share it
@@ -324,7 +325,7 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 			if (w.shadowsPerPath) {
 				TraceArgs sh;
 				memset(&sh, 0, sizeof(sh));
-				sh.nodes = a.nodes; sh.subdags = a.subdags; sh.rays = b.shadowRays; sh.flags = b.shadowFlags;
+				sh.volume = a.volume; sh.rays = b.shadowRays; sh.flags = b.shadowFlags;
 				sh.maxFootprint = p.max_footprint; sh.abandoned = a.abandoned;
 				sh.countPtr = b.counters + d; sh.countScale = w.shadowsPerPath; sh.count = (uint64_t)w.paths * w.shadowsPerPath;
 				if (nextQueue(user, stream, &sh.queue) != 0) return cudaErrorUnknown;

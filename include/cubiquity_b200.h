@@ -237,8 +237,7 @@ int cbq_host_alloc(void** out, uint64_t bytes);
 int cbq_host_free(void* p);
 
 /* Options: "block_threads", "blocks_per_sm", "refill_threshold" (idle lanes of a warp that trigger a
- * mid-flight refill, 1..32), "l2_persist" (0/1), "kernel" (0 = persistent queue kernel, 1 = plain
- * one-thread-per-ray), "render_mode" (0 = wavefront path tracer, 1 = persistent megakernel), "sample_group" (samples of a
+ * mid-flight refill, 1..32), "l2_persist" (0/1), "sample_group" (samples of a
  * pixel the wavefront tracer traces together, 1..16; 0 = choose from the size of the rectangle),
  * "adaptive_order" (0/1, default 1: coherent batches -- refill_threshold 32, cbq_raycast_frame_device -- record how
  * long each 32-ray ticket took, and the next launch over the same ray buffer, size and stream deals the tickets

@@ -110,25 +110,6 @@ def test_render_device_pointer_and_sample_sharding(gpu, port, api, scenes):
     assert np.array_equal(c.cpu().numpy(), whole)
 
 
-@pytest.mark.parametrize("variant,bounces", [(0, 1), (1, 0), (1, 3)])
-def test_wavefront_and_megakernel_agree_bit_for_bit(gpu, port, api, scenes, variant, bounces):
-    """render_mode 0 (per-bounce kernels, compaction between bounces) and 1 (one persistent kernel) are two
-    schedules of the same arithmetic: identical images, including the one-bounce variant's powf."""
-    sc = scenes("soup", 8)
-    gpu.upload(sc.nodes, sc.root, sc.colours)
-    cam, _ = both_cameras(api, port, sc)
-    p = api.pt_params(200, 120, spp=3, bounces=bounces, variant=variant, rect=(8, 4, 197, 118))
-    imgs = []
-    try:
-        for mode in (0, 1):
-            gpu.set_option("render_mode", mode)
-            imgs.append(gpu.render(cam, p))
-    finally:
-        gpu.set_option("render_mode", 0)
-    assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32))
-    assert imgs[0][4:118, 8:197].std() > 0.05 and not imgs[0][:4].any() and not imgs[0][:, :8].any()
-
-
 def test_sample_group_size_does_not_change_the_image(gpu, port, api, scenes):
     sc = scenes("sphere_noise", 7)
     gpu.upload(sc.nodes, sc.root, sc.colours)
@@ -145,29 +126,24 @@ def test_sample_group_size_does_not_change_the_image(gpu, port, api, scenes):
         assert np.array_equal(im.view(np.uint32), imgs[0].view(np.uint32))
 
 
-@pytest.mark.parametrize("mode", [0, 1])
-def test_band_interleaved_shares_tile_the_frame_exactly(gpu, port, api, scenes, mode):
+def test_band_interleaved_shares_tile_the_frame_exactly(gpu, port, api, scenes):
     """Round-robin tile sharding in ONE call per GPU: `bands=(count, index)` renders every count-th 64-row
     band. The shares are disjoint, cover the frame, and sum to the whole-frame render bit for bit."""
     sc = scenes("sphere_noise", 7)
     gpu.upload(sc.nodes, sc.root, sc.colours)
     cam, _ = both_cameras(api, port, sc)
     w, h = 90, 200            # 4 bands: 64 + 64 + 64 + 8 rows
-    try:
-        gpu.set_option("render_mode", mode)
-        whole = gpu.render(cam, api.pt_params(w, h, spp=2, bounces=2, variant=1))
-        for count in (2, 3, 8):
-            total = np.zeros_like(whole)
-            for index in range(count):
-                share = gpu.render(cam, api.pt_params(w, h, spp=2, bounces=2, variant=1, bands=(count, index)))
-                rows = np.array([((y // 64) % count) == index for y in range(h)])
-                assert not share[~rows].any()                       # nothing outside the share
-                assert np.array_equal(share[rows], whole[rows])     # and exactly the frame inside it
-                total += share
-            assert np.array_equal(total, whole)
-        # a banded sub-rectangle
-        part = gpu.render(cam, api.pt_params(w, h, spp=2, bounces=2, variant=1, rect=(10, 30, 80, 190), bands=(2, 1)))
-        rows = np.array([30 <= y < 190 and (((y - 30) // 64) % 2) == 1 for y in range(h)])
-        assert np.array_equal(part[rows][:, 10:80], whole[rows][:, 10:80]) and not part[~rows].any() and not part[:, :10].any()
-    finally:
-        gpu.set_option("render_mode", 0)
+    whole = gpu.render(cam, api.pt_params(w, h, spp=2, bounces=2, variant=1))
+    for count in (2, 3, 8):
+        total = np.zeros_like(whole)
+        for index in range(count):
+            share = gpu.render(cam, api.pt_params(w, h, spp=2, bounces=2, variant=1, bands=(count, index)))
+            rows = np.array([((y // 64) % count) == index for y in range(h)])
+            assert not share[~rows].any()                       # nothing outside the share
+            assert np.array_equal(share[rows], whole[rows])     # and exactly the frame inside it
+            total += share
+        assert np.array_equal(total, whole)
+    # a banded sub-rectangle
+    part = gpu.render(cam, api.pt_params(w, h, spp=2, bounces=2, variant=1, rect=(10, 30, 80, 190), bands=(2, 1)))
+    rows = np.array([30 <= y < 190 and (((y - 30) // 64) % 2) == 1 for y in range(h)])
+    assert np.array_equal(part[rows][:, 10:80], whole[rows][:, 10:80]) and not part[~rows].any() and not part[:, :10].any()

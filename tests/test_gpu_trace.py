@@ -48,7 +48,7 @@ def test_ragged_batch_sizes(gpu, port, scenes, n):
         assert_hits_identical(got, oracle_hits(port, sc, rays, True, -1.0), "n=%d" % n)
 
 
-@pytest.mark.parametrize("option,value", [("kernel", 1), ("refill_threshold", 1), ("refill_threshold", 32),
+@pytest.mark.parametrize("option,value", [("refill_threshold", 1), ("refill_threshold", 32), ("block_threads", 32), ("block_threads", 64),
                                           ("block_threads", 128), ("blocks_per_sm", 2), ("l2_persist", 0)])
 def test_every_kernel_configuration_agrees(gpu, port, scenes, option, value):
     sc = scenes("terrain", 9)
@@ -255,7 +255,7 @@ def test_error_codes_and_option_validation(gpu, api, scenes):
             fresh.render(api.camera_from_pose([0, 0, 0], 0, 0), api.pt_params(8, 8))
         assert e.value.code == api.ERROR_NO_VOLUME
         for key, bad in [("block_threads", 100), ("block_threads", 512), ("blocks_per_sm", 0), ("refill_threshold", 33),
-                         ("kernel", 2), ("render_mode", 5), ("sample_group", 17), ("no_such_option", 1)]:
+                         ("sample_group", 17), ("no_such_option", 1)]:
             with pytest.raises(api.CubiquityError) as e:
                 fresh.set_option(key, bad)
             assert e.value.code == api.ERROR_INVALID_ARGUMENT
