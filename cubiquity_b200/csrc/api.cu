@@ -115,11 +115,6 @@ struct cbq_context {
 	uint64_t generation = 0;
 	cbq::SubDag subdags[8]{};
 	int maxSubDagHeight = 0;
-	// The packed references the ray cast follows (traverse.cuh), derived from the node array on the device:
-	// nodeCapacity x 8 references of refBits bits, same indexing as the nodes.
-	uint8_t* refs = nullptr;
-	size_t refBytes = 0;
-	int refBits = 32;
 
 	// Launch bookkeeping.
 	unsigned long long* queues = nullptr; // kQueueSlots x {ticket counter, finished CTAs} + 1 abandoned counter at the end
@@ -171,7 +166,7 @@ struct cbq_context {
 	unsigned long long* abandonedPtr() const { return queues + 2 * kQueueSlots; }
 	cbq::VolumeView view() const
 	{
-		return cbq::VolumeView{ refs, refBits, subdagsPtr(), reinterpret_cast<const unsigned long long*>(volume + cbq::kRootRefOffset) };
+		return cbq::VolumeView{ nodesPtr(), subdagsPtr() };
 	}
 };
 
@@ -216,36 +211,10 @@ int writeHeaderAndSubdags(cbq_context* ctx)
 	h.magic = 0x31514243u; h.version = CBQ_VERSION;
 	h.nodeCount = ctx->nodeCount; h.nodeCapacity = ctx->nodeCapacity;
 	h.rootIndex = ctx->root; h.maxSubDagHeight = (uint32_t)ctx->maxSubDagHeight; h.generation = ctx->generation;
-	h.refBits = (uint32_t)ctx->refBits;
-	// The root references behind byte 64 are written on the device (publishVolume).
-	CBQ_CUDA(cudaMemcpyAsync(ctx->volume + cbq::kHeaderOffset, &h, cbq::kRootRefOffset, cudaMemcpyHostToDevice, ctx->stream));
+	CBQ_CUDA(cudaMemcpyAsync(ctx->volume + cbq::kHeaderOffset, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
 	CBQ_CUDA(cudaMemcpyAsync(ctx->volume + cbq::kSubDagOffset, ctx->subdags, sizeof(ctx->subdags), cudaMemcpyHostToDevice, ctx->stream));
 	CBQ_CUDA(cudaStreamSynchronize(ctx->stream)); // h is on our stack
-	ctx->bytesH2D += cbq::kRootRefOffset + sizeof(ctx->subdags);
-	return CBQ_OK;
-}
-
-// Header and sub-DAGs to the device, then the packed references of nodes [dirtyBegin, nodeCount) and of the 8
-// sub-DAG roots (pack_kernels.cu). Nodes below dirtyBegin must be unchanged since they were last packed AND must not
-// point into the dirty range -- true for copy-on-write tails (storage.cpp:152-167: a shared node is never written, so it
-// cannot have learnt about a younger node). Everything is re-packed when the buffer moved or the width changed.
-int publishVolume(cbq_context* ctx, uint64_t dirtyBegin)
-{
-	int rc = writeHeaderAndSubdags(ctx); if (rc) return rc;
-	const int bits = ctx->nodeCapacity <= (1ull << 24) ? 32 : 64;
-	const size_t bytes = (size_t)ctx->nodeCapacity * 8 * (size_t)(bits / 8);
-	if (bits != ctx->refBits || bytes > ctx->refBytes || !ctx->refs) {
-		CBQ_CUDA(cudaDeviceSynchronize());           // nobody may still be reading the old references
-		poolFree(ctx, ctx->refs); ctx->refs = nullptr; ctx->refBytes = 0;
-		CBQ_CUDA(poolAlloc(ctx, &ctx->refs, bytes));
-		ctx->refBytes = bytes; ctx->refBits = bits;
-		dirtyBegin = 0;
-		rc = writeHeaderAndSubdags(ctx); if (rc) return rc;   // refBits changed
-	}
-	CBQ_CUDA(cbq::launchPackNodes(ctx->nodesPtr(), dirtyBegin, ctx->nodeCount, ctx->refs, ctx->refBits, ctx->cfg.smCount, ctx->stream));
-	CBQ_CUDA(cbq::launchPackRoots(ctx->nodesPtr(), ctx->subdagsPtr(), reinterpret_cast<unsigned long long*>(ctx->volume + cbq::kRootRefOffset), ctx->stream));
-	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
-	ctx->launches += 2;
+	ctx->bytesH2D += sizeof(h) + sizeof(ctx->subdags);
 	return CBQ_OK;
 }
 
@@ -432,7 +401,7 @@ int bakeAndInstall(cbq_context* ctx, const uint32_t* dNodes, uint64_t n, uint32_
 	for (int i = 0; i < 8; i++) if (ctx->subdags[i].node > 0) maxH = std::max(maxH, ctx->subdags[i].height);
 	ctx->maxSubDagHeight = maxH;
 	ctx->cfg.stackLevels = maxH + 1;
-	return publishVolume(ctx, 0);
+	return writeHeaderAndSubdags(ctx);
 }
 
 // findSubDAGs on the device copy for `root` (read from *dRoot when dRoot != nullptr), result adopted by the context.
@@ -545,7 +514,6 @@ void cbq_destroy(cbq_context* ctx)
 	if (ctx->orderEvent) cudaEventDestroy(ctx->orderEvent);
 	cbq::wavefrontRelease(ctx->wavefront);
 	cudaFree(ctx->queues);
-	poolFree(ctx, ctx->refs);
 	poolFree(ctx, ctx->volume);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
@@ -599,7 +567,7 @@ int cbq_upload(cbq_context* ctx, const uint32_t* nodes, uint64_t node_count, uin
 	ctx->deviceDiverged = false;
 	adoptSubdags(ctx, sd);
 	rc = cbq_set_colours(ctx, colours_rgb); if (rc) return rc;
-	return publishVolume(ctx, 0);
+	return writeHeaderAndSubdags(ctx);
 }
 
 int cbq_update(cbq_context* ctx, const uint32_t* nodes, uint64_t dirty_begin, uint64_t node_count, uint32_t root_index)
@@ -636,7 +604,7 @@ int cbq_update(cbq_context* ctx, const uint32_t* nodes, uint64_t dirty_begin, ui
 	ctx->root = root_index;
 	ctx->generation++;
 	adoptSubdags(ctx, sd);
-	return publishVolume(ctx, dirty_begin);
+	return writeHeaderAndSubdags(ctx);
 }
 
 int cbq_bake(cbq_context* ctx, uint64_t* node_count, uint32_t* root_index)
@@ -740,8 +708,7 @@ int cbq_fill_sphere(cbq_context* ctx, float x, float y, float z, float radius, u
 		ctx->deviceDiverged = true;
 		if (root_index) *root_index = ctx->root;
 		if (node_count) *node_count = ctx->nodeCount;
-		// The stroke only appended nodes (and re-pointed children inside what it appended).
-		return publishVolume(ctx, oldCount);
+		return writeHeaderAndSubdags(ctx);
 	}
 	return fail(CBQ_ERROR_OUT_OF_MEMORY, "cbq_fill_sphere: could not make room for the edit");
 }
@@ -760,7 +727,7 @@ int cbq_set_root(cbq_context* ctx, uint32_t root_index)
 	poolFree(ctx, work);
 	if (rc) { ctx->root = oldRoot; return rc; }
 	ctx->generation++;
-	return publishVolume(ctx, ctx->nodeCount);
+	return writeHeaderAndSubdags(ctx);
 }
 
 int cbq_set_colours(cbq_context* ctx, const float* colours_rgb)
@@ -1070,7 +1037,6 @@ int cbq_get_option(cbq_context* ctx, const char* key, int64_t* value)
 	else if (k == "l2_persist") *value = ctx->l2Persist;
 	else if (k == "adaptive_order") *value = ctx->adaptiveOrder;
 	else if (k == "order_refresh") *value = ctx->orderRefresh;
-	else if (k == "ref_bits") *value = ctx->refBits;
 	else if (k == "sample_group") *value = ctx->cfg.sampleGroup;
 	else if (k == "sm_count") *value = ctx->cfg.smCount;
 	else if (k == "stack_levels") *value = ctx->cfg.stackLevels;

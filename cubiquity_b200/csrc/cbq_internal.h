@@ -11,14 +11,11 @@
 namespace cbq {
 
 // Layout of the ONE linear device buffer a volume lives in (cbq_upload):
-//   [0, 256)        VolumeHeader (the packed references of the 8 sub-DAG roots at byte 64)
+//   [0, 256)        VolumeHeader
 //   [256, 512)      SubDag[8]
 //   [512, 4608)     float4 colours[256]   (rgb + pad, so a material colour is one 16-byte load)
-//   [4608, ...)     nodes, 32 bytes each, 128-byte aligned start => every node is one L2 sector:
-//                   nodeCapacity nodes in the reference's layout (what edits, bake and download work on), then,
-//                   128-byte aligned, nodeCapacity x 8 packed references (traverse.cuh) -- what the ray cast reads
+//   [4608, ...)     nodes, 32 bytes each, 128-byte aligned start => every node is one L2 sector
 constexpr size_t kHeaderOffset = 0;
-constexpr size_t kRootRefOffset = 64;
 constexpr size_t kSubDagOffset = 256;
 constexpr size_t kColourOffset = 512;
 constexpr size_t kNodeOffset = 4608;
@@ -31,12 +28,8 @@ struct VolumeHeader {
 	uint32_t rootIndex;
 	uint32_t maxSubDagHeight;
 	uint64_t generation;   // bumped by every upload / update
-	uint32_t refBits;      // width of a packed reference: 32 while nodeCapacity <= 2^24, else 64
-	uint8_t pad0[kRootRefOffset - 44];
-	uint64_t rootRefs[8];  // written on the device (packRoots)
-	uint8_t pad1[256 - kRootRefOffset - 64];
+	uint8_t pad[256 - 40];
 };
-static_assert(offsetof(VolumeHeader, rootRefs) == kRootRefOffset, "root references at byte 64");
 static_assert(sizeof(VolumeHeader) == 256, "header is 256 bytes");
 
 // Row l of a banded rectangle -> image row: bands of 64 rows counted from y0, this share owns every
@@ -66,10 +59,8 @@ struct LaunchConfig {
 
 // What a kernel needs to know about the uploaded volume (device pointers into the volume buffer).
 struct VolumeView {
-	const void* refs;                      // packed references, 8 per node: uint32_t or uint64_t by refBits
-	int refBits;
+	const uint32_t* nodes;                 // 8 words per node, the reference's layout
 	const SubDag* subdags;
-	const unsigned long long* rootRefs;    // packed references of the 8 sub-DAG roots
 };
 
 struct TraceArgs {
@@ -131,10 +122,6 @@ void wavefrontRelease(WavefrontBuffers& b);
 typedef int (*QueueFn)(void* user, cudaStream_t stream, unsigned long long** out);
 cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, const LaunchConfig& cfg, cudaStream_t stream,
 	QueueFn nextQueue, void* user, uint64_t* launches);
-
-// Packed references (pack_kernels.cu): refs[begin * 8 .. end * 8) from the reference-layout nodes; the 8 root references.
-cudaError_t launchPackNodes(const uint32_t* nodes, uint64_t begin, uint64_t end, void* refs, int refBits, int smCount, cudaStream_t stream);
-cudaError_t launchPackRoots(const uint32_t* nodes, const SubDag* subdags, unsigned long long* rootRefs, cudaStream_t stream);
 
 // Device-side bake (bake_kernels.cu).
 size_t bakeScratchBytes(uint64_t nodeCount, uint64_t* tableSlots);

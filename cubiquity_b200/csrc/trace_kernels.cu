@@ -14,9 +14,8 @@
 //   * Per-ray short stack in SHARED memory, one column per thread ([level][thread]: conflict-free),
 //     sized to the deepest sub-DAG of the uploaded volume (13 entries for 4096^3) instead of the
 //     reference's 33-entry local array (raytracing.cpp:251).
-//   * The traversal follows PACKED REFERENCES (traverse.cuh): a step is a node visit, empty siblings are skipped
-//     with the occupancy mask that travels with the node's index, and the one load of a step -- the reference
-//     of the occupied child -- goes through the read-only path (ld.global.nc).
+//   * Node words are fetched through the read-only path (ld.global.nc). A sibling step re-reads a
+//     different word of the SAME 32-byte node, i.e. the same L1 sector.
 //   * Rays come either from a buffer (24-byte records) or straight from the camera in 8x4-pixel
 //     tiles per warp (Morton-like locality for primary rays) -- cbq_raycast_frame_device.
 #include "cbq_internal.h"
@@ -33,52 +32,43 @@ constexpr int kChunk = 32;            // rays claimed per atomic ticket (small: 
 #endif
 constexpr int kStepsPerRound = CBQ_STEPS_PER_ROUND;     // traversal steps between two refill votes
 
-// Child references through the read-only path. The array starts 128-byte aligned (cbq_internal.h) and a node is
-// 8 references, so index * 8 * sizeof(Ref) + base never carries into the slot offset.
-template <typename Ref>
+// Node words through the read-only path. The node array starts 128-byte aligned (cbq_internal.h), so
+// node * 32 + base never carries into the word offset: one IMAD.WIDE + one LEA instead of a 64-bit
+// scaled add.
 struct GlobalNodes {
-	const Ref* __restrict__ base;
-	__device__ __forceinline__ Ref child(Ref node, uint32_t slot) const
+	const uint32_t* __restrict__ base;
+	__device__ __forceinline__ const uint32_t* address(uint32_t node, uint32_t slot) const
 	{
-		return __ldg(base + ((size_t)refIndex(node) * 8u + slot));
+		const uint64_t a = reinterpret_cast<uint64_t>(base) + (uint64_t)node * 32u;
+		const uint32_t lo = (uint32_t)a + (slot << 2);
+		return reinterpret_cast<const uint32_t*>((a & 0xffffffff00000000ull) | lo);
 	}
+	__device__ __forceinline__ uint32_t child(uint32_t node, uint32_t slot) const { return __ldg(address(node, slot)); }
+	__device__ __forceinline__ void prefetch(uint32_t) const {}
 };
 
-// One column of a [levels][blockDim.x] array of references in shared memory (conflict-free: consecutive threads,
-// consecutive words). clear() zero-fills the levels a sub-DAG can pop to when the ray enters it, so that a pop to a
-// level that was never pushed reads 0 like the oracle's zero-initialised array (see stepOctant in traverse.cuh).
-template <typename Ref> struct SharedStack;
-template <> struct SharedStack<uint32_t> {
+// One column of a [levels][blockDim.x] array in shared memory (conflict-free: consecutive threads, consecutive
+// words). `written` has one bit per level stored to since the current sub-DAG was entered: a pop to a level that
+// was never pushed (only possible when NaNs or collapsed float planes defeat the `tExit < lastExit` guard,
+// raytracing.cpp:285) then reads 0, the value the oracle's zero-initialised array holds, instead of what an
+// earlier ray left behind. (Zero-filling the column on entry instead was measured: +1.9 % warp instructions and
+// 62 registers instead of 56, profiles/r02_analysis.md.)
+struct SharedStack {
 	uint32_t column;      // shared-window address of this thread's level-0 slot
 	uint32_t strideBytes; // blockDim.x * 4
-	__device__ __forceinline__ void store(int h, uint32_t n) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(column + (uint32_t)h * strideBytes), "r"(n)); }
+	uint32_t written;
+	__device__ __forceinline__ void store(int h, uint32_t n)
+	{
+		asm volatile("st.shared.u32 [%0], %1;" :: "r"(column + (uint32_t)h * strideBytes), "r"(n));
+		written |= 1u << h;
+	}
 	__device__ __forceinline__ uint32_t load(int h) const
 	{
 		uint32_t v;
 		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(column + (uint32_t)h * strideBytes));
-		return v;
+		return ((written >> h) & 1u) ? v : 0u;
 	}
-	__device__ __forceinline__ void clear(int top) { for (int h = 0; h <= top; h++) store(h, 0u); }
-};
-template <> struct SharedStack<uint64_t> {
-	uint32_t column;      // level-0 slot of the low words; the high words follow `levels` rows later
-	uint32_t strideBytes;
-	uint32_t highOffset;  // levels * strideBytes
-	__device__ __forceinline__ void store(int h, uint64_t n)
-	{
-		const uint32_t a = column + (uint32_t)h * strideBytes;
-		asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"((uint32_t)n));
-		asm volatile("st.shared.u32 [%0], %1;" :: "r"(a + highOffset), "r"((uint32_t)(n >> 32)));
-	}
-	__device__ __forceinline__ uint64_t load(int h) const
-	{
-		const uint32_t a = column + (uint32_t)h * strideBytes;
-		uint32_t lo, hi;
-		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(a));
-		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(a + highOffset));
-		return ((uint64_t)hi << 32) | lo;
-	}
-	__device__ __forceinline__ void clear(int top) { for (int h = 0; h <= top; h++) store(h, 0ull); }
+	__device__ __forceinline__ void clear(int) { written = 0u; }
 };
 
 __device__ __forceinline__ void loadRay(const Ray* __restrict__ rays, uint64_t i, Ray& r)
@@ -157,11 +147,11 @@ struct FlagSink {
 #define CBQ_TRACE_MIN_BLOCKS 4
 #endif
 
-template <bool kSurface, bool kLodOff, bool kDeviceCount, typename Ref, typename Source, typename Sink>
+template <bool kSurface, bool kLodOff, bool kDeviceCount, typename Source, typename Sink>
 __global__ void __launch_bounds__(256, CBQ_TRACE_MIN_BLOCKS)
-tracePersistent(const Ref* __restrict__ refBase, const SubDag* __restrict__ subdagsGlobal, const unsigned long long* __restrict__ rootRefsGlobal,
+tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict__ subdagsGlobal,
 	Source source, Sink sink, const uint64_t hostCount, const unsigned long long* __restrict__ countPtr, uint32_t countScale,
-	float maxFootprint, int refillThreshold, int refillQuantum, uint32_t stackLevels,
+	float maxFootprint, int refillThreshold, int refillQuantum,
 	unsigned long long* __restrict__ queue, unsigned long long* __restrict__ abandoned,
 	const uint32_t* __restrict__ ticketOrder, uint32_t* __restrict__ ticketCost)
 {
@@ -171,23 +161,19 @@ tracePersistent(const Ref* __restrict__ refBase, const SubDag* __restrict__ subd
 	const uint64_t count = kDeviceCount ? (uint64_t)(*countPtr) * countScale : hostCount;
 	extern __shared__ uint32_t stackMem[];
 	__shared__ SubDag subdags[8];
-	__shared__ Ref rootRefs[8];
 	for (uint32_t i = threadIdx.x; i < 64u; i += blockDim.x) reinterpret_cast<uint32_t*>(subdags)[i] = reinterpret_cast<const uint32_t*>(subdagsGlobal)[i];
-	for (uint32_t i = threadIdx.x; i < 8u; i += blockDim.x) rootRefs[i] = (Ref)rootRefsGlobal[i];
 	__syncthreads();
 
-	const GlobalNodes<Ref> nodes{ refBase };
+	const GlobalNodes nodes{ nodeBase };
 	// The two address terms are made opaque so that they stay in registers: left alone, the compiler re-derives them
 	// (tid, shared-window base, blockDim: 9 extra instructions) at every push and pop.
 	uint32_t stackColumn = (uint32_t)__cvta_generic_to_shared(stackMem + threadIdx.x), stackStride = blockDim.x * 4u;
 	asm volatile("" : "+r"(stackColumn), "+r"(stackStride));
-	SharedStack<Ref> stack;
-	stack.column = stackColumn; stack.strideBytes = stackStride;
-	if constexpr (sizeof(Ref) == 8) stack.highOffset = stackLevels * stackStride;
+	SharedStack stack{ stackColumn, stackStride, 0u };
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lowerLanes = (1u << lane) - 1u;
 
-	RayState<Ref> s;
+	RayState s;
 	s.phase = kPhaseIdle;
 	uint64_t slot = 0, ticketOfRay = 0;
 	// Warp-uniform window of claimed tickets.
@@ -248,8 +234,8 @@ tracePersistent(const Ref* __restrict__ refBase, const SubDag* __restrict__ subd
 			if (s.phase == kPhaseIdle) continue;
 			Hit out;
 			StepResult res;
-			if (s.phase == kPhaseOctant) res = stepOctant(s, subdags, rootRefs, stack);
-			else res = stepEsvo<kLodOff>(s, nodes, stack, maxFootprint, kSurface, out);
+			if (s.phase == kPhaseOctant) res = stepOctant(s, subdags, stack);
+			else res = stepEsvo<kLodOff>(s, fetchNext(s, nodes), nodes, stack, maxFootprint, kSurface, out);
 			if (res != kStepContinue) {
 				if (res == kStepHit) {
 					if (!kSurface) { out.material = 0; out.normal[0] = out.normal[1] = out.normal[2] = 0.0f; }
@@ -379,40 +365,34 @@ randomRays(uint64_t seed, float lx, float ly, float lz, float ex, float ey, floa
 	}
 }
 
-template <typename Ref, typename Kernel, typename Source, typename Sink>
+template <typename Kernel, typename Source, typename Sink>
 cudaError_t launchKernel(Kernel kernel, const TraceArgs& a, const Source& src, const Sink& sink, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
 {
-	const size_t smem = (size_t)cfg.stackLevels * (size_t)cfg.blockThreads * sizeof(Ref);
+	const size_t smem = (size_t)cfg.stackLevels * (size_t)cfg.blockThreads * sizeof(uint32_t);
 	cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	int grid = cfg.smCount * cfg.blocksPerSm;
 	const uint64_t needed = (tickets + (uint64_t)cfg.blockThreads - 1) / (uint64_t)cfg.blockThreads;
 	if (!a.countPtr && (uint64_t)grid > needed) grid = (int)(needed ? needed : 1);
-	kernel<<<grid, cfg.blockThreads, smem, stream>>>(static_cast<const Ref*>(a.volume.refs), a.volume.subdags, a.volume.rootRefs, src, sink, tickets,
-		a.countPtr, a.countScale, a.maxFootprint, cfg.refillThreshold, cfg.refillQuantum > 0 ? cfg.refillQuantum : 1, (uint32_t)cfg.stackLevels,
+	kernel<<<grid, cfg.blockThreads, smem, stream>>>(a.volume.nodes, a.volume.subdags, src, sink, tickets,
+		a.countPtr, a.countScale, a.maxFootprint, cfg.refillThreshold, cfg.refillQuantum > 0 ? cfg.refillQuantum : 1,
 		a.queue, a.abandoned, a.ticketOrder, a.ticketCost);
 	return cudaGetLastError();
 }
 
-template <bool kSurface, bool kLodOff, typename Ref, typename Source, typename Sink>
+template <bool kSurface, bool kLodOff, typename Source, typename Sink>
 cudaError_t launchPersistentImpl(const TraceArgs& a, const Source& src, const Sink& sink, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
 {
-	if (a.countPtr) return launchKernel<Ref>(tracePersistent<kSurface, kLodOff, true, Ref, Source, Sink>, a, src, sink, tickets, cfg, stream);
-	return launchKernel<Ref>(tracePersistent<kSurface, kLodOff, false, Ref, Source, Sink>, a, src, sink, tickets, cfg, stream);
+	if (a.countPtr) return launchKernel(tracePersistent<kSurface, kLodOff, true, Source, Sink>, a, src, sink, tickets, cfg, stream);
+	return launchKernel(tracePersistent<kSurface, kLodOff, false, Source, Sink>, a, src, sink, tickets, cfg, stream);
 }
 
 template <bool kSurface, typename Source, typename Sink>
 cudaError_t launchPersistentLod(const TraceArgs& a, const Source& src, const Sink& sink, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
 {
-	// maxFootprint == -1 exactly (MAX_FOOTPRINT_DISABLED) selects the division-free LOD test; 64-bit references only
-	// for volumes of 2^24 nodes or more.
-	const bool lodOff = a.maxFootprint == CBQ_MAX_FOOTPRINT_DISABLED;
-	if (a.volume.refBits == 32) {
-		if (lodOff) return launchPersistentImpl<kSurface, true, uint32_t>(a, src, sink, tickets, cfg, stream);
-		return launchPersistentImpl<kSurface, false, uint32_t>(a, src, sink, tickets, cfg, stream);
-	}
-	if (lodOff) return launchPersistentImpl<kSurface, true, uint64_t>(a, src, sink, tickets, cfg, stream);
-	return launchPersistentImpl<kSurface, false, uint64_t>(a, src, sink, tickets, cfg, stream);
+	// maxFootprint == -1 exactly (MAX_FOOTPRINT_DISABLED) selects the division-free LOD test.
+	if (a.maxFootprint == CBQ_MAX_FOOTPRINT_DISABLED) return launchPersistentImpl<kSurface, true>(a, src, sink, tickets, cfg, stream);
+	return launchPersistentImpl<kSurface, false>(a, src, sink, tickets, cfg, stream);
 }
 
 template <typename Source>

@@ -64,14 +64,14 @@ def hostcore():
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++",
                         "-o", so, src], check=True)
     lib = C.CDLL(so)
-    lib.host_core_trace.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    lib.host_core_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_float, C.c_void_p]
 
-    def trace(nodes, subdags, rays, surface=True, max_footprint=-1.0, ref_bits=32):
+    def trace(nodes, subdags, rays, surface=True, max_footprint=-1.0):
         nodes = np.ascontiguousarray(nodes, dtype=np.uint32)
         rays = np.ascontiguousarray(rays, dtype=pyoracle.RAY_DTYPE)
         hits = np.zeros(len(rays), dtype=pyoracle.HIT_DTYPE)
-        lib.host_core_trace(nodes.ctypes.data, len(nodes), subdags.ctypes.data, rays.ctypes.data, len(rays), int(surface),
-                            float(max_footprint), int(ref_bits), hits.ctypes.data)
+        lib.host_core_trace(nodes.ctypes.data, subdags.ctypes.data, rays.ctypes.data, len(rays), int(surface),
+                            float(max_footprint), hits.ctypes.data)
         return hits
     return trace
 

@@ -23,7 +23,7 @@ def test_edit_protocol_with_reference_edits(gpu, port, ref, scenes):
         before = gpu.counter("bytes_h2d")
         gpu.update(nodes, synced, root)
         sent = gpu.counter("bytes_h2d") - before
-        assert sent == (len(nodes) - synced) * 32 + 64 + 256       # the tail + header + 8 sub-DAGs, nothing else
+        assert sent == (len(nodes) - synced) * 32 + 512            # the tail + header + 8 sub-DAGs, nothing else
         assert sent < 0.2 * nodes.nbytes
         synced = v.shared_end()
         assert np.array_equal(gpu.download_nodes(), nodes)

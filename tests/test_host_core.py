@@ -11,13 +11,12 @@ from conftest import assert_hits_identical, mixed_rays
 
 @pytest.mark.parametrize("kind,size_log2", [("sphere_noise", 7), ("terrain", 8), ("soup", 7), ("city", 10)])
 @pytest.mark.parametrize("surface,max_footprint", [(True, -1.0), (False, -1.0), (True, 0.0035), (True, 0.05)])
-@pytest.mark.parametrize("ref_bits", [32, 64])
-def test_core_matches_oracle(port, hostcore, scenes, kind, size_log2, surface, max_footprint, ref_bits):
+def test_core_matches_oracle(port, hostcore, scenes, kind, size_log2, surface, max_footprint):
     sc = scenes(kind, size_log2)
     sd = port.find_subdags(sc.nodes, sc.root)
     rays = mixed_rays(sc.lower, sc.upper, 40000, seed=11)
     want, _, _ = port.trace(sc.nodes, sd, rays, surface, max_footprint)
-    got = hostcore(sc.nodes, sd, rays, surface, max_footprint, ref_bits=ref_bits)
+    got = hostcore(sc.nodes, sd, rays, surface, max_footprint)
     assert want["hit"].sum() > 1000
     assert_hits_identical(got, want, "%s %d" % (kind, size_log2))
 
@@ -31,5 +30,4 @@ def test_core_abandons_the_same_rays(port, hostcore, scenes):
     rays["d"] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 256)]   # ... with zero components
     want, _, _ = port.trace(sc.nodes, sd, rays, True, -1.0)
     assert want["pad"].sum() > 0
-    assert_hits_identical(hostcore(sc.nodes, sd, rays, True, -1.0, ref_bits=32), want, "degenerate, 32-bit references")
-    assert_hits_identical(hostcore(sc.nodes, sd, rays, True, -1.0, ref_bits=64), want, "degenerate, 64-bit references")
+    assert_hits_identical(hostcore(sc.nodes, sd, rays, True, -1.0), want, "degenerate")
