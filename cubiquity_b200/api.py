@@ -17,7 +17,8 @@ HIT_DTYPE = np.dtype([("hit", "<u4"), ("distance", "<f4"), ("material", "<u4"),
                       ("position", "<f4", 3), ("normal", "<f4", 3), ("status", "<u4")])
 SUBDAG_DTYPE = np.dtype([("lower", "<i4", 3), ("height", "<i4"), ("pad0", "<u4"),
                          ("node", "<u4"), ("pad1", "<u4"), ("pad2", "<u4")])
-assert RAY_DTYPE.itemsize == 24 and HIT_DTYPE.itemsize == 40 and SUBDAG_DTYPE.itemsize == 32
+COMPACT_DTYPE = np.dtype([("distance", "<f4"), ("code", "<u4")])      # cbq_hit_compact
+assert RAY_DTYPE.itemsize == 24 and HIT_DTYPE.itemsize == 40 and SUBDAG_DTYPE.itemsize == 32 and COMPACT_DTYPE.itemsize == 8
 
 TRACE_SURFACE = 1
 MAX_FOOTPRINT_DISABLED = -1.0
@@ -60,14 +61,13 @@ EXPORTS = [
     "cbq_create", "cbq_destroy", "cbq_last_error", "cbq_device_count", "cbq_synchronize",
     "cbq_upload", "cbq_update", "cbq_bake", "cbq_build_dense", "cbq_build_dense_device", "cbq_fill_sphere", "cbq_set_root", "cbq_set_colours", "cbq_get_subdags", "cbq_find_subdags",
     "cbq_download_nodes", "cbq_node_count",
-    "cbq_trace", "cbq_trace_device", "cbq_camera_from_pose", "cbq_primary_rays_device", "cbq_primary_rays_tiled_device", "cbq_random_rays_device",
+    "cbq_upload_device", "cbq_update_device",
+    "cbq_trace", "cbq_trace_device", "cbq_trace_compact", "cbq_trace_compact_device", "cbq_expand_hits", "cbq_camera_from_pose", "cbq_primary_rays_device", "cbq_primary_rays_tiled_device", "cbq_random_rays_device",
     "cbq_raycast_frame_device",
     "cbq_render", "cbq_render_device", "cbq_rng_points_device",
     "cbq_host_alloc", "cbq_host_free", "cbq_set_option", "cbq_get_option", "cbq_get_counter", "cbq_reset_counters",
     "cbq_editable_create", "cbq_editable_destroy", "cbq_editable_checkpoint", "cbq_editable_undo", "cbq_editable_redo",
     "cbq_editable_fill_sphere", "cbq_editable_nodes", "cbq_editable_root", "cbq_editable_shared_end", "cbq_editable_sync",
-    "cbq_scene_build", "cbq_scene_nodes", "cbq_scene_root", "cbq_scene_bounds", "cbq_scene_colours",
-    "cbq_scene_voxels", "cbq_scene_free",
 ]
 
 _lib = None
@@ -106,6 +106,11 @@ def load_library():
     L.cbq_node_count.argtypes = [vp, C.POINTER(u64)]
     L.cbq_trace.argtypes = [vp, vp, u64, u32, f32, vp]
     L.cbq_trace_device.argtypes = [vp, vp, u64, u32, f32, vp, vp]
+    L.cbq_trace_compact.argtypes = [vp, vp, u64, u32, f32, vp]
+    L.cbq_trace_compact_device.argtypes = [vp, vp, u64, u32, f32, vp, vp]
+    L.cbq_expand_hits.argtypes = [vp, vp, u64, vp, i32]
+    L.cbq_upload_device.argtypes = [vp, vp, u64, u32, vp, vp]
+    L.cbq_update_device.argtypes = [vp, vp, u64, u64, u32, vp]
     L.cbq_camera_from_pose.argtypes = [C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double, C.POINTER(Camera)]
     L.cbq_primary_rays_device.argtypes = [vp, C.POINTER(Camera), u32, u32, vp, vp]
     L.cbq_primary_rays_tiled_device.argtypes = [vp, C.POINTER(Camera), u32, u32, vp, vp, vp]
@@ -133,19 +138,6 @@ def load_library():
     L.cbq_editable_shared_end.restype = u64
     L.cbq_editable_shared_end.argtypes = [vp]
     L.cbq_editable_sync.argtypes = [vp, vp, i32, vp]
-    L.cbq_scene_build.argtypes = [C.c_char_p, u32, u64, C.POINTER(vp)]
-    L.cbq_scene_nodes.restype = C.POINTER(u32)
-    L.cbq_scene_nodes.argtypes = [vp, C.POINTER(u64)]
-    L.cbq_scene_root.restype = u32
-    L.cbq_scene_root.argtypes = [vp]
-    L.cbq_scene_bounds.restype = None
-    L.cbq_scene_bounds.argtypes = [vp, vp, vp]
-    L.cbq_scene_colours.restype = None
-    L.cbq_scene_colours.argtypes = [vp, vp]
-    L.cbq_scene_voxels.restype = None
-    L.cbq_scene_voxels.argtypes = [vp, vp, u64, vp]
-    L.cbq_scene_free.restype = None
-    L.cbq_scene_free.argtypes = [vp]
     _lib = L
     return L
 
@@ -226,43 +218,14 @@ class PinnedArray:
             pass
 
 
-class Scene:
-    """A procedural volume (csrc/scene_builder.cpp). Host only."""
-
-    def __init__(self, kind, size_log2, seed=1):
-        L = load_library()
-        self.kind, self.size_log2, self.seed = kind, int(size_log2), int(seed)
-        h = C.c_void_p()
-        _check(L.cbq_scene_build(kind.encode(), int(size_log2), int(seed), C.byref(h)))
-        self._h = h
-        n = C.c_uint64()
-        p = L.cbq_scene_nodes(h, C.byref(n))
-        self.nodes = np.ctypeslib.as_array(p, shape=(int(n.value), 8))   # view into the scene's memory
-        self.root = int(L.cbq_scene_root(h))
-        lo = np.zeros(3, dtype=np.int32)
-        hi = np.zeros(3, dtype=np.int32)
-        L.cbq_scene_bounds(h, _ptr(lo), _ptr(hi))
-        self.lower, self.upper = lo, hi
-        self.colours = np.zeros((256, 3), dtype=np.float32)
-        L.cbq_scene_colours(h, _ptr(self.colours))
-
-    def voxels(self, xyz):
-        xyz = np.ascontiguousarray(xyz, dtype=np.int32).reshape(-1, 3)
-        out = np.zeros(len(xyz), dtype=np.uint8)
-        load_library().cbq_scene_voxels(self._h, _ptr(xyz), len(xyz), _ptr(out))
-        return out
-
-    def close(self):
-        if getattr(self, "_h", None):
-            self.nodes = None
-            load_library().cbq_scene_free(self._h)
-            self._h = None
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+def Scene(kind, size_log2, seed=1):
+    """A procedural test / benchmark volume. The generator is not part of this library: scenes/ (repository root)."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import scenes
+    return scenes.Scene(kind, size_log2, seed)
 
 
 class Editable:
@@ -317,6 +280,16 @@ class Editable:
         _check(self.L.cbq_editable_sync(self._h, ctx._h, int(bool(first_upload)), _ptr(colours)))
 
 
+def expand_hits(rays, compact, out=None, threads=0):
+    """cbq_expand_hits: COMPACT_DTYPE records + their rays -> the HIT_DTYPE records cbq_trace writes (host only)."""
+    rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+    compact = np.ascontiguousarray(compact, dtype=COMPACT_DTYPE)
+    assert len(rays) == len(compact)
+    hits = out if out is not None else np.zeros(len(rays), dtype=HIT_DTYPE)
+    _check(load_library().cbq_expand_hits(_ptr(rays), _ptr(compact), len(rays), _ptr(hits), int(threads)))
+    return hits
+
+
 class Context:
     """One GPU. Mirrors the reference call sites: upload the Volume's node array, then intersect_volume."""
 
@@ -354,6 +327,16 @@ class Context:
     def update(self, nodes, dirty_begin, root):
         nodes = np.ascontiguousarray(nodes, dtype=np.uint32).reshape(-1, 8)
         _check(self.L.cbq_update(self._h, _ptr(nodes), int(dirty_begin), len(nodes), int(root)))
+
+    def upload_device(self, d_nodes, node_count, root, colours=None, stream=None):
+        """cbq_upload for a node array already in device memory (d_nodes: device pointer to node_count x 8 u32)."""
+        if colours is not None:
+            colours = np.ascontiguousarray(colours, dtype=np.float32).reshape(256, 3)
+        _check(self.L.cbq_upload_device(self._h, C.c_void_p(int(d_nodes)), int(node_count), int(root), _ptr(colours), _stream(stream)))
+
+    def update_device(self, d_tail, dirty_begin, node_count, root, stream=None):
+        """cbq_update with the dirty tail (nodes [dirty_begin, node_count), tail only) in device memory."""
+        _check(self.L.cbq_update_device(self._h, C.c_void_p(int(d_tail)) if d_tail else None, int(dirty_begin), int(node_count), int(root), _stream(stream)))
 
     def bake(self):
         """Volume::bake (reference storage.cpp:388-395) on the device copy; returns (node_count, root) of the merged
@@ -420,6 +403,20 @@ class Context:
         flags = TRACE_SURFACE if compute_surface_properties else 0
         _check(self.L.cbq_trace(self._h, _ptr(rays), len(rays), flags, float(max_footprint), _ptr(hits)))
         return hits
+
+    def intersect_volume_compact(self, rays, compute_surface_properties=True, max_footprint=MAX_FOOTPRINT_DISABLED, out=None):
+        """intersect_volume with 8-byte results (COMPACT_DTYPE); expand_hits() widens them to HIT_DTYPE on the host."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = out if out is not None else np.zeros(len(rays), dtype=COMPACT_DTYPE)
+        flags = TRACE_SURFACE if compute_surface_properties else 0
+        _check(self.L.cbq_trace_compact(self._h, _ptr(rays), len(rays), flags, float(max_footprint), _ptr(hits)))
+        return hits
+
+    def trace_compact_device(self, d_rays, n, d_hits, compute_surface_properties=True,
+                             max_footprint=MAX_FOOTPRINT_DISABLED, stream=None):
+        flags = TRACE_SURFACE if compute_surface_properties else 0
+        _check(self.L.cbq_trace_compact_device(self._h, C.c_void_p(int(d_rays)), int(n), flags, float(max_footprint),
+                                               C.c_void_p(int(d_hits)), _stream(stream)))
 
     def trace_device(self, d_rays, n, d_hits, compute_surface_properties=True,
                      max_footprint=MAX_FOOTPRINT_DISABLED, stream=None):

@@ -14,14 +14,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libcubiquity_b200.so")
-SOURCES = ["api.cu", "trace_kernels.cu", "wavefront_kernels.cu", "bake_kernels.cu", "edit_kernels.cu", "scene_builder.cpp", "edit.cpp"]
+SOURCES = ["api.cu", "trace_kernels.cu", "wavefront_kernels.cu", "bake_kernels.cu", "edit_kernels.cu", "edit.cpp", "host_shim.cpp"]
 HEADERS = ["traverse.cuh", "shading.cuh", "cbq_internal.h", os.path.join("..", "..", "include", "cubiquity_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-std=c++17", "-O3", "-lineinfo",
     "-fmad=false",                      # arithmetic contract, see module docstring
-    "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
+    "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function,-ffp-contract=off",   # host code: no fused multiply-add either (host_shim.cpp)
     "--diag-suppress", "549",
 ]
 

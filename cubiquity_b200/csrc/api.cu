@@ -314,14 +314,14 @@ int orderAfterTrace(cbq_context* ctx, const cbq::TraceArgs& a, cudaStream_t stre
 }
 
 int traceDevice(cbq_context* ctx, const cbq::Ray* dRays, uint64_t n, uint32_t flags, float maxFootprint,
-	cbq::Hit* dHits, cudaStream_t stream, const cbq_camera* cam, uint32_t width, uint32_t height)
+	cbq::Hit* dHits, cudaStream_t stream, const cbq_camera* cam, uint32_t width, uint32_t height, cbq_hit_compact* dCompact = nullptr)
 {
 	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "no volume uploaded");
 	if (n == 0) return CBQ_OK;
 	cbq::TraceArgs a;
 	std::memset(&a, 0, sizeof(a));
 	a.volume = ctx->view();
-	a.rays = dRays; a.hits = dHits; a.count = n; a.maxFootprint = maxFootprint;
+	a.rays = dRays; a.hits = dHits; a.compact = dCompact; a.count = n; a.maxFootprint = maxFootprint;
 	a.abandoned = ctx->abandonedPtr();
 	if (cam) { a.camera = *cam; a.width = width; a.height = height; }
 	int rc = nextQueue(ctx, stream, &a.queue);
@@ -607,6 +607,101 @@ int cbq_update(cbq_context* ctx, const uint32_t* nodes, uint64_t dirty_begin, ui
 	return writeHeaderAndSubdags(ctx);
 }
 
+namespace {
+
+// Child-index check and findSubDAGs for a node array that is already in the volume buffer: nodes [begin, count) are
+// scanned for a child >= count, the sub-DAGs of `root` are computed by subdagKernel. On success `sd` holds them.
+int checkOnDevice(cbq_context* ctx, uint64_t begin, uint64_t count, uint32_t root, cbq::SubDag sd[8], const char* what)
+{
+	uint8_t* work = nullptr;
+	CBQ_CUDA(poolAlloc(ctx, &work, 1024));
+	cbq::SubDag* dSubdags = reinterpret_cast<cbq::SubDag*>(work);
+	uint32_t* dStatus = reinterpret_cast<uint32_t*>(work + 256);       // [0] sub-DAG status, [1] largest child word
+	struct { cbq::SubDag subdags[8]; uint32_t status, worst; } host;
+	cudaError_t e = cudaMemsetAsync(dStatus, 0, 64, ctx->stream);
+	if (e == cudaSuccess) e = cbq::launchMaxChild(ctx->nodesPtr() + begin * 8, count - begin, dStatus + 1, ctx->cfg.smCount, ctx->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(&host.worst, dStatus + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	if (e == cudaSuccess && host.worst >= count) { poolFree(ctx, work); return fail(CBQ_ERROR_CORRUPT_VOLUME, "%s: a child index (%u) is >= the node count %llu", what, host.worst, (unsigned long long)count); }
+	// only now is it safe to walk the chains
+	if (e == cudaSuccess) e = cbq::launchSubdags(ctx->nodesPtr(), (uint32_t)count, root, nullptr, dSubdags, dStatus, ctx->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(&host, dSubdags, sizeof(host.subdags) + sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	poolFree(ctx, work);
+	if (e != cudaSuccess) return fail(CBQ_ERROR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+	ctx->launches += 2;
+	ctx->bytesD2H += sizeof(host);
+	if (host.status != 0) return fail(CBQ_ERROR_CORRUPT_VOLUME, "%s: node array is not a valid DAG below root %u (runaway chain)", what, root);
+	std::memcpy(sd, host.subdags, sizeof(host.subdags));
+	return CBQ_OK;
+}
+
+} // namespace
+
+int cbq_upload_device(cbq_context* ctx, const uint32_t* d_nodes, uint64_t node_count, uint32_t root_index, const float* colours_rgb, void* stream)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!d_nodes || node_count < cbq::kMaterialCount) return fail(CBQ_ERROR_INVALID_ARGUMENT, "node array must include the 256 material nodes");
+	if (node_count > 0xffffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "node indices are 32-bit");
+	if (root_index >= node_count) return fail(CBQ_ERROR_CORRUPT_VOLUME, "root %u is >= the node count %llu", root_index, (unsigned long long)node_count);
+	const uint64_t capacity = node_count + std::max<uint64_t>(node_count / 4, 1u << 16);
+	const size_t bytes = cbq::kNodeOffset + (size_t)capacity * 32;
+	CBQ_CUDA(cudaDeviceSynchronize());   // the producer of d_nodes has finished; nobody is still reading the old volume
+	(void)stream;
+	if (bytes > ctx->volumeBytes) {
+		if (ctx->volume) { poolFree(ctx, ctx->volume); ctx->volume = nullptr; ctx->volumeBytes = 0; }
+		CBQ_CUDA(poolAlloc(ctx, &ctx->volume, bytes));
+		ctx->volumeBytes = bytes;
+	}
+	// From here on the old volume is gone: a failure below leaves the context without one.
+	ctx->nodeCount = 0;
+	CBQ_CUDA(cudaMemcpyAsync(ctx->volume + cbq::kNodeOffset, d_nodes, (size_t)node_count * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+	ctx->nodeCapacity = (ctx->volumeBytes - cbq::kNodeOffset) / 32;
+	cbq::SubDag sd[8];
+	rc = checkOnDevice(ctx, 0, node_count, root_index, sd, "cbq_upload_device");
+	if (rc) { poolFree(ctx, ctx->volume); ctx->volume = nullptr; ctx->volumeBytes = 0; return rc; }
+	ctx->nodeCount = node_count;
+	ctx->root = root_index;
+	ctx->generation++;
+	ctx->deviceDiverged = false;
+	adoptSubdags(ctx, sd);
+	rc = cbq_set_colours(ctx, colours_rgb); if (rc) return rc;
+	return writeHeaderAndSubdags(ctx);
+}
+
+int cbq_update_device(cbq_context* ctx, const uint32_t* d_tail, uint64_t dirty_begin, uint64_t node_count, uint32_t root_index, void* stream)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "cbq_update_device before cbq_upload");
+	if (ctx->deviceDiverged) return fail(CBQ_ERROR_INVALID_ARGUMENT, "the device copy was changed on the device (cbq_fill_sphere / cbq_bake / cbq_build_dense): "
+		"no array is a delta of it any more; upload it again");
+	if (node_count < cbq::kMaterialCount || dirty_begin > node_count || (dirty_begin < node_count && !d_tail)) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad dirty range");
+	if (dirty_begin > ctx->nodeCount) return fail(CBQ_ERROR_INVALID_ARGUMENT, "dirty_begin %llu is past the %llu nodes on the device", (unsigned long long)dirty_begin, (unsigned long long)ctx->nodeCount);
+	if (node_count > 0xffffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "node indices are 32-bit");
+	if (root_index >= node_count) return fail(CBQ_ERROR_CORRUPT_VOLUME, "root %u is >= the node count %llu", root_index, (unsigned long long)node_count);
+	CBQ_CUDA(cudaDeviceSynchronize());
+	(void)stream;
+	if (node_count > ctx->nodeCapacity) {
+		const uint64_t capacity = node_count + std::max<uint64_t>(node_count / 4, 1u << 16);
+		const size_t bytes = cbq::kNodeOffset + (size_t)capacity * 32;
+		uint8_t* bigger = nullptr;
+		CBQ_CUDA(poolAlloc(ctx, &bigger, bytes));
+		CBQ_CUDA(cudaMemcpyAsync(bigger, ctx->volume, cbq::kNodeOffset + (size_t)dirty_begin * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+		poolFree(ctx, ctx->volume);
+		ctx->volume = bigger; ctx->volumeBytes = bytes; ctx->nodeCapacity = capacity;
+	}
+	const uint64_t tail = node_count - dirty_begin;
+	if (tail) CBQ_CUDA(cudaMemcpyAsync(ctx->volume + cbq::kNodeOffset + (size_t)dirty_begin * 32, d_tail, (size_t)tail * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+	cbq::SubDag sd[8];
+	rc = checkOnDevice(ctx, dirty_begin, node_count, root_index, sd, "cbq_update_device");
+	if (rc) return rc;      // the tail is bad: the header still describes the previous, intact state
+	ctx->nodeCount = node_count;
+	ctx->root = root_index;
+	ctx->generation++;
+	adoptSubdags(ctx, sd);
+	return writeHeaderAndSubdags(ctx);
+}
+
 int cbq_bake(cbq_context* ctx, uint64_t* node_count, uint32_t* root_index)
 {
 	int rc = bind(ctx); if (rc) return rc;
@@ -783,18 +878,21 @@ int cbq_trace_device(cbq_context* ctx, const cbq_ray* d_rays, uint64_t n, uint32
 	return traceDevice(ctx, reinterpret_cast<const cbq::Ray*>(d_rays), n, flags, max_footprint, reinterpret_cast<cbq::Hit*>(d_hits), s, nullptr, 0, 0);
 }
 
-int cbq_trace(cbq_context* ctx, const cbq_ray* rays, uint64_t n, uint32_t flags, float max_footprint, cbq_hit* hits)
+namespace {
+
+// Host rays in, host results out: a three-stage pipeline over chunks -- H2D on copyIn, kernel on stream, D2H on copyOut,
+// kStages staging buffers in flight. With pinned host memory the three overlap; with pageable memory the copies
+// degrade to synchronous but the result is the same. The copy back is the longest leg for 40-byte records, so the first
+// stages are short -- 2^15, 2^16, 2^17 rays -- to get it going early; after that every stage is kPipelineChunk rays.
+// recordBytes = 40 (cbq_hit) or 8 (cbq_hit_compact).
+int tracePipeline(cbq_context* ctx, const cbq_ray* rays, uint64_t n, uint32_t flags, float max_footprint, void* results, size_t recordBytes)
 {
-	int rc = bind(ctx); if (rc) return rc;
 	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "no volume uploaded");
 	if (n == 0) return CBQ_OK;
-	if (!rays || !hits) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null ray or hit buffer");
-	rc = ensureStaging(ctx); if (rc) return rc;
-	// Three-stage pipeline over chunks: H2D on copyIn, kernel on stream, D2H on copyOut, kStages
-	// staging buffers in flight. With pinned host memory the three overlap; with pageable memory
-	// the copies degrade to synchronous but the result is the same.
-	// The copy back (40 B/ray) is the longest leg, so the first stages are short -- 2^15, 2^16, 2^17 rays -- to get it
-	// going early; after that every stage is kPipelineChunk rays.
+	if (!rays || !results) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null ray or hit buffer");
+	int rc = ensureStaging(ctx); if (rc) return rc;
+	const bool compact = recordBytes == sizeof(cbq_hit_compact);
+	uint8_t* out = static_cast<uint8_t*>(results);
 	uint64_t begin = 0, stage = std::min<uint64_t>(kPipelineChunk, 1u << 15);
 	for (uint64_t c = 0; begin < n; c++) {
 		const int b = (int)(c % kStages);
@@ -804,11 +902,12 @@ int cbq_trace(cbq_context* ctx, const cbq_ray* rays, uint64_t n, uint32_t flags,
 		CBQ_CUDA(cudaEventRecord(ctx->evIn[b], ctx->copyIn));
 		CBQ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evIn[b], 0));
 		if (c >= (uint64_t)kStages) CBQ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evOut[b], 0));
-		rc = traceDevice(ctx, ctx->stageRays[b], len, flags, max_footprint, ctx->stageHits[b], ctx->stream, nullptr, 0, 0);
+		rc = traceDevice(ctx, ctx->stageRays[b], len, flags, max_footprint, compact ? nullptr : ctx->stageHits[b], ctx->stream, nullptr, 0, 0,
+			compact ? reinterpret_cast<cbq_hit_compact*>(ctx->stageHits[b]) : nullptr);
 		if (rc) return rc;
 		CBQ_CUDA(cudaEventRecord(ctx->evKernel[b], ctx->stream));
 		CBQ_CUDA(cudaStreamWaitEvent(ctx->copyOut, ctx->evKernel[b], 0));
-		CBQ_CUDA(cudaMemcpyAsync(hits + begin, ctx->stageHits[b], len * sizeof(cbq_hit), cudaMemcpyDeviceToHost, ctx->copyOut));
+		CBQ_CUDA(cudaMemcpyAsync(out + begin * recordBytes, ctx->stageHits[b], len * recordBytes, cudaMemcpyDeviceToHost, ctx->copyOut));
 		CBQ_CUDA(cudaEventRecord(ctx->evOut[b], ctx->copyOut));
 		begin += len;
 		stage = std::min<uint64_t>(stage * 2, kPipelineChunk);
@@ -816,8 +915,30 @@ int cbq_trace(cbq_context* ctx, const cbq_ray* rays, uint64_t n, uint32_t flags,
 	CBQ_CUDA(cudaStreamSynchronize(ctx->copyOut));
 	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->bytesH2D += n * sizeof(cbq_ray);
-	ctx->bytesD2H += n * sizeof(cbq_hit);
+	ctx->bytesD2H += n * recordBytes;
 	return CBQ_OK;
+}
+
+} // namespace
+
+int cbq_trace(cbq_context* ctx, const cbq_ray* rays, uint64_t n, uint32_t flags, float max_footprint, cbq_hit* hits)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	return tracePipeline(ctx, rays, n, flags, max_footprint, hits, sizeof(cbq_hit));
+}
+
+int cbq_trace_compact(cbq_context* ctx, const cbq_ray* rays, uint64_t n, uint32_t flags, float max_footprint, cbq_hit_compact* hits)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	return tracePipeline(ctx, rays, n, flags, max_footprint, hits, sizeof(cbq_hit_compact));
+}
+
+int cbq_trace_compact_device(cbq_context* ctx, const cbq_ray* d_rays, uint64_t n, uint32_t flags, float max_footprint, cbq_hit_compact* d_hits, void* stream)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (n && (!d_rays || !d_hits)) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null ray or hit buffer");
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	return traceDevice(ctx, reinterpret_cast<const cbq::Ray*>(d_rays), n, flags, max_footprint, nullptr, s, nullptr, 0, 0, d_hits);
 }
 
 int cbq_camera_from_pose(const double position[3], double pitch, double yaw, double fov_degrees, cbq_camera* c)

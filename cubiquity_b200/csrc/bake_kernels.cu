@@ -535,6 +535,28 @@ cudaError_t launchBuildDense(const uint8_t* voxels, uint32_t k, const int32_t or
 	return cudaGetLastError();
 }
 
+// Largest child word of a node array (cbq_upload_device / cbq_update_device: every child index must be < the node count,
+// the kernels follow them unchecked). One 16-byte load per thread, a warp max, one atomicMax per warp.
+__global__ void __launch_bounds__(256) maxChildKernel(const uint4* __restrict__ words, uint64_t quads, uint32_t* worst)
+{
+	uint32_t m = 0;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint4 w = words[i];
+		m = max(max(m, max(w.x, w.y)), max(w.z, w.w));
+	}
+	m = __reduce_max_sync(0xffffffffu, m);
+	if ((threadIdx.x & 31u) == 0u && m != 0u) atomicMax(worst, m);
+}
+
+cudaError_t launchMaxChild(const uint32_t* nodes, uint64_t count, uint32_t* worst, int smCount, cudaStream_t stream)
+{
+	if (count == 0) return cudaSuccess;
+	uint64_t blocks = (count * 2 + 255) / 256;
+	if (blocks > (uint64_t)smCount * 8u) blocks = (uint64_t)smCount * 8u;
+	maxChildKernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(nodes), count * 2, worst);
+	return cudaGetLastError();
+}
+
 cudaError_t launchSubdags(const uint32_t* nodes, uint32_t nodeCount, uint32_t root, const unsigned long long* rootPtr, SubDag* out, uint32_t* status, cudaStream_t stream)
 {
 	subdagKernel<<<1, 32, 0, stream>>>(nodes, nodeCount, root, rootPtr, out, status);

@@ -80,6 +80,7 @@ struct TraceArgs {
 	const unsigned long long* countPtr;
 	uint32_t countScale;
 	uint8_t* flags;
+	cbq_hit_compact* compact;        // != nullptr: 8-byte results (cbq_trace_compact) instead of `hits`
 	uint32_t untileWidth;            // != 0: rays are in 8x4-tile order of an image this wide; write hits row-major
 	// optional cost feedback (refillThreshold == 32 only): deal the 32-ray tickets in this order / record their cost
 	const uint32_t* ticketOrder;     // permutation of [0, ceil(count / 32)), or nullptr
@@ -128,6 +129,8 @@ size_t bakeScratchBytes(uint64_t nodeCount, uint64_t* tableSlots);
 cudaError_t launchBake(const uint32_t* nodes, uint64_t nodeCount, uint32_t root, uint8_t* scratch, uint64_t tableSlots, uint32_t* out,
 	unsigned long long* results, int smCount, cudaStream_t stream, uint64_t* launches);
 // findSubDAGs on a device array; root is read from *rootPtr when rootPtr != nullptr. *status |= 1 on a runaway chain.
+// *worst = max(*worst, largest child word of nodes [0, count)): the device-side half of the child-index check.
+cudaError_t launchMaxChild(const uint32_t* nodes, uint64_t count, uint32_t* worst, int smCount, cudaStream_t stream);
 cudaError_t launchSubdags(const uint32_t* nodes, uint32_t nodeCount, uint32_t root, const unsigned long long* rootPtr, SubDag* out, uint32_t* status, cudaStream_t stream);
 
 // Dense voxel grid -> complete (un-merged) octree below a height-32 root; launchBake then merges it.

@@ -137,6 +137,19 @@ struct TiledSink {
 		storeHit(hits, (uint64_t)y * width + x, h);
 	}
 };
+// 8-byte results (cbq_hit_compact): no position, so the ray is not fetched again and one 64-bit store replaces five.
+struct CompactSink {
+	cbq_hit_compact* __restrict__ hits;
+	static constexpr bool kNeedsPosition = false;
+	__device__ __forceinline__ void write(uint64_t slot, const Hit& h) const
+	{
+		const uint32_t nx = __float_as_uint(h.normal[0]), ny = __float_as_uint(h.normal[1]), nz = __float_as_uint(h.normal[2]);
+		const uint32_t normal = ((nx << 1) != 0u ? 1u : 0u) | (nx >> 31) << 1 | ((ny << 1) != 0u ? 4u : 0u) | (ny >> 31) << 3 |
+		                        ((nz << 1) != 0u ? 16u : 0u) | (nz >> 31) << 5;
+		const uint32_t code = (h.material & 0xffu) | normal << 8 | (h.hit ? 1u << 14 : 0u) | (h.status ? 1u << 15 : 0u);
+		reinterpret_cast<uint2*>(hits)[slot] = make_uint2(__float_as_uint(h.distance), code);
+	}
+};
 struct FlagSink {
 	uint8_t* __restrict__ flags;
 	static constexpr bool kNeedsPosition = false;
@@ -401,6 +414,10 @@ cudaError_t launchPersistent(const TraceArgs& a, bool surface, const Source& src
 	if (a.flags) {
 		// Flag-only results are for shadow rays, which never ask for surface properties.
 		return launchPersistentLod<false>(a, src, FlagSink{ a.flags }, tickets, cfg, stream);
+	}
+	if (a.compact) {
+		const CompactSink sink{ a.compact };
+		return surface ? launchPersistentLod<true>(a, src, sink, tickets, cfg, stream) : launchPersistentLod<false>(a, src, sink, tickets, cfg, stream);
 	}
 	if (a.untileWidth) {
 		const TiledSink sink{ a.hits, a.untileWidth, a.untileWidth / 8u };

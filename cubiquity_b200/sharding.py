@@ -42,6 +42,53 @@ def broadcast_volume(dist, nodes, root, device=None, src=0):
     return buf.cpu().numpy().view(np.uint32).reshape(-1, 8), root
 
 
+def replicate_volume(dist, ctx, nodes, root, colours, device, src=0):
+    """broadcast_volume straight into the ray caster: the NCCL broadcast lands in device memory and
+    cbq_upload_device copies it device to device into the volume buffer (no trip through the host: the
+    reference's upload is the one-off glBufferData of gpu_pathtracing_viewer.cpp:46-50). Rank `src` passes the
+    host arrays, the others None. Returns (node_count, root, colours)."""
+    import torch
+    meta = torch.zeros(2, dtype=torch.int64, device=device)
+    if dist.get_rank() == src:
+        meta[0], meta[1] = len(nodes), int(root)
+    dist.broadcast(meta, src=src)
+    count, root = int(meta[0].item()), int(meta[1].item())
+    if dist.get_rank() == src:
+        buf = torch.from_numpy(np.ascontiguousarray(nodes, dtype=np.uint32).view(np.int32).reshape(-1)).to(device)
+        col = torch.from_numpy(np.ascontiguousarray(colours, dtype=np.float32).reshape(256, 3).copy()).to(device)
+    else:
+        buf = torch.empty(count * 8, dtype=torch.int32, device=device)
+        col = torch.empty(256, 3, dtype=torch.float32, device=device)
+    dist.broadcast(buf, src=src)
+    dist.broadcast(col, src=src)
+    colours = col.cpu().numpy()
+    torch.cuda.synchronize(device)
+    ctx.upload_device(buf.data_ptr(), count, root, colours)
+    return count, root, colours
+
+
+def replicate_tail(dist, ctx, nodes, dirty_begin, root, device, src=0):
+    """broadcast_tail straight into the ray caster: rank `src` passes its current host array, the first dirty node
+    and the new root; every rank (src included) applies the tail with cbq_update_device. Returns (node_count, root,
+    tail_bytes)."""
+    import torch
+    meta = torch.zeros(3, dtype=torch.int64, device=device)
+    if dist.get_rank() == src:
+        meta[0], meta[1], meta[2] = len(nodes), int(dirty_begin), int(root)
+    dist.broadcast(meta, src=src)
+    count, dirty_begin, root = (int(v) for v in meta.tolist())
+    tail = count - dirty_begin
+    if dist.get_rank() == src:
+        buf = torch.from_numpy(np.ascontiguousarray(nodes[dirty_begin:], dtype=np.uint32).view(np.int32).reshape(-1)).to(device)
+    else:
+        buf = torch.empty(tail * 8, dtype=torch.int32, device=device)
+    if tail:
+        dist.broadcast(buf, src=src)
+    torch.cuda.synchronize(device)
+    ctx.update_device(buf.data_ptr() if tail else 0, dirty_begin, count, root)
+    return count, root, tail * 32
+
+
 def broadcast_tail(dist, nodes, dirty_begin, root, device=None, src=0):
     """After an edit on rank `src`: ship only nodes[dirty_begin:] and the new root.
     Other ranks pass their current (stale) array as `nodes`; returns the refreshed (array, root)."""

@@ -53,6 +53,16 @@ typedef struct cbq_hit {
 } cbq_hit;                                                                          /* 40 bytes */
 #define CBQ_HIT_ABANDONED 1u
 
+/* The same result in 8 bytes, for callers on the far side of PCIe (cbq_trace_compact): everything cbq_hit carries
+ * except `position`, which is a function of the ray and `distance` alone -- origin + dir * (float)distance with an
+ * un-fused multiply and add (raytracing.cpp:463-466) -- and is re-formed bit for bit by cbq_expand_hits() on the host.
+ *   code bits 0..7   material
+ *        bits 8..13  normal, two bits per axis (x: 8-9, y: 10-11, z: 12-13): bit 0 = the component is +-1 rather
+ *                    than +-0, bit 1 = its sign bit (quirk Q3: zero components are signed, raytracing.cpp:317-318)
+ *        bit  14     hit
+ *        bit  15     CBQ_HIT_ABANDONED */
+typedef struct cbq_hit_compact { float distance; uint32_t code; } cbq_hit_compact;            /* 8 bytes */
+
 /* struct SubDAG verbatim (src/library/raytracing.h:57-65; GLSL mirror glsl/pathtracing.frag:118-126). */
 typedef struct cbq_subdag {
 	int32_t  lower[3];
@@ -120,6 +130,12 @@ int  cbq_synchronize(cbq_context* ctx);
 int cbq_upload(cbq_context* ctx, const uint32_t* nodes, uint64_t node_count, uint32_t root_index,
                const float* colours_rgb);
 
+/* cbq_upload for a node array that is already in device memory (e.g. landed there by an NCCL broadcast): one
+ * device-to-device copy, sub-DAGs and the child-index check computed on the device. `stream` is the stream the
+ * array was produced on (waited for), NULL = none. colours_rgb is a HOST pointer as in cbq_upload. */
+int cbq_upload_device(cbq_context* ctx, const uint32_t* d_nodes, uint64_t node_count, uint32_t root_index,
+                      const float* colours_rgb, void* stream);
+
 /* Delta re-upload after a runtime edit (Viewer::onMouseButtonDown, viewer.cpp:152-172:
  * checkpoint -> fillBrush -> onVolumeModified). Copy-on-write (NodeStore::setNodeChild,
  * storage.cpp:152-167) only ever touches nodes at or above sharedNodesEnd(), so the device copy
@@ -131,6 +147,11 @@ int cbq_upload(cbq_context* ctx, const uint32_t* nodes, uint64_t node_count, uin
  * the next cbq_upload. */
 int cbq_update(cbq_context* ctx, const uint32_t* nodes, uint64_t dirty_begin, uint64_t node_count,
                uint32_t root_index);
+
+/* cbq_update with the dirty tail in device memory: d_tail holds nodes [dirty_begin, node_count) -- the tail only,
+ * which is what a broadcast after an edit ships -- and is copied device to device. */
+int cbq_update_device(cbq_context* ctx, const uint32_t* d_tail, uint64_t dirty_begin, uint64_t node_count,
+                      uint32_t root_index, void* stream);
 
 /* Volume::bake() (reference src/library/storage.cpp:388-395 -> NodeStore::merge / merge_node, :208-290) on the
  * DEVICE copy, without a host round trip: everything the root reaches is hash-consed bottom-up, a node whose eight
@@ -190,6 +211,14 @@ int cbq_trace(cbq_context* ctx, const cbq_ray* rays, uint64_t n, uint32_t flags,
  * non-blocking stream; to order the work on the CUDA default stream pass cudaStreamLegacy. */
 int cbq_trace_device(cbq_context* ctx, const cbq_ray* d_rays, uint64_t n, uint32_t flags,
                      float max_footprint, cbq_hit* d_hits, void* stream);
+
+/* cbq_trace with 8-byte results: 24 + 8 bytes per ray cross PCIe instead of 24 + 40. cbq_expand_hits (host only,
+ * `threads` worker threads, 0 = all cores) widens them into exactly the records cbq_trace writes for the same rays. */
+int cbq_trace_compact(cbq_context* ctx, const cbq_ray* rays, uint64_t n, uint32_t flags, float max_footprint,
+                      cbq_hit_compact* hits);
+int cbq_trace_compact_device(cbq_context* ctx, const cbq_ray* d_rays, uint64_t n, uint32_t flags,
+                             float max_footprint, cbq_hit_compact* d_hits, void* stream);
+int cbq_expand_hits(const cbq_ray* rays, const cbq_hit_compact* compact, uint64_t n, cbq_hit* hits, int threads);
 
 /* Camera::rayFromViewportPos (camera.cpp:12-38) for every pixel, row-major, cast to float like
  * static_cast<Ray3f> in PathtracingDemo::raytrace (pathtracing_demo.cpp:220). */
@@ -268,18 +297,6 @@ uint32_t cbq_editable_root(const cbq_editable* e);
 uint64_t cbq_editable_shared_end(const cbq_editable* e);
 /* first_upload != 0: cbq_upload; otherwise cbq_update with the tail that changed since the last sync. */
 int  cbq_editable_sync(cbq_editable* e, cbq_context* ctx, int first_upload, const float* colours_rgb);
-
-/* ---- procedural scenes (inputs for tests and benchmarks; host only) --------------------- */
-
-typedef struct cbq_scene cbq_scene;
-/* kind: "sphere_noise" | "terrain" | "soup" | "city". The volume is 2^size_log2 voxels a side. */
-int cbq_scene_build(const char* kind, uint32_t size_log2, uint64_t seed, cbq_scene** out);
-const uint32_t* cbq_scene_nodes(const cbq_scene* s, uint64_t* node_count);
-uint32_t cbq_scene_root(const cbq_scene* s);
-void cbq_scene_bounds(const cbq_scene* s, int32_t lower[3], int32_t upper[3]);
-void cbq_scene_colours(const cbq_scene* s, float* rgb768);
-void cbq_scene_voxels(const cbq_scene* s, const int32_t* xyz, uint64_t n, uint8_t* out);
-void cbq_scene_free(cbq_scene* s);
 
 #ifdef __cplusplus
 }

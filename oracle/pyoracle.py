@@ -67,6 +67,15 @@ def build(port=True, ref=None):
         subprocess.run(["make", "-s", "-C", HERE, "-j8"] + targets, check=True)
 
 
+def write_dag(path, nodes, root):
+    """The checker's own writer of the reference's .dag file (storage.cpp:192-206: u32 root, u32 count, then the
+    count non-material nodes) -- inputs reach the reference without passing through product code."""
+    nodes = np.ascontiguousarray(nodes, dtype="<u4").reshape(-1, 8)
+    with open(path, "wb") as f:
+        np.array([int(root), len(nodes) - 256], dtype="<u4").tofile(f)
+        nodes[256:].tofile(f)
+
+
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -197,7 +206,6 @@ class Ref:
     def pt_render(self, nodes, root, colours, position, pitch, yaw, params, reseed=True, accum=None):
         """The reference's own PathtracingDemo::traceSingleRay / traceSingleRayRecurse over a pixel rectangle
         (oracle/ref_pt_shim.cpp). `params` is a PtParams. Single threaded: the reference's RNG is a global."""
-        from cubiquity_b200.dagfile import write_dag
         colours = np.ascontiguousarray(colours, dtype=np.float32)
         pos = np.asarray(position, dtype=np.float64)
         if accum is None:
@@ -233,7 +241,6 @@ class RefVolume:
 
     def load_arrays(self, nodes, root):
         """Round-trips through the reference's own .dag reader (storage.cpp:505-528)."""
-        from cubiquity_b200.dagfile import write_dag
         with tempfile.NamedTemporaryFile(suffix=".dag", delete=False) as f:
             path = f.name
         try:

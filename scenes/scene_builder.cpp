@@ -13,7 +13,7 @@
 // ORDER differs; traversal results do not depend on it).
 //
 // All scene maths is integer so every machine builds bit-identical volumes from a seed.
-#include "../../include/cubiquity_b200.h"
+#include "cbq_scenes.h"
 
 #include <algorithm>
 #include <array>

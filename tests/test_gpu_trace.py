@@ -369,3 +369,38 @@ def test_cost_feedback_order_is_only_a_schedule(gpu, port, api):
     finally:
         gpu.set_option("adaptive_order", 1)
         gpu.set_option("refill_threshold", old)
+
+
+@pytest.mark.parametrize("surface,mf", [(True, -1.0), (False, -1.0), (True, 0.0035)])
+def test_compact_results_expand_to_the_full_records(gpu, port, api, scenes, surface, mf):
+    """cbq_trace_compact moves 8 bytes per ray instead of 40; cbq_expand_hits re-forms position = origin + dir * distance
+    on the host (un-fused, raytracing.cpp:463-466) and must give back cbq_trace's records byte for byte -- degenerate
+    and abandoned rays included."""
+    sc = scenes("terrain", 9)
+    gpu.upload(sc.nodes, sc.root, sc.colours)
+    rays = mixed_rays(sc.lower, sc.upper, 300000, seed=33)
+    rng = np.random.default_rng(3)
+    rays["o"][:256] = rng.integers(-60, 60, (256, 3)) + 0.5
+    rays["d"][:256] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 256)]
+    full = gpu.intersect_volume(rays, surface, mf)
+    before = gpu.counter("bytes_d2h")
+    compact = gpu.intersect_volume_compact(rays, surface, mf)
+    assert gpu.counter("bytes_d2h") - before == 8 * len(rays)
+    assert full["status"].sum() > 0 and full["hit"].sum() > 10000
+    assert_hits_identical(api.expand_hits(rays, compact), full, "compact, expanded")
+    assert_hits_identical(api.expand_hits(rays, compact, threads=1), full, "compact, expanded by one thread")
+    assert_hits_identical(full, oracle_hits(port, sc, rays, surface, mf), "and both are the oracle's")
+
+
+def test_compact_device_pointer_variant(gpu, api, scenes):
+    torch = pytest.importorskip("torch")
+    sc = scenes("soup", 8)
+    gpu.upload(sc.nodes, sc.root)
+    rays = mixed_rays(sc.lower, sc.upper, 100001, seed=8)
+    d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1)).cuda()
+    d_out = torch.zeros(len(rays) * 2, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    gpu.trace_compact_device(d_rays.data_ptr(), len(rays), d_out.data_ptr(), True, -1.0, stream)
+    torch.cuda.synchronize()
+    compact = d_out.cpu().numpy().view(api.COMPACT_DTYPE).reshape(-1)
+    assert_hits_identical(api.expand_hits(rays, compact), gpu.intersect_volume(rays, True, -1.0), "compact, device pointers")

@@ -100,3 +100,38 @@ def test_city_65536_with_runtime_edits_and_lod(gpu, port, ref, api):
         op = pyoracle.pt_params_from(p)
         want_img, _, _ = port.render(nodes, sd, sc.colours, ocam, op, threads=8)
         assert np.array_equal(gpu.render(cam, p), want_img)
+
+
+def test_device_resident_upload_and_tail(gpu, port, ref, api, scenes):
+    """cbq_upload_device / cbq_update_device: the node array (or its dirty tail) is already in device memory, as
+    after an NCCL broadcast; the result must be the volume cbq_upload / cbq_update would have made."""
+    torch = pytest.importorskip("torch")
+    sc = scenes("sphere_noise", 7)
+    v = ref.volume().load_arrays(sc.nodes, sc.root)
+    nodes, root = v.nodes(), v.root()
+    d_nodes = torch.from_numpy(nodes.view(np.int32).reshape(-1)).cuda()
+    gpu.upload_device(d_nodes.data_ptr(), len(nodes), root, sc.colours)
+    assert np.array_equal(gpu.download_nodes(), nodes)
+    assert gpu.subdags().tobytes() == port.find_subdags(nodes, root).tobytes()
+    rays = mixed_rays(sc.lower, sc.upper, 50000, seed=2)
+    sd = port.find_subdags(nodes, root)
+    assert_hits_identical(gpu.intersect_volume(rays, True, -1.0), port.trace(nodes, sd, rays, True, -1.0)[0], "device upload")
+    # the reference's edit, shipped as a device-resident tail
+    synced = len(nodes)
+    v.checkpoint()
+    v.fill_sphere(0.0, 0.0, float(sc.upper[2]) - 10.0, 14.0, 0)
+    nodes, root = v.nodes(), v.root()
+    d_tail = torch.from_numpy(nodes[synced:].view(np.int32).reshape(-1).copy()).cuda()
+    before = gpu.counter("bytes_h2d")
+    gpu.update_device(d_tail.data_ptr(), synced, len(nodes), root)
+    assert gpu.counter("bytes_h2d") - before == 512                     # header + sub-DAGs; the tail never touched the host link
+    assert np.array_equal(gpu.download_nodes(), nodes)
+    sd = port.find_subdags(nodes, root)
+    assert_hits_identical(gpu.intersect_volume(rays, True, -1.0), port.trace(nodes, sd, rays, True, -1.0)[0], "device tail")
+    # a child index past the end is refused and the previous state survives
+    bad = nodes[synced:].copy()
+    bad[0, 0] = len(nodes) + 5
+    d_bad = torch.from_numpy(bad.view(np.int32).reshape(-1)).cuda()
+    with pytest.raises(api.CubiquityError) as e:
+        gpu.update_device(d_bad.data_ptr(), synced, len(nodes), root)
+    assert e.value.code == api.ERROR_CORRUPT_VOLUME

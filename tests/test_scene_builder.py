@@ -1,4 +1,4 @@
-"""The procedural scene builder (csrc/scene_builder.cpp) against the reference's own volume code."""
+"""The procedural scene builder (scenes/scene_builder.cpp, the host-only input generator) against the reference's own volume code."""
 import os
 import tempfile
 
