@@ -65,6 +65,7 @@ EXPORTS = [
     "cbq_trace", "cbq_trace_device", "cbq_trace_compact", "cbq_trace_compact_device", "cbq_expand_hits", "cbq_camera_from_pose", "cbq_primary_rays_device", "cbq_primary_rays_tiled_device", "cbq_random_rays_device",
     "cbq_raycast_frame_device",
     "cbq_render", "cbq_render_device", "cbq_rng_points_device",
+    "cbq_shared_alloc", "cbq_shared_open", "cbq_shared_close", "cbq_shared_free", "cbq_copy_device",
     "cbq_host_alloc", "cbq_host_free", "cbq_set_option", "cbq_get_option", "cbq_get_counter", "cbq_reset_counters",
     "cbq_editable_create", "cbq_editable_destroy", "cbq_editable_checkpoint", "cbq_editable_undo", "cbq_editable_redo",
     "cbq_editable_fill_sphere", "cbq_editable_nodes", "cbq_editable_root", "cbq_editable_shared_end", "cbq_editable_sync",
@@ -119,6 +120,11 @@ def load_library():
     L.cbq_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(PtParams), vp]
     L.cbq_render_device.argtypes = [vp, C.POINTER(Camera), C.POINTER(PtParams), vp, vp]
     L.cbq_rng_points_device.argtypes = [vp, vp, u64, i32, vp, vp, vp]
+    L.cbq_shared_alloc.argtypes = [vp, u64, C.POINTER(vp), vp]
+    L.cbq_shared_open.argtypes = [vp, vp, C.POINTER(vp)]
+    L.cbq_shared_close.argtypes = [vp, vp]
+    L.cbq_shared_free.argtypes = [vp, vp]
+    L.cbq_copy_device.argtypes = [vp, vp, vp, u64, vp]
     L.cbq_host_alloc.argtypes = [C.POINTER(vp), u64]
     L.cbq_host_free.argtypes = [vp]
     L.cbq_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
@@ -460,6 +466,29 @@ class Context:
     def rng_points_device(self, d_seeds, n, draws, d_points, d_states, stream=None):
         _check(self.L.cbq_rng_points_device(self._h, C.c_void_p(int(d_seeds)), int(n), int(draws), C.c_void_p(int(d_points)),
                                             C.c_void_p(int(d_states)), _stream(stream)))
+
+    # -- multi-GPU: one result buffer on one GPU, addressed by every process over NVLink --------
+    def shared_alloc(self, nbytes):
+        """(device pointer, 64-byte IPC handle as bytes) of a zero-filled buffer other processes can open."""
+        p = C.c_void_p()
+        h = (C.c_ubyte * 64)()
+        _check(self.L.cbq_shared_alloc(self._h, int(nbytes), C.byref(p), h))
+        return int(p.value), bytes(h)
+
+    def shared_open(self, handle):
+        p = C.c_void_p()
+        h = (C.c_ubyte * 64).from_buffer_copy(bytes(handle))
+        _check(self.L.cbq_shared_open(self._h, h, C.byref(p)))
+        return int(p.value)
+
+    def shared_close(self, ptr):
+        _check(self.L.cbq_shared_close(self._h, C.c_void_p(int(ptr))))
+
+    def shared_free(self, ptr):
+        _check(self.L.cbq_shared_free(self._h, C.c_void_p(int(ptr))))
+
+    def copy_device(self, dst, src, nbytes, stream=None):
+        _check(self.L.cbq_copy_device(self._h, C.c_void_p(int(dst)), C.c_void_p(int(src)), int(nbytes), _stream(stream)))
 
     # -- misc --------------------------------------------------------------------------------
     def synchronize(self):

@@ -44,7 +44,9 @@ int fail(int code, const char* fmt, ...)
 	} while (0)
 
 constexpr int kQueueSlots = 64;        // ticket counters, one per stream that has launched a trace (the kernel re-arms its own)
-constexpr uint64_t kPipelineChunk = 1u << 18;  // rays per host<->device pipeline stage (6 MB in, 10 MB out); 2^16 was 45 % slower end to end (API overhead per stage)
+constexpr uint64_t kPipelineChunkMin = 1u << 18;  // rays per host<->device pipeline stage: at least 2^18 (6 MB in; 2^16 was 45 % slower end to end, API overhead per stage) ...
+constexpr uint64_t kPipelineChunkMax = 1u << 21;  // ... and for big batches an eighth of the batch up to 2^21: a stage's kernel must fill the GPU, or the kernels, not the link, set the pace
+                                                  // (132 M rays in 2^18-ray stages: 79.6 ms, kernel-bound at ~150 us a stage; the link needs 58 ms)
 constexpr int kStages = 3;                     // staging buffers in flight
 
 // findSubDAG (reference src/library/raytracing.cpp:43-87), host side, bounds-checked because the
@@ -122,12 +124,15 @@ struct cbq_context {
 	int queueUsed = 0;
 	cbq::LaunchConfig cfg{};
 	int l2Persist = 1;
-	cudaStream_t windowStream = nullptr;  // stream the access-policy window was last applied to
-	uint64_t windowGeneration = ~0ull;
+	cudaStream_t windowStream[kQueueSlots]{};   // streams the access-policy window has been applied to, and for which generation
+	uint64_t windowGeneration[kQueueSlots]{};
+	int windowUsed = 0;
+	size_t l2Carve = ~(size_t)0;
 
 	// cbq_trace staging (device side), double buffered.
 	cbq::Ray* stageRays[kStages]{};
 	cbq::Hit* stageHits[kStages]{};
+	uint64_t stageCapacity = 0;          // rays each staging buffer holds
 
 	// cbq_raycast_frame_device: primary rays of the frame in 8x4-tile order
 	cbq::Ray* frameRays = nullptr;
@@ -235,17 +240,29 @@ void adoptSubdags(cbq_context* ctx, const cbq::SubDag sd[8])
 	ctx->cfg.stackLevels = maxH + 1;
 }
 
-// Pin the node array in L2 (persisting access-policy window) for kernels on `stream`.
+// Pin the node array in L2 (persisting access-policy window) for kernels on `stream`. Applied once per stream and
+// volume generation: the calls below are not free (cudaDeviceSetLimit synchronises the device), and a caller that
+// alternates between streams must not pay them per launch.
 void applyL2Window(cbq_context* ctx, cudaStream_t stream)
 {
-	if (ctx->windowStream == stream && ctx->windowGeneration == ctx->generation) return;
+	for (int i = 0; i < ctx->windowUsed; i++) {
+		if (ctx->windowStream[i] == stream) {
+			if (ctx->windowGeneration[i] == ctx->generation) return;
+			ctx->windowGeneration[i] = ctx->generation;
+			goto apply;
+		}
+	}
+	if (ctx->windowUsed == kQueueSlots) ctx->windowUsed = 0;
+	ctx->windowStream[ctx->windowUsed] = stream;
+	ctx->windowGeneration[ctx->windowUsed++] = ctx->generation;
+apply:
 	cudaStreamAttrValue attr;
 	std::memset(&attr, 0, sizeof(attr));
 	if (ctx->l2Persist && ctx->volume && ctx->prop.persistingL2CacheMaxSize > 0) {
 		const size_t nodeBytes = (size_t)ctx->nodeCount * 32;
 		const size_t window = std::min(nodeBytes + cbq::kNodeOffset, (size_t)ctx->prop.accessPolicyMaxWindowSize);
 		const size_t carve = std::min((size_t)ctx->prop.persistingL2CacheMaxSize, window);
-		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+		if (carve != ctx->l2Carve) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve); ctx->l2Carve = carve; }
 		attr.accessPolicyWindow.base_ptr = ctx->volume;
 		attr.accessPolicyWindow.num_bytes = window;
 		attr.accessPolicyWindow.hitRatio = window ? (float)std::min(1.0, (double)carve / (double)window) : 0.0f;
@@ -255,16 +272,22 @@ void applyL2Window(cbq_context* ctx, cudaStream_t stream)
 		attr.accessPolicyWindow.num_bytes = 0;
 	}
 	if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
-	ctx->windowStream = stream;
-	ctx->windowGeneration = ctx->generation;
 }
 
-int ensureStaging(cbq_context* ctx)
+int ensureStaging(cbq_context* ctx, uint64_t chunk)
 {
+	if (chunk <= ctx->stageCapacity) return CBQ_OK;
+	CBQ_CUDA(cudaDeviceSynchronize());
 	for (int i = 0; i < kStages; i++) {
-		if (!ctx->stageRays[i]) CBQ_CUDA(cudaMalloc(&ctx->stageRays[i], kPipelineChunk * sizeof(cbq::Ray)));
-		if (!ctx->stageHits[i]) CBQ_CUDA(cudaMalloc(&ctx->stageHits[i], kPipelineChunk * sizeof(cbq::Hit)));
+		cudaFree(ctx->stageRays[i]); cudaFree(ctx->stageHits[i]);
+		ctx->stageRays[i] = nullptr; ctx->stageHits[i] = nullptr;
 	}
+	ctx->stageCapacity = 0;
+	for (int i = 0; i < kStages; i++) {
+		CBQ_CUDA(cudaMalloc(&ctx->stageRays[i], chunk * sizeof(cbq::Ray)));
+		CBQ_CUDA(cudaMalloc(&ctx->stageHits[i], chunk * sizeof(cbq::Hit)));
+	}
+	ctx->stageCapacity = chunk;
 	return CBQ_OK;
 }
 
@@ -883,17 +906,18 @@ namespace {
 // Host rays in, host results out: a three-stage pipeline over chunks -- H2D on copyIn, kernel on stream, D2H on copyOut,
 // kStages staging buffers in flight. With pinned host memory the three overlap; with pageable memory the copies
 // degrade to synchronous but the result is the same. The copy back is the longest leg for 40-byte records, so the first
-// stages are short -- 2^15, 2^16, 2^17 rays -- to get it going early; after that every stage is kPipelineChunk rays.
+// stages are short -- 2^15, 2^16, 2^17 rays -- to get it going early; after that every stage is `chunk` rays.
 // recordBytes = 40 (cbq_hit) or 8 (cbq_hit_compact).
 int tracePipeline(cbq_context* ctx, const cbq_ray* rays, uint64_t n, uint32_t flags, float max_footprint, void* results, size_t recordBytes)
 {
 	if (!ctx->volume) return fail(CBQ_ERROR_NO_VOLUME, "no volume uploaded");
 	if (n == 0) return CBQ_OK;
 	if (!rays || !results) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null ray or hit buffer");
-	int rc = ensureStaging(ctx); if (rc) return rc;
+	const uint64_t chunk = std::min(kPipelineChunkMax, std::max(kPipelineChunkMin, n / 8));
+	int rc = ensureStaging(ctx, chunk); if (rc) return rc;
 	const bool compact = recordBytes == sizeof(cbq_hit_compact);
 	uint8_t* out = static_cast<uint8_t*>(results);
-	uint64_t begin = 0, stage = std::min<uint64_t>(kPipelineChunk, 1u << 15);
+	uint64_t begin = 0, stage = std::min<uint64_t>(chunk, 1u << 15);
 	for (uint64_t c = 0; begin < n; c++) {
 		const int b = (int)(c % kStages);
 		const uint64_t len = std::min(stage, n - begin);
@@ -910,7 +934,7 @@ int tracePipeline(cbq_context* ctx, const cbq_ray* rays, uint64_t n, uint32_t fl
 		CBQ_CUDA(cudaMemcpyAsync(out + begin * recordBytes, ctx->stageHits[b], len * recordBytes, cudaMemcpyDeviceToHost, ctx->copyOut));
 		CBQ_CUDA(cudaEventRecord(ctx->evOut[b], ctx->copyOut));
 		begin += len;
-		stage = std::min<uint64_t>(stage * 2, kPipelineChunk);
+		stage = std::min<uint64_t>(stage * 2, chunk);
 	}
 	CBQ_CUDA(cudaStreamSynchronize(ctx->copyOut));
 	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1099,6 +1123,53 @@ int cbq_rng_points_device(cbq_context* ctx, const uint32_t* d_seeds, uint64_t n,
 	return CBQ_OK;
 }
 
+int cbq_shared_alloc(cbq_context* ctx, uint64_t bytes, void** d_ptr, cbq_ipc_handle* handle)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!d_ptr || !handle || bytes == 0) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad argument");
+	static_assert(sizeof(cbq_ipc_handle) == sizeof(cudaIpcMemHandle_t), "IPC handle size");
+	void* p = nullptr;
+	CBQ_CUDA(cudaMalloc(&p, bytes));            // its own allocation: an IPC handle exports a whole cudaMalloc block
+	cudaError_t e = cudaMemset(p, 0, bytes);
+	if (e == cudaSuccess) e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle), p);
+	if (e != cudaSuccess) { cudaFree(p); return fail(CBQ_ERROR_CUDA, "cbq_shared_alloc: %s", cudaGetErrorString(e)); }
+	*d_ptr = p;
+	return CBQ_OK;
+}
+
+int cbq_shared_open(cbq_context* ctx, const cbq_ipc_handle* handle, void** d_ptr)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!d_ptr || !handle) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");
+	cudaIpcMemHandle_t h;
+	std::memcpy(&h, handle, sizeof(h));
+	CBQ_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return CBQ_OK;
+}
+
+int cbq_shared_close(cbq_context* ctx, void* d_ptr)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (d_ptr) CBQ_CUDA(cudaIpcCloseMemHandle(d_ptr));
+	return CBQ_OK;
+}
+
+int cbq_shared_free(cbq_context* ctx, void* d_ptr)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (d_ptr) { CBQ_CUDA(cudaDeviceSynchronize()); CBQ_CUDA(cudaFree(d_ptr)); }
+	return CBQ_OK;
+}
+
+int cbq_copy_device(cbq_context* ctx, void* d_dst, const void* d_src, uint64_t bytes, void* stream)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (bytes == 0) return CBQ_OK;
+	if (!d_dst || !d_src) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");
+	CBQ_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, stream ? (cudaStream_t)stream : ctx->stream));
+	return CBQ_OK;
+}
+
 int cbq_host_alloc(void** out, uint64_t bytes)
 {
 	if (!out) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");
@@ -1140,7 +1211,7 @@ int cbq_set_option(cbq_context* ctx, const char* key, int64_t value)
 		ctx->orderTickets = 0;         // forget what was learnt
 	} else if (k == "l2_persist") {
 		ctx->l2Persist = value ? 1 : 0;
-		ctx->windowGeneration = ~0ull; // re-apply on next launch
+		ctx->windowUsed = 0;           // re-apply on next launch
 	} else {
 		return fail(CBQ_ERROR_INVALID_ARGUMENT, "unknown option '%s'", key);
 	}

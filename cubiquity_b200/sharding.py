@@ -23,6 +23,66 @@ def tile_rows(height, world_size, rank, tile=64):
     return [b for i, b in enumerate(bands) if i % world_size == rank]
 
 
+def job_chunks(units, unit_items, world_size, rank, chunk_units):
+    """A job of `units` equal units (frames) of `unit_items` items (rays) each: rank's contiguous share of the units, cut
+    into chunks of `chunk_units` units. Returns [(begin, end)] in GLOBAL item indices. A chunk is what one launch traces
+    and one message carries to rank 0."""
+    u0, u1 = split_range(units, world_size, rank)
+    step = max(1, int(chunk_units))
+    return [(u * unit_items, min(u + step, u1) * unit_items) for u in range(u0, u1, step)]
+
+
+def post_receives(dist, out, plans, words_per_item, dst=0):
+    """On rank `dst`: the receives of the whole exchange, straight into the job-sized result tensor `out`
+    (`words_per_item` elements per item), posted before its own work starts. plans[r] = job_chunks(..., rank=r).
+    Round j = chunk j of every other rank, ONE batched (grouped) operation per round, so that the ranks' transfers
+    of a round run side by side instead of queueing behind each other. Returns the work handles."""
+    works = []
+    rounds = max((len(p) for r, p in enumerate(plans) if r != dst), default=0)
+    for j in range(rounds):
+        ops = []
+        for src, plan in enumerate(plans):
+            if src != dst and j < len(plan) and plan[j][1] > plan[j][0]:
+                b, e = plan[j]
+                ops.append(dist.P2POp(dist.irecv, out[b * words_per_item:e * words_per_item], src))
+        if ops:
+            works += dist.batch_isend_irecv(ops)
+    return works
+
+
+def send_chunk(dist, piece, dst=0):
+    """On the other ranks: ship one finished chunk (the matching half of a post_receives round); the transfer runs
+    beside the trace of the next chunk."""
+    return dist.batch_isend_irecv([dist.P2POp(dist.isend, piece, dst)])
+
+
+class SharedResults:
+    """The job's result buffer: allocated on rank `dst`'s GPU (cbq_shared_alloc), opened by every other rank as a
+    device pointer into that GPU's memory (CUDA IPC; the accesses travel over NVLink). `ptr` is the buffer in THIS
+    process's address space -- pass ptr + offset as the result pointer of a trace (the kernel's stores are the
+    transfer) or as the destination of cbq_copy_device (copy engines)."""
+
+    def __init__(self, dist, ctx, nbytes, device, dst=0):
+        import torch
+        self.ctx, self.owner = ctx, dist.get_rank() == dst
+        h = torch.zeros(64, dtype=torch.uint8, device=device)
+        if self.owner:
+            self.ptr, handle = ctx.shared_alloc(nbytes)
+            h.copy_(torch.frombuffer(bytearray(handle), dtype=torch.uint8))
+        dist.broadcast(h, src=dst)
+        if not self.owner:
+            self.ptr = ctx.shared_open(bytes(h.cpu().numpy().tobytes()))
+        self.nbytes = nbytes
+
+    def close(self, dist):
+        dist.barrier()                    # nobody may still be writing when the owner frees
+        if self.owner:
+            self.ctx.shared_free(self.ptr)
+        else:
+            self.ctx.shared_close(self.ptr)
+        self.ptr = 0
+
+
 def broadcast_volume(dist, nodes, root, device=None, src=0):
     """Replicate the DAG: rank `src` passes (nodes, root); the others pass (None, None)."""
     import torch

@@ -260,6 +260,20 @@ int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_para
 int cbq_rng_points_device(cbq_context* ctx, const uint32_t* d_seeds, uint64_t n, int draws, float* d_points,
                           uint32_t* d_states, void* stream);
 
+/* ---- multi-GPU: results gathered over peer memory ----------------------------------- */
+
+/* The reference is single-GPU; this is the one exchange the partitioned path needs: every GPU's results end up in ONE
+ * buffer on one GPU. That buffer is allocated here (cudaMalloc, zero-filled) and exported as a CUDA IPC handle; the
+ * other processes (one per GPU) open it and get a device pointer that addresses the owner's HBM over NVLink. A rank
+ * then either passes that pointer (+ its slice offset) as the result buffer of cbq_trace_compact_device -- the ray-cast
+ * kernel's stores ARE the transfer -- or ships finished chunks with cbq_copy_device (copy engines, no SM involved). */
+typedef struct cbq_ipc_handle { unsigned char bytes[64]; } cbq_ipc_handle;
+int cbq_shared_alloc(cbq_context* ctx, uint64_t bytes, void** d_ptr, cbq_ipc_handle* handle);
+int cbq_shared_open(cbq_context* ctx, const cbq_ipc_handle* handle, void** d_ptr);
+int cbq_shared_close(cbq_context* ctx, void* d_ptr);     /* a pointer from cbq_shared_open */
+int cbq_shared_free(cbq_context* ctx, void* d_ptr);      /* a pointer from cbq_shared_alloc */
+int cbq_copy_device(cbq_context* ctx, void* d_dst, const void* d_src, uint64_t bytes, void* stream);
+
 /* ---- pinned host memory, tuning, counters ---------------------------------------------- */
 
 int cbq_host_alloc(void** out, uint64_t bytes);

@@ -105,20 +105,13 @@ static inline void record_event(uint8_t e)
 	}
 }
 
-/* EXPERIMENT (design study for DESIGN.md section 10, never used by a parity check): when > 0, a descend into a node of
- * this height that the ray enters from outside (tEntry > 0, LOD off) is replaced by a voxel-by-voxel DDA through the
- * node's cube -- what a GPU "occupancy brick" layer would do -- and the traversal rejoins the reference's loop with
- * the reference's own pop rule when the DDA leaves the cube. scripts/brick_equivalence.py counts how often the result
- * differs from the reference's. */
-static int g_brickHeight = 0;
-void cbqo_experiment_set_brick_height(int h) { g_brickHeight = h; }
-/* EXPERIMENT, same status: when > 0, a sub-DAG the ray enters from outside is crossed by a flat DDA over cells of this
- * height (what a dense top-level grid would do); occupied cells are traversed by the reference's loop with the cell's node
- * as a local root. */
-static int g_gridHeight = 0;
-static uint64_t g_gridEntries = 0, g_gridCells = 0;
-void cbqo_experiment_set_grid_height(int h) { g_gridHeight = h; }
-void cbqo_experiment_grid_counters(uint64_t out[2]) { out[0] = g_gridEntries; out[1] = g_gridCells; g_gridEntries = g_gridCells = 0; }
+/* The design-study variants of the traversal (a voxel-by-voxel walk of bottom-level bricks, a flat grid walk over the top
+ * of a sub-DAG) live in oracle/experiments/ and are compiled in ONLY with -DCBQO_EXPERIMENTS, into a
+ * library of their own (make experiments) that scripts/brick_equivalence.py loads. The parity checker built by
+ * `make port` contains none of that code and no mutable switches. */
+#ifdef CBQO_EXPERIMENTS
+#include "experiments/switches.inc"
+#endif
 
 /* ---------------------------------------------------------------- ray cast */
 
@@ -173,69 +166,9 @@ static int esvo_node(const uint32_t* nodes, uint32_t node, const int32_t nodePos
 	if (st) st->subdag_entries++;
 	record_event('O');
 
-	if (g_gridHeight > 0 && nodeHeight > g_gridHeight && nodeEntry > 0.0f && maxFootprint == -1.0f) {
-		/* ---- experiment: the top of this sub-DAG as a flat grid of cells 2^g_gridHeight voxels wide ---- */
-		const int G = g_gridHeight;
-		const int32_t cell = (int32_t)(1u << G);
-		int32_t v[3] = { nodePos[0], nodePos[1], nodePos[2] };
-		for (int32_t s2 = (int32_t)(nodeSize / 2); s2 >= cell; s2 /= 2) {        /* entry cell: findFirstChild, level by level */
-			int32_t c2[3], b2[3];
-			for (int a = 0; a < 3; a++) c2[a] = (int32_t)((uint32_t)v[a] + (uint32_t)s2);
-			first_child(nodeEntry, o, inv, c2, b2);
-			for (int a = 0; a < 3; a++) v[a] = (int32_t)((uint32_t)v[a] + (uint32_t)(b2[a] * s2));
-		}
-		const int saved = g_gridHeight;
-		g_gridEntries++;
-		for (int guard = 0; guard < 100000; guard++) {
-			g_gridCells++;
-			uint32_t n = node;
-			int32_t lower[3] = { nodePos[0], nodePos[1], nodePos[2] };
-			int32_t sz = (int32_t)nodeSize;
-			uint32_t value = 0;
-			int internalCell = 0;
-			while (sz > cell) {
-				sz /= 2;
-				uint32_t sl = 0;
-				for (int a = 0; a < 3; a++) {
-					const int bit = ((int32_t)((uint32_t)v[a] - (uint32_t)lower[a]) >= sz) ? 1 : 0;
-					lower[a] = (int32_t)((uint32_t)lower[a] + (uint32_t)(bit * sz));
-					sl |= (uint32_t)bit << a;
-				}
-				const uint32_t c = nodes[(uint64_t)n * 8 + (sl ^ signBits)];
-				if (c < MATERIAL_COUNT) { value = c; break; }
-				n = c;
-				if (sz == cell) internalCell = 1;
-			}
-			if (internalCell) {
-				g_gridHeight = 0;
-				const int got = esvo_node(nodes, n, lower, G, o, d, sign, signBits, surf, maxFootprint, hit, st);
-				g_gridHeight = saved;
-				if (got || hit->pad) return got;
-			} else if (value > 0) {
-				float c0[3];
-				for (int a = 0; a < 3; a++) c0[a] = ((float)lower[a] - o[a]) * inv[a];
-				const float te = greatest3(c0);
-				hit->hit = 1;
-				hit->distance = te;
-				if (surf) {
-					hit->material = value;
-					for (int a = 0; a < 3; a++) hit->normal[a] = ((te == c0[a]) ? 1.0f : 0.0f) * (-sign[a]);
-				}
-				return 1;
-			}
-			float u[3];
-			int moved = 0;
-			for (int a = 0; a < 3; a++) u[a] = ((float)(int32_t)((uint32_t)v[a] + (uint32_t)cell) - o[a]) * inv[a];
-			const float ex = least3(u);
-			for (int a = 0; a < 3; a++) {
-				if (u[a] <= ex) { v[a] = (int32_t)((uint32_t)v[a] + (uint32_t)cell); moved = 1; }
-				if ((int32_t)((uint32_t)v[a] - (uint32_t)nodePos[a]) >= (int32_t)nodeSize) return 0;   /* left the sub-DAG */
-			}
-			if (!moved) { hit->pad = 1; return 0; }
-		}
-		hit->pad = 1;
-		return 0;
-	}
+#ifdef CBQO_EXPERIMENTS
+#include "experiments/grid_walk.inc"
+#endif
 
 	const int startHeight = nodeHeight;
 	int32_t childSize = (int32_t)(nodeSize / 2);
@@ -275,79 +208,9 @@ static int esvo_node(const uint32_t* nodes, uint32_t node, const int32_t nodePos
 			const float tEntry = greatest3(c0);
 			const int internal = child >= MATERIAL_COUNT;
 			const int bigEnough = ((float)childSize / tExit) > maxFootprint;
-			if (internal && bigEnough && g_brickHeight > 0 && nodeHeight - 1 == g_brickHeight && tEntry > 0.0f && maxFootprint == -1.0f) {
-				/* ---- experiment: the child's cube as a brick ---- */
-				if (tExit < lastExit) stack[nodeHeight] = node;          /* the reference's push on this descend */
-				int32_t v[3] = { pos[0], pos[1], pos[2] };
-				for (int32_t s2 = childSize / 2; s2 >= 1; s2 /= 2) {         /* entry voxel: findFirstChild, level by level */
-					int32_t c2[3], b2[3];
-					for (int a = 0; a < 3; a++) c2[a] = (int32_t)((uint32_t)v[a] + (uint32_t)s2);
-					first_child(tEntry, o, inv, c2, b2);
-					for (int a = 0; a < 3; a++) v[a] = (int32_t)((uint32_t)v[a] + (uint32_t)(b2[a] * s2));
-				}
-				int left = 0;
-				int32_t prev[3] = { v[0], v[1], v[2] };
-				while (!found && !left) {
-					if (++trips > cap) { hit->pad = 1; return 0; }
-					/* look the voxel up: walk the brick's own sub-tree */
-					uint32_t n = child;
-					int32_t lower[3] = { pos[0], pos[1], pos[2] };
-					int32_t sz = childSize;
-					uint32_t value = 0;
-					for (;;) {
-						sz /= 2;
-						uint32_t sl = 0;
-						for (int a = 0; a < 3; a++) {
-							const int bit = ((int32_t)((uint32_t)v[a] - (uint32_t)lower[a]) >= sz) ? 1 : 0;
-							lower[a] = (int32_t)((uint32_t)lower[a] + (uint32_t)(bit * sz));
-							sl |= (uint32_t)bit << a;
-						}
-						const uint32_t c = nodes[(uint64_t)n * 8 + (sl ^ signBits)];
-						if (c < MATERIAL_COUNT || sz == 1) { value = c; break; }
-						n = c;
-					}
-					if (value > 0) {
-						/* the reference reports the whole uniform cell (lower, sz), not the voxel */
-						float c0[3];
-						for (int a = 0; a < 3; a++) c0[a] = ((float)lower[a] - o[a]) * inv[a];
-						const float te = greatest3(c0);
-						found = 1;
-						hit->hit = 1;
-						hit->distance = te;
-						if (surf) {
-							hit->material = value;
-							for (int a = 0; a < 3; a++) hit->normal[a] = ((te == c0[a]) ? 1.0f : 0.0f) * (-sign[a]);
-						}
-						break;
-					}
-					float u[3];
-					for (int a = 0; a < 3; a++) u[a] = ((float)(int32_t)((uint32_t)v[a] + 1u) - o[a]) * inv[a];
-					const float ex = least3(u);
-					for (int a = 0; a < 3; a++) {
-						prev[a] = v[a];
-						if (u[a] <= ex) v[a] = (int32_t)((uint32_t)v[a] + 1u);
-						if ((int32_t)((uint32_t)v[a] - (uint32_t)pos[a]) >= childSize) left = 1;
-					}
-					if (v[0] == prev[0] && v[1] == prev[1] && v[2] == prev[2]) { hit->pad = 1; return 0; }   /* NaN planes: no progress */
-				}
-				if (found) break;
-				/* left the cube: the reference's pop, from voxel-granular positions */
-				uint32_t diff = 0;
-				for (int a = 0; a < 3; a++) diff |= (uint32_t)(prev[a] ^ v[a]);
-				const int msb = msb_index(diff);
-				nodeHeight = msb + 1;
-				node = stack[nodeHeight <= ROOT_HEIGHT ? nodeHeight : ROOT_HEIGHT];
-				if (nodeHeight <= startHeight) {
-					childSize = (int32_t)(1u << msb);
-					for (int a = 0; a < 3; a++) {
-						id[a] = (v[a] >> msb) & 1;
-						pos[a] = (int32_t)(((uint32_t)(v[a] >> nodeHeight)) << nodeHeight);
-						pos[a] = (int32_t)((uint32_t)pos[a] + (uint32_t)(id[a] * childSize));
-					}
-				}
-				lastExit = 0.0f;
-				continue;
-			}
+#ifdef CBQO_EXPERIMENTS
+#include "experiments/brick_walk.inc"
+#endif
 			if (internal && bigEnough) {
 				if (st) st->descents++;
 				g_eventHeight = nodeHeight;

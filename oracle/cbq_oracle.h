@@ -108,9 +108,11 @@ uint32_t cbqo_fmix32(uint32_t h);
 }
 #endif
 /* EXPERIMENT (design study): see cbq_oracle.c. 0 = off (the default; every test runs with it off). */
+#ifdef CBQO_EXPERIMENTS   /* oracle/experiments/, never part of the parity checker */
 void cbqo_experiment_set_brick_height(int h);
 void cbqo_experiment_set_grid_height(int h);
 void cbqo_experiment_grid_counters(uint64_t out[2]);   /* sub-DAGs crossed by the grid walk, grid cells visited; resets */
+#endif
 
 /* Event strings per ray ('O' sub-DAG entered, 'D' descend, 'A' advance, 'P' advance + pop, 'H' hit): events is n * cap bytes. */
 void cbqo_trace_events(const uint32_t* nodes, const cbqo_subdag sd[8], const cbqo_ray* rays, uint64_t n,

@@ -81,12 +81,17 @@ def _ptr(a):
 
 
 class Port:
-    """The plain-C restatement."""
+    """The plain-C restatement. experiments=True loads the design-study build (oracle/experiments/ compiled in, `make
+    experiments`) instead of the parity checker; only scripts/brick_equivalence.py asks for it."""
 
-    def __init__(self):
-        if not os.path.exists(PORT_SO):
+    def __init__(self, experiments=False):
+        so = PORT_SO
+        if experiments:
+            so = os.path.join(os.path.dirname(PORT_SO), "libcbq_oracle_experiments.so")
+            subprocess.run(["make", "-s", "-C", HERE, "experiments"], check=True)
+        elif not os.path.exists(PORT_SO):
             build(port=True, ref=False)
-        L = self.lib = C.CDLL(PORT_SO)
+        L = self.lib = C.CDLL(so)
         L.cbqo_trace.restype = C.c_double
         L.cbqo_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_float,
                                  C.c_void_p, C.c_int, C.c_void_p]

@@ -16,17 +16,15 @@ def main():
     from oracle import pyoracle
     import bench
     from conftest import mixed_rays
-    port = pyoracle.Port()
+    port = pyoracle.Port(experiments=True)        # the design-study build; the parity checker has no such switches
     port.lib.cbqo_experiment_set_brick_height.restype = None
     port.lib.cbqo_experiment_set_grid_height.restype = None
     threads = 1                                   # the switch is a process-wide global: keep the comparison single-threaded per call
     for kind, log2 in (("terrain", 12), ("sphere_noise", 8), ("soup", 9), ("city", 12)):
         sc = api.Scene(kind, log2, 1)
         sub = port.find_subdags(sc.nodes, sc.root)
-        class B: pass
-        b = B(); b.lower, b.upper = sc.lower, sc.upper
-        cam, pos, yaw = bench.orbit_camera(api, b, 0)
-        prim = port.camera_rays(cam, 1920, 1080).reshape(1080, 1920)[::9].reshape(-1)
+        pos, yaw = bench.orbit_pose(sc.lower, sc.upper, 0, bench.FRAMES)
+        prim = port.camera_rays(port.camera(pos, bench.PITCH, yaw), 1920, 1080).reshape(1080, 1920)[::9].reshape(-1)
         sets = {"primary (every 9th row)": np.ascontiguousarray(prim), "mixed incl. degenerate": mixed_rays(sc.lower, sc.upper, 200000, seed=3)}
         for name, rays in sets.items():
             port.lib.cbqo_experiment_set_brick_height(0)

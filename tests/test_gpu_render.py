@@ -20,7 +20,16 @@ def oracle_params(pyoracle, p):
 
 @pytest.mark.parametrize("kind,size_log2", [("sphere_noise", 8), ("soup", 8)])
 @pytest.mark.parametrize("bounces,spp", [(0, 1), (1, 2), (4, 3)])
-def test_recursive_variant_is_bit_exact(gpu, port, api, scenes, kind, size_log2, bounces, spp):
+def reference_image(ref, sc, cam, p):
+    """ONE hop: the same frame from the reference's own PathtracingDemo::traceSingleRay / traceSingleRayRecurse
+    (unmodified pathtracing_demo.cpp in oracle/_ref, per-pixel RNG streams seeded as cbq_render seeds them)."""
+    from oracle import pyoracle
+    op = pyoracle.pt_params_from(p)
+    img, _ = ref.pt_render(sc.nodes, sc.root, sc.colours, list(cam.position), -(PI_F / 4.0), 0.0, op)
+    return img
+
+
+def test_recursive_variant_is_bit_exact(gpu, port, ref, api, scenes, kind, size_log2, bounces, spp):
     from oracle import pyoracle
     sc = scenes(kind, size_log2)
     gpu.upload(sc.nodes, sc.root, sc.colours)
@@ -32,6 +41,8 @@ def test_recursive_variant_is_bit_exact(gpu, port, api, scenes, kind, size_log2,
     assert nrays > 160 * 120 * spp
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "max abs diff %g" % np.abs(got - want).max()
     assert got.std() > 0.05
+    direct = reference_image(ref, sc, cam, p)
+    assert np.array_equal(got.view(np.uint32), direct.view(np.uint32)), "vs the reference itself: max abs diff %g" % np.abs(got - direct).max()
 
 
 def test_one_bounce_variant_within_gamma_tolerance(gpu, port, api, scenes):
@@ -74,7 +85,7 @@ def test_flags_tiles_and_accumulation(gpu, port, api, scenes):
     assert np.array_equal(acc, whole)
 
 
-def test_soup_four_bounces_config4_in_miniature(gpu, port, api):
+def test_soup_four_bounces_config4_in_miniature(gpu, port, ref, api):
     """BASELINE config 4 at reduced size: voxelised solids (2048^3), 4 bounces, 2 spp, LOD 0.0035."""
     from oracle import pyoracle
     sc = api.Scene("soup", 11, seed=5)
@@ -86,6 +97,10 @@ def test_soup_four_bounces_config4_in_miniature(gpu, port, api):
     got = gpu.render(cam, p)
     assert nrays > 4 * 320 * 180
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # one hop, on a 96-row band (the reference's tracer is single threaded)
+    band = api.pt_params(320, 180, spp=2, bounces=4, variant=api.VARIANT_RECURSIVE, rect=(0, 40, 320, 136))
+    direct = reference_image(ref, sc, cam, band)
+    assert np.array_equal(got[40:136].view(np.uint32), direct[40:136].view(np.uint32))
 
 
 def test_render_device_pointer_and_sample_sharding(gpu, port, api, scenes):

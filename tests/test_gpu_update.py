@@ -95,7 +95,12 @@ def test_city_65536_with_runtime_edits_and_lod(gpu, port, ref, api):
         assert gpu.subdags().tobytes() == sd.tobytes()
         for mf in (-1.0, 0.0035):
             want, _, _ = port.trace(nodes, sd, rays, True, mf, threads=8)
-            assert_hits_identical(gpu.intersect_volume(rays, True, mf), want, "city edit %d mf %g" % (step, mf))
+            got = gpu.intersect_volume(rays, True, mf)
+            assert_hits_identical(got, want, "city edit %d mf %g" % (step, mf))
+            # one hop: the edited volume `v` IS the reference's object; trace the rays the port could finish with it
+            ok = want["pad"] == 0
+            direct, _ = v.intersect(np.ascontiguousarray(rays[ok]), True, mf, threads=8)
+            assert_hits_identical(np.ascontiguousarray(got[ok]), direct, "city edit %d mf %g vs the reference itself" % (step, mf))
         p = api.pt_params(160, 90, spp=1, bounces=2, variant=api.VARIANT_RECURSIVE, frame_id=step)
         op = pyoracle.pt_params_from(p)
         want_img, _, _ = port.render(nodes, sd, sc.colours, ocam, op, threads=8)

@@ -22,6 +22,7 @@ def free_port():
 
 def worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
     import torch
     from cubiquity_b200 import api, sharding
@@ -63,6 +64,29 @@ def worker(rank, world, port, out_dir):
     gathered = [None] * world
     dist.all_gather_object(gathered, hits.tobytes())
 
+    # the bench's job exchange: a job of 5 "frames" (16-row strips of the image), contiguous shares, one message per chunk
+    # to rank 0 while the next chunk is computed. Results travel as 8-byte compact records.
+    from test_host_shim import compact_of
+    strip = 16 * w
+    plans = [sharding.job_chunks(5, strip, world, r, 1) for r in range(world)]
+    job_out = torch.zeros(5 * strip * 2, dtype=torch.int32)
+    works = sharding.post_receives(dist, job_out, plans, 2) if rank == 0 else []
+    for b0, b1 in plans[rank]:
+        piece, _, _ = oracle.trace(nodes, sd, rays[b0:b1], True, -1.0)
+        words = torch.from_numpy(compact_of(piece, api).view(np.int32).reshape(-1).copy())
+        if rank == 0:
+            job_out[b0 * 2:b1 * 2] = words
+        else:
+            works += sharding.send_chunk(dist, words)
+    for wk in works:
+        wk.wait()
+    # sample-sharded path tracing: every rank renders its share of the samples of the whole frame, one reduce
+    s0, s1 = sharding.split_range(4, world, rank)
+    part = np.zeros((h, w, 3), dtype=np.float32)
+    oracle.render(nodes, sd, colours, ocam, pyoracle.PtParams(w, h, s1 - s0, 2, 1, 1, 1, 1, 0.0035, 10 + s0, 0, 0, w, h, 0), accum=part)
+    tp = torch.from_numpy(part)
+    sharding.reduce_image(dist, tp, dst=0)
+
     # an "edit" on rank 0: append a copy of the root with one octant cleared, ship only the tail
     if rank == 0:
         new_root = nodes[root].copy()
@@ -78,6 +102,8 @@ def worker(rank, world, port, out_dir):
 
     if rank == 0:
         np.save(os.path.join(out_dir, "image.npy"), t.numpy())
+        np.save(os.path.join(out_dir, "job.npy"), job_out.numpy())
+        np.save(os.path.join(out_dir, "samples.npy"), tp.numpy())
         np.save(os.path.join(out_dir, "hits.npy"), np.frombuffer(b"".join(gathered), dtype=pyoracle.HIT_DTYPE))
         np.save(os.path.join(out_dir, "nodes.npy"), nodes)
         np.save(os.path.join(out_dir, "meta.npy"), np.array([root, froot, dirty]))
@@ -106,6 +132,14 @@ def test_two_ranks_reproduce_the_single_process_result(tmp_path, port, api):
     rays = port.camera_rays(ocam, w, h)
     want, _, _ = port.trace(nodes, sd, rays, True, -1.0)
     assert np.load(tmp_path / "hits.npy").tobytes() == want.tobytes()
+    # the chunked job exchange assembled exactly the single-process result on rank 0
+    from test_host_shim import compact_of
+    job = np.load(tmp_path / "job.npy").view(api.COMPACT_DTYPE).reshape(-1)
+    assert job.tobytes() == compact_of(want[:5 * 16 * w], api).tobytes()
+    assert api.expand_hits(rays[:len(job)], job).tobytes() == want[:len(job)].tobytes()
+    # sample sharding: the same 4 samples per pixel whoever renders them (float sums regrouped: equal to rounding)
+    four, _, _ = port.render(nodes, sd, colours, ocam, pyoracle.PtParams(w, h, 4, 2, 1, 1, 1, 1, 0.0035, 10, 0, 0, w, h, 0))
+    np.testing.assert_allclose(np.load(tmp_path / "samples.npy"), four, rtol=2e-6, atol=1e-6)
     # the delta broadcast left both ranks with the same edited array
     f0, f1 = np.load(tmp_path / "fresh_0.npy"), np.load(tmp_path / "fresh_1.npy")
     assert np.array_equal(f0, f1) and len(f0) == len(nodes) + 1 and dirty == len(nodes) and froot == len(nodes)
