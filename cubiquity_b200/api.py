@@ -121,7 +121,7 @@ def load_library():
     L.cbq_render_device.argtypes = [vp, C.POINTER(Camera), C.POINTER(PtParams), vp, vp]
     L.cbq_rng_points_device.argtypes = [vp, vp, u64, i32, vp, vp, vp]
     L.cbq_shared_alloc.argtypes = [vp, u64, C.POINTER(vp), vp]
-    L.cbq_shared_open.argtypes = [vp, vp, C.POINTER(vp)]
+    L.cbq_shared_open.argtypes = [vp, vp, u64, C.POINTER(vp)]
     L.cbq_shared_close.argtypes = [vp, vp]
     L.cbq_shared_free.argtypes = [vp, vp]
     L.cbq_copy_device.argtypes = [vp, vp, vp, u64, vp]
@@ -475,10 +475,10 @@ class Context:
         _check(self.L.cbq_shared_alloc(self._h, int(nbytes), C.byref(p), h))
         return int(p.value), bytes(h)
 
-    def shared_open(self, handle):
+    def shared_open(self, handle, nbytes):
         p = C.c_void_p()
         h = (C.c_ubyte * 64).from_buffer_copy(bytes(handle))
-        _check(self.L.cbq_shared_open(self._h, h, C.byref(p)))
+        _check(self.L.cbq_shared_open(self._h, h, int(nbytes), C.byref(p)))
         return int(p.value)
 
     def shared_close(self, ptr):

@@ -145,6 +145,8 @@ struct cbq_context {
 
 	// Cost feedback for coherent batches (refill threshold 32): the kernel records how long each 32-ray ticket
 	// took; the next launch over the same batch (same ray buffer, size and stream) deals them longest first.
+	std::vector<std::pair<uintptr_t, uintptr_t>> remote;   // [begin, end) of the buffers opened with cbq_shared_open
+	int parkResults = 0;              // option "park_results": use the coalescing sink even for a local buffer (testing)
 	int adaptiveOrder = 1;
 	uint32_t* ticketCost = nullptr;
 	uint32_t* ticketHist = nullptr;
@@ -345,6 +347,12 @@ int traceDevice(cbq_context* ctx, const cbq::Ray* dRays, uint64_t n, uint32_t fl
 	std::memset(&a, 0, sizeof(a));
 	a.volume = ctx->view();
 	a.rays = dRays; a.hits = dHits; a.compact = dCompact; a.count = n; a.maxFootprint = maxFootprint;
+	if (dCompact) {
+		// A result buffer opened from another process / GPU (cbq_shared_open) is written over NVLink: say so to the kernel.
+		const uintptr_t p = reinterpret_cast<uintptr_t>(dCompact);
+		for (const auto& r : ctx->remote) if (p >= r.first && p < r.second) a.remoteResults = true;
+		if (ctx->parkResults) a.remoteResults = true;
+	}
 	a.abandoned = ctx->abandonedPtr();
 	if (cam) { a.camera = *cam; a.width = width; a.height = height; }
 	int rc = nextQueue(ctx, stream, &a.queue);
@@ -1137,20 +1145,25 @@ int cbq_shared_alloc(cbq_context* ctx, uint64_t bytes, void** d_ptr, cbq_ipc_han
 	return CBQ_OK;
 }
 
-int cbq_shared_open(cbq_context* ctx, const cbq_ipc_handle* handle, void** d_ptr)
+int cbq_shared_open(cbq_context* ctx, const cbq_ipc_handle* handle, uint64_t bytes, void** d_ptr)
 {
 	int rc = bind(ctx); if (rc) return rc;
-	if (!d_ptr || !handle) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");
+	if (!d_ptr || !handle || bytes == 0) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad argument");
 	cudaIpcMemHandle_t h;
 	std::memcpy(&h, handle, sizeof(h));
 	CBQ_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+	// Remember the range: a trace whose results land in it stores them a warp at a time (ParkedCompactSink).
+	ctx->remote.push_back({ reinterpret_cast<uintptr_t>(*d_ptr), reinterpret_cast<uintptr_t>(*d_ptr) + bytes });
 	return CBQ_OK;
 }
 
 int cbq_shared_close(cbq_context* ctx, void* d_ptr)
 {
 	int rc = bind(ctx); if (rc) return rc;
-	if (d_ptr) CBQ_CUDA(cudaIpcCloseMemHandle(d_ptr));
+	if (!d_ptr) return CBQ_OK;
+	CBQ_CUDA(cudaDeviceSynchronize());
+	for (size_t i = 0; i < ctx->remote.size(); i++) if (ctx->remote[i].first == reinterpret_cast<uintptr_t>(d_ptr)) { ctx->remote.erase(ctx->remote.begin() + i); break; }
+	CBQ_CUDA(cudaIpcCloseMemHandle(d_ptr));
 	return CBQ_OK;
 }
 
@@ -1206,6 +1219,8 @@ int cbq_set_option(cbq_context* ctx, const char* key, int64_t value)
 	} else if (k == "order_refresh") {
 		if (value < 1 || value > 1024) return fail(CBQ_ERROR_INVALID_ARGUMENT, "order_refresh must be in [1, 1024]");
 		ctx->orderRefresh = (int)value;
+	} else if (k == "park_results") {
+		ctx->parkResults = value ? 1 : 0;
 	} else if (k == "adaptive_order") {
 		ctx->adaptiveOrder = value ? 1 : 0;
 		ctx->orderTickets = 0;         // forget what was learnt
@@ -1228,6 +1243,7 @@ int cbq_get_option(cbq_context* ctx, const char* key, int64_t* value)
 	else if (k == "refill_quantum") *value = ctx->cfg.refillQuantum;
 	else if (k == "l2_persist") *value = ctx->l2Persist;
 	else if (k == "adaptive_order") *value = ctx->adaptiveOrder;
+	else if (k == "park_results") *value = ctx->parkResults;
 	else if (k == "order_refresh") *value = ctx->orderRefresh;
 	else if (k == "sample_group") *value = ctx->cfg.sampleGroup;
 	else if (k == "sm_count") *value = ctx->cfg.smCount;

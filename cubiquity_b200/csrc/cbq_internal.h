@@ -81,6 +81,7 @@ struct TraceArgs {
 	uint32_t countScale;
 	uint8_t* flags;
 	cbq_hit_compact* compact;        // != nullptr: 8-byte results (cbq_trace_compact) instead of `hits`
+	bool remoteResults;              // `compact` lives in another GPU's memory: coalesce the stores per warp (ParkedCompactSink)
 	uint32_t untileWidth;            // != 0: rays are in 8x4-tile order of an image this wide; write hits row-major
 	// optional cost feedback (refillThreshold == 32 only): deal the 32-ray tickets in this order / record their cost
 	const uint32_t* ticketOrder;     // permutation of [0, ceil(count / 32)), or nullptr

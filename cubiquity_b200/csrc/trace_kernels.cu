@@ -121,12 +121,14 @@ struct CameraSource {
 // Result sinks. FullSink writes the 40-byte record; FlagSink one byte (hit or not), which is all a
 // shadow ray needs (gatherLighting only tests .hit, reference pathtracing_demo.cpp:96,111).
 struct FullSink {
+	static constexpr bool kParked = false;
 	Hit* __restrict__ hits;
 	static constexpr bool kNeedsPosition = true;
 	__device__ __forceinline__ void write(uint64_t slot, const Hit& h) const { storeHit(hits, slot, h); }
 };
 // Rays arrive in 8x4-tile order (primaryRays, tiled); results go back to row-major pixel order.
 struct TiledSink {
+	static constexpr bool kParked = false;
 	Hit* __restrict__ hits;
 	uint32_t width, tilesX;
 	static constexpr bool kNeedsPosition = true;
@@ -138,19 +140,32 @@ struct TiledSink {
 	}
 };
 // 8-byte results (cbq_hit_compact): no position, so the ray is not fetched again and one 64-bit store replaces five.
+__device__ __forceinline__ uint2 compactRecord(const Hit& h)
+{
+	const uint32_t nx = __float_as_uint(h.normal[0]), ny = __float_as_uint(h.normal[1]), nz = __float_as_uint(h.normal[2]);
+	const uint32_t normal = ((nx << 1) != 0u ? 1u : 0u) | (nx >> 31) << 1 | ((ny << 1) != 0u ? 4u : 0u) | (ny >> 31) << 3 |
+	                        ((nz << 1) != 0u ? 16u : 0u) | (nz >> 31) << 5;
+	const uint32_t code = (h.material & 0xffu) | normal << 8 | (h.hit ? 1u << 14 : 0u) | (h.status ? 1u << 15 : 0u);
+	return make_uint2(__float_as_uint(h.distance), code);
+}
 struct CompactSink {
 	cbq_hit_compact* __restrict__ hits;
 	static constexpr bool kNeedsPosition = false;
-	__device__ __forceinline__ void write(uint64_t slot, const Hit& h) const
-	{
-		const uint32_t nx = __float_as_uint(h.normal[0]), ny = __float_as_uint(h.normal[1]), nz = __float_as_uint(h.normal[2]);
-		const uint32_t normal = ((nx << 1) != 0u ? 1u : 0u) | (nx >> 31) << 1 | ((ny << 1) != 0u ? 4u : 0u) | (ny >> 31) << 3 |
-		                        ((nz << 1) != 0u ? 16u : 0u) | (nz >> 31) << 5;
-		const uint32_t code = (h.material & 0xffu) | normal << 8 | (h.hit ? 1u << 14 : 0u) | (h.status ? 1u << 15 : 0u);
-		reinterpret_cast<uint2*>(hits)[slot] = make_uint2(__float_as_uint(h.distance), code);
-	}
+	static constexpr bool kParked = false;
+	__device__ __forceinline__ void write(uint64_t slot, const Hit& h) const { reinterpret_cast<uint2*>(hits)[slot] = compactRecord(h); }
+};
+// The same records for a buffer in ANOTHER GPU's memory (multi-GPU gather over NVLink, cbq_shared_open): a finished ray
+// parks its 8 bytes in two registers and the warp stores them when it takes its next rays -- for tile-ordered batches
+// all 32 lanes at once, consecutive slots, i.e. two full 128-byte NVLink writes instead of thirty-two 8-byte ones.
+// (Stored one by one as rays finish, eight GPUs' results saturate the receiver's link: 0.55 scaling efficiency.)
+struct ParkedCompactSink {
+	cbq_hit_compact* __restrict__ hits;
+	static constexpr bool kNeedsPosition = false;
+	static constexpr bool kParked = true;
+	__device__ __forceinline__ void write(uint64_t slot, uint2 record) const { reinterpret_cast<uint2*>(hits)[slot] = record; }
 };
 struct FlagSink {
+	static constexpr bool kParked = false;
 	uint8_t* __restrict__ flags;
 	static constexpr bool kNeedsPosition = false;
 	__device__ __forceinline__ void write(uint64_t slot, const Hit& h) const { flags[slot] = (uint8_t)h.hit; }
@@ -197,8 +212,16 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 	// the tickets longest first (ticketOrder), which removes most of the end-of-kernel tail.
 	uint32_t rounds = 0;      // since the current ticket was claimed
 
+	// Sink::kParked: the result of the lane's finished ray, waiting to be stored (see ParkedCompactSink).
+	uint2 parked = make_uint2(0u, 0u);
+	bool hasParked = false;
+
 	for (;;) {
 		const unsigned idle = __ballot_sync(kFullMask, s.phase == kPhaseIdle);
+		if (Sink::kParked && hasParked && (drained || idle == kFullMask || __popc(idle) >= refillThreshold)) {
+			if constexpr (Sink::kParked) sink.write(slot, parked);
+			hasParked = false;
+		}
 		if (idle != 0u && !drained && (__popc(idle) >= refillThreshold || idle == kFullMask)) {
 			// Only whole groups of `refillQuantum` tickets are dealt (a power of two <= 32): with tile-ordered
 			// rays a quantum of 16 keeps every refill an aligned 8x2-pixel half tile, so the warp's ticket
@@ -262,7 +285,8 @@ tracePersistent(const uint32_t* __restrict__ nodeBase, const SubDag* __restrict_
 					clearHit(out);
 					if (res == kStepAbandoned) { out.status = CBQ_HIT_ABANDONED; atomicAdd(abandoned, 1ull); }
 				}
-				sink.write(slot, out);
+				if constexpr (Sink::kParked) { parked = compactRecord(out); hasParked = true; }
+				else sink.write(slot, out);
 				s.phase = kPhaseIdle;
 			}
 		}
@@ -414,6 +438,10 @@ cudaError_t launchPersistent(const TraceArgs& a, bool surface, const Source& src
 	if (a.flags) {
 		// Flag-only results are for shadow rays, which never ask for surface properties.
 		return launchPersistentLod<false>(a, src, FlagSink{ a.flags }, tickets, cfg, stream);
+	}
+	if (a.compact && a.remoteResults) {
+		const ParkedCompactSink sink{ a.compact };
+		return surface ? launchPersistentLod<true>(a, src, sink, tickets, cfg, stream) : launchPersistentLod<false>(a, src, sink, tickets, cfg, stream);
 	}
 	if (a.compact) {
 		const CompactSink sink{ a.compact };

@@ -71,7 +71,7 @@ class SharedResults:
             h.copy_(torch.frombuffer(bytearray(handle), dtype=torch.uint8))
         dist.broadcast(h, src=dst)
         if not self.owner:
-            self.ptr = ctx.shared_open(bytes(h.cpu().numpy().tobytes()))
+            self.ptr = ctx.shared_open(bytes(h.cpu().numpy().tobytes()), nbytes)
         self.nbytes = nbytes
 
     def close(self, dist):

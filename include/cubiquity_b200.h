@@ -269,7 +269,7 @@ int cbq_rng_points_device(cbq_context* ctx, const uint32_t* d_seeds, uint64_t n,
  * kernel's stores ARE the transfer -- or ships finished chunks with cbq_copy_device (copy engines, no SM involved). */
 typedef struct cbq_ipc_handle { unsigned char bytes[64]; } cbq_ipc_handle;
 int cbq_shared_alloc(cbq_context* ctx, uint64_t bytes, void** d_ptr, cbq_ipc_handle* handle);
-int cbq_shared_open(cbq_context* ctx, const cbq_ipc_handle* handle, void** d_ptr);
+int cbq_shared_open(cbq_context* ctx, const cbq_ipc_handle* handle, uint64_t bytes, void** d_ptr);   /* bytes: as allocated */
 int cbq_shared_close(cbq_context* ctx, void* d_ptr);     /* a pointer from cbq_shared_open */
 int cbq_shared_free(cbq_context* ctx, void* d_ptr);      /* a pointer from cbq_shared_alloc */
 int cbq_copy_device(cbq_context* ctx, void* d_dst, const void* d_src, uint64_t bytes, void* stream);
@@ -284,7 +284,9 @@ int cbq_host_free(void* p);
  * pixel the wavefront tracer traces together, 1..16; 0 = choose from the size of the rectangle),
  * "adaptive_order" (0/1, default 1: coherent batches -- refill_threshold 32, cbq_raycast_frame_device -- record how
  * long each 32-ray ticket took, and the next launch over the same ray buffer, size and stream deals the tickets
- * longest first; a scheduling hint only, results do not depend on it), "order_refresh" (that order is rebuilt from
+ * longest first; a scheduling hint only, results do not depend on it), "park_results" (0/1, default 0: cbq_trace_compact_device already coalesces a warp's result stores when the result
+ * buffer lies in another GPU's memory, see cbq_shared_open; 1 forces that path for local buffers too -- a testing aid),
+ * "order_refresh" (that order is rebuilt from
  * the recorded costs every this many launches, default 4; cbq_raycast_frame_device also rebuilds it after every
  * frame whose camera differs from the previous one). */
 int cbq_set_option(cbq_context* ctx, const char* key, int64_t value);

@@ -18,6 +18,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--lod", type=float, default=-1.0)
 ap.add_argument("--random", type=int, default=0)
 ap.add_argument("--launches", type=int, default=3)
+ap.add_argument("--frames", type=int, default=1, help="orbit poses in the batch (bench.py's job is 64)")
+ap.add_argument("--compact", action="store_true", help="8-byte results (cbq_trace_compact_device), as bench.py's job")
 ap.add_argument("--opt", action="append", default=[])
 args = ap.parse_args()
 W, H = 1920, 1080
@@ -35,18 +37,23 @@ lower = np.asarray(scene.lower, dtype=np.float64); upper = np.asarray(scene.uppe
 centre = (lower + upper) * 0.5
 hd = float(np.sqrt(((upper - lower) ** 2).sum())) * 0.5
 PI_F = float(np.float32(3.14159265358979))
-cam = api.camera_from_pose([centre[0], centre[1] - hd, centre[2] + hd], -(PI_F / 4.0), 0.0)
-n = args.random or W * H
+n = args.random or W * H * args.frames
 rays = torch.empty(n * 6, dtype=torch.float32, device=dev)
 if args.random:
     ext = (upper - lower) * 0.1
     ctx.random_rays_device(100, (lower - ext).astype(np.float32), (upper + ext).astype(np.float32), n, rays.data_ptr(), stream)
 else:
-    ctx.primary_rays_tiled_device(cam, W, H, rays.data_ptr(), None, stream)
-hits = torch.zeros(n * 10, dtype=torch.int32, device=dev)
+    for f in range(args.frames):
+        yaw = f * (2.0 * np.pi / max(args.frames, 1))
+        cam = api.camera_from_pose([centre[0] - hd * np.sin(yaw), centre[1] - hd * np.cos(yaw), centre[2] + hd], -(PI_F / 4.0), yaw)
+        ctx.primary_rays_tiled_device(cam, W, H, rays.data_ptr() + f * W * H * 24, None, stream)
+hits = torch.zeros(n * (2 if args.compact else 10), dtype=torch.int32, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for _ in range(args.launches):
     flush.zero_()
-    ctx.trace_device(rays.data_ptr(), n, hits.data_ptr(), True, args.lod, stream)
+    if args.compact:
+        ctx.trace_compact_device(rays.data_ptr(), n, hits.data_ptr(), True, args.lod, stream)
+    else:
+        ctx.trace_device(rays.data_ptr(), n, hits.data_ptr(), True, args.lod, stream)
 torch.cuda.synchronize()
 print("done")

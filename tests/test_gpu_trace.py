@@ -407,3 +407,24 @@ def test_compact_device_pointer_variant(gpu, api, scenes):
     torch.cuda.synchronize()
     compact = d_out.cpu().numpy().view(api.COMPACT_DTYPE).reshape(-1)
     assert_hits_identical(api.expand_hits(rays, compact), gpu.intersect_volume(rays, True, -1.0), "compact, device pointers")
+
+
+@pytest.mark.parametrize("threshold", [32, 8, 1])
+def test_parked_result_stores_change_nothing(gpu, api, scenes, threshold):
+    """The sink used when the result buffer is another GPU's memory (results parked in registers, stored a warp at a
+    time) against the plain compact sink: same records, whatever the refill policy and batch size."""
+    sc = scenes("terrain", 9)
+    gpu.upload(sc.nodes, sc.root)
+    old = gpu.get_option("refill_threshold")
+    try:
+        gpu.set_option("refill_threshold", threshold)
+        for n in (1, 33, 100001, 300000):
+            rays = mixed_rays(sc.lower, sc.upper, n, seed=40 + n) if n > 1000 else R.random_rays(n, sc.lower, sc.upper, seed=n)
+            plain = gpu.intersect_volume_compact(rays, True, -1.0)
+            gpu.set_option("park_results", 1)
+            parked = gpu.intersect_volume_compact(rays, True, -1.0)
+            gpu.set_option("park_results", 0)
+            assert parked.tobytes() == plain.tobytes(), (threshold, n)
+    finally:
+        gpu.set_option("refill_threshold", old)
+        gpu.set_option("park_results", 0)
