@@ -18,8 +18,6 @@ def oracle_params(pyoracle, p):
     return pyoracle.pt_params_from(p)
 
 
-@pytest.mark.parametrize("kind,size_log2", [("sphere_noise", 8), ("soup", 8)])
-@pytest.mark.parametrize("bounces,spp", [(0, 1), (1, 2), (4, 3)])
 def reference_image(ref, sc, cam, p):
     """ONE hop: the same frame from the reference's own PathtracingDemo::traceSingleRay / traceSingleRayRecurse
     (unmodified pathtracing_demo.cpp in oracle/_ref, per-pixel RNG streams seeded as cbq_render seeds them)."""
@@ -29,6 +27,8 @@ def reference_image(ref, sc, cam, p):
     return img
 
 
+@pytest.mark.parametrize("kind,size_log2", [("sphere_noise", 8), ("soup", 8)])
+@pytest.mark.parametrize("bounces,spp", [(0, 1), (1, 2), (4, 3)])
 def test_recursive_variant_is_bit_exact(gpu, port, ref, api, scenes, kind, size_log2, bounces, spp):
     from oracle import pyoracle
     sc = scenes(kind, size_log2)
