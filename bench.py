@@ -192,6 +192,12 @@ def orbit_pose(lower, upper, k, frames):
     return [centre[0] - half_diag * np.sin(yaw), centre[1] - half_diag * np.cos(yaw), centre[2] + half_diag], yaw
 
 
+def orbit_camera(api, bounds, k, frames=8):
+    """(camera, position, yaw) of orbit pose k: what the analysis scripts under scripts/ use."""
+    pos, yaw = orbit_pose(bounds.lower, bounds.upper, k, frames)
+    return api.camera_from_pose(pos, PITCH, yaw), pos, yaw
+
+
 class OnlyJsonOnStdout:
     """The driver reads ONE JSON line from stdout; libraries (NCCL prints its version banner there) must not add to it.
     File descriptor 1 points at stderr until emit() prints the line."""

@@ -44,8 +44,7 @@ def render_sweep(ctx, scene, dev, stream):
     cam = api.default_camera(scene.lower, scene.upper)
     acc = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
     for mode, variant, bounces, spp, thr, grp in [(0, 1, 4, 16, 8, 1), (0, 1, 4, 16, 8, 2), (0, 1, 4, 16, 8, 4), (0, 1, 4, 16, 8, 8), (0, 1, 4, 16, 8, 16),
-                                                  (0, 1, 4, 16, 4, 8), (0, 1, 4, 16, 2, 8), (0, 1, 1, 16, 8, 8), (0, 0, 1, 16, 8, 8), (1, 1, 4, 4, 8, 4)]:
-        ctx.set_option("render_mode", mode)
+                                                  (0, 1, 4, 16, 4, 8), (0, 1, 4, 16, 2, 8), (0, 1, 1, 16, 8, 8), (0, 0, 1, 16, 8, 8)]:
         ctx.set_option("sample_group", grp)
         ctx.set_option("refill_threshold", thr)
         p = api.pt_params(W, H, spp=spp, bounces=bounces, variant=variant)
