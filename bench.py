@@ -772,6 +772,21 @@ def secondary(args, api, ctx, torch, flush, stream, dev, scene, d_rays, n_rays, 
         extra["pathtrace"] = {"spp_per_s": WIDTH * HEIGHT * args.spp / (ms6 * 1e-3), "ms": ms6,
                               "config": "1920x1080, %d spp, %d bounces, traceSingleRayRecurse, sun+sky+noise, maxFootprint 0.0035, same terrain" % (args.spp, args.bounces),
                               "mean_radiance": float(acc.mean().item()) / args.spp}
+        # its roofline: B_spp = sum over the rays of a sample of (32 B x V + 24 B + 40 B) + 12 B accumulate; rays and node
+        # visits per sample counted by the instrumented oracle on six 8-row bands of the same frame, 1 sample per pixel
+        ocam = port.camera(pos, PITCH, yaw)
+        o_rays = o_visits = o_px = 0
+        for y0 in range(60, HEIGHT, 180):
+            op = pyoracle.PtParams(WIDTH, HEIGHT, 1, args.bounces, 1, 1, 1, 1, 0.0035, 0, 0, y0, WIDTH, y0 + 8, 0)
+            _, _, nr = port.render(nodes, sd, scene.colours, ocam, op, threads=threads)
+            o_rays += nr; o_visits += port.last_render_stats().node_visits(); o_px += WIDTH * 8
+        b_spp = 32.0 * o_visits / o_px + 64.0 * o_rays / o_px + 12.0
+        spp_rate = extra["pathtrace"]["spp_per_s"]
+        peak_pt, _ = peaks()
+        extra["pathtrace"]["roofline"] = {"bound": "hbm", "bytes_per_spp": b_spp, "rays_per_spp": o_rays / o_px, "node_visits_per_spp": o_visits / o_px,
+                                          "achieved": b_spp * spp_rate / 1e9, "peak": peak_pt, "unit": "GB/s", "frac": b_spp * spp_rate / 1e9 / peak_pt,
+                                          "rays_per_s": o_rays / o_px * spp_rate,
+                                          "sample": "%d pixels (six 8-row bands), 1 spp, instrumented oracle" % o_px}
         del acc
         ctx.set_option("refill_threshold", 32)
 

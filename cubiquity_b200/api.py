@@ -44,17 +44,20 @@ class PtParams(C.Structure):
                 ("variant", C.c_uint32), ("include_sun", C.c_uint32), ("include_sky", C.c_uint32),
                 ("add_noise", C.c_uint32), ("max_footprint", C.c_float), ("frame_id", C.c_uint32),
                 ("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32), ("y1", C.c_uint32),
-                ("band_count", C.c_uint32), ("band_index", C.c_uint32)]
+                ("band_count", C.c_uint32), ("band_index", C.c_uint32),
+                ("tile_group_count", C.c_uint32), ("tile_group_index", C.c_uint32)]
 
 
 def pt_params(width, height, spp=1, bounces=1, variant=VARIANT_ONE_BOUNCE, include_sun=True, include_sky=True,
-              add_noise=True, max_footprint=0.0035, frame_id=0, rect=None, bands=None):
+              add_noise=True, max_footprint=0.0035, frame_id=0, rect=None, bands=None, tile_group=None):
     """Defaults are PathtracingDemo's (reference pathtracing_demo.h:80-84). bands = (count, index) renders only
-    the 64-row bands b of the rectangle with b % count == index (round-robin tile sharding)."""
+    the 64-row bands b of the rectangle with b % count == index (round-robin tile sharding); tile_group = (count, index)
+    only the 64x64-pixel tiles of that group of the GLSL viewer's progressive schedule."""
     x0, y0, x1, y1 = rect if rect is not None else (0, 0, width, height)
     bc, bi = bands if bands is not None else (1, 0)
+    tc, ti = tile_group if tile_group is not None else (0, 0)
     return PtParams(width, height, spp, bounces, variant, int(include_sun), int(include_sky), int(add_noise),
-                    max_footprint, frame_id, x0, y0, x1, y1, bc, bi)
+                    max_footprint, frame_id, x0, y0, x1, y1, bc, bi, tc, ti)
 
 
 EXPORTS = [
@@ -65,6 +68,8 @@ EXPORTS = [
     "cbq_trace", "cbq_trace_device", "cbq_trace_compact", "cbq_trace_compact_device", "cbq_expand_hits", "cbq_camera_from_pose", "cbq_primary_rays_device", "cbq_primary_rays_tiled_device", "cbq_random_rays_device",
     "cbq_raycast_frame_device",
     "cbq_render", "cbq_render_device", "cbq_rng_points_device",
+    "cbq_progressive_pass_device", "cbq_normalise_device", "cbq_blur_device",
+    "cbq_dag_load", "cbq_dag_free", "cbq_dag_save", "cbq_upload_dag", "cbq_set_log_callback",
     "cbq_shared_alloc", "cbq_shared_open", "cbq_shared_close", "cbq_shared_free", "cbq_copy_device",
     "cbq_host_alloc", "cbq_host_free", "cbq_set_option", "cbq_get_option", "cbq_get_counter", "cbq_reset_counters",
     "cbq_editable_create", "cbq_editable_destroy", "cbq_editable_checkpoint", "cbq_editable_undo", "cbq_editable_redo",
@@ -120,6 +125,17 @@ def load_library():
     L.cbq_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(PtParams), vp]
     L.cbq_render_device.argtypes = [vp, C.POINTER(Camera), C.POINTER(PtParams), vp, vp]
     L.cbq_rng_points_device.argtypes = [vp, vp, u64, i32, vp, vp, vp]
+    L.cbq_progressive_pass_device.argtypes = [vp, C.POINTER(Camera), C.POINTER(PtParams), u32, vp, vp]
+    L.cbq_normalise_device.argtypes = [vp, vp, u32, u32, vp, vp]
+    L.cbq_blur_device.argtypes = [vp, vp, u32, u32, vp, i32, vp]
+    L.cbq_dag_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(u32)), C.POINTER(u64), C.POINTER(u32)]
+    L.cbq_dag_free.argtypes = [C.POINTER(u32)]
+    L.cbq_dag_free.restype = None
+    L.cbq_dag_save.argtypes = [C.c_char_p, vp, u64, u32]
+    L.cbq_upload_dag.argtypes = [vp, C.c_char_p, vp]
+    L.cbq_set_log_callback.argtypes = [vp]
+    L.cbq_set_log_callback.restype = None
+    L.cbq_dag_error.restype = C.c_char_p
     L.cbq_shared_alloc.argtypes = [vp, u64, C.POINTER(vp), vp]
     L.cbq_shared_open.argtypes = [vp, vp, u64, C.POINTER(vp)]
     L.cbq_shared_close.argtypes = [vp, vp]
@@ -284,6 +300,45 @@ class Editable:
         if colours is not None:
             colours = np.ascontiguousarray(colours, dtype=np.float32).reshape(256, 3)
         _check(self.L.cbq_editable_sync(self._h, ctx._h, int(bool(first_upload)), _ptr(colours)))
+
+
+def dag_load(path):
+    """cbq_dag_load: (nodes (n, 8) uint32 incl. the 256 material nodes, root) from a reference .dag file, validated."""
+    L = load_library()
+    p = C.POINTER(C.c_uint32)()
+    n = C.c_uint64()
+    root = C.c_uint32()
+    rc = L.cbq_dag_load(os.fsencode(path), C.byref(p), C.byref(n), C.byref(root))
+    if rc != OK:
+        raise CubiquityError(rc, L.cbq_dag_error().decode("utf-8", "replace"))
+    try:
+        nodes = np.ctypeslib.as_array(p, shape=(int(n.value), 8)).copy()
+    finally:
+        L.cbq_dag_free(p)
+    return nodes, int(root.value)
+
+
+def dag_save(path, nodes, root):
+    L = load_library()
+    nodes = np.ascontiguousarray(nodes, dtype=np.uint32).reshape(-1, 8)
+    rc = L.cbq_dag_save(os.fsencode(path), _ptr(nodes), len(nodes), int(root))
+    if rc != OK:
+        raise CubiquityError(rc, L.cbq_dag_error().decode("utf-8", "replace"))
+
+
+_log_handler = None
+
+
+def set_log_callback(fn):
+    """Failed calls also report their message to fn(str) (reference MessageHandlerPtr, base.h:102-107); None = off."""
+    global _log_handler
+    L = load_library()
+    if fn is None:
+        _log_handler = None
+        L.cbq_set_log_callback(None)
+        return
+    _log_handler = C.CFUNCTYPE(None, C.c_char_p)(lambda m: fn(m.decode("utf-8", "replace")))
+    L.cbq_set_log_callback(C.cast(_log_handler, C.c_void_p))
 
 
 def expand_hits(rays, compact, out=None, threads=0):
@@ -462,6 +517,21 @@ class Context:
     def render_device(self, cam, params, d_accum, stream=None):
         _check(self.L.cbq_render_device(self._h, C.byref(cam), C.byref(params), C.c_void_p(int(d_accum)),
                                         _stream(stream)))
+
+    def upload_dag(self, path, colours=None):
+        if colours is not None:
+            colours = np.ascontiguousarray(colours, dtype=np.float32).reshape(256, 3)
+        _check(self.L.cbq_upload_dag(self._h, os.fsencode(path), _ptr(colours)))
+
+    def progressive_pass_device(self, cam, params, frame, d_rgba, stream=None):
+        """GPUPathtracingViewer's progressive frame `frame`: one tile group gets params.spp more samples, added into RGBA."""
+        _check(self.L.cbq_progressive_pass_device(self._h, C.byref(cam), C.byref(params), int(frame), C.c_void_p(int(d_rgba)), _stream(stream)))
+
+    def normalise_device(self, d_rgba, width, height, d_rgb, stream=None):
+        _check(self.L.cbq_normalise_device(self._h, C.c_void_p(int(d_rgba)), int(width), int(height), C.c_void_p(int(d_rgb)), _stream(stream)))
+
+    def blur_device(self, d_rgba, width, height, d_scratch, passes=1, stream=None):
+        _check(self.L.cbq_blur_device(self._h, C.c_void_p(int(d_rgba)), int(width), int(height), C.c_void_p(int(d_scratch)), int(passes), _stream(stream)))
 
     def rng_points_device(self, d_seeds, n, draws, d_points, d_states, stream=None):
         _check(self.L.cbq_rng_points_device(self._h, C.c_void_p(int(d_seeds)), int(n), int(draws), C.c_void_p(int(d_points)),

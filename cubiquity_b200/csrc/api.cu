@@ -10,6 +10,8 @@
 //   render      PathtracingDemo::raytrace, src/application/commands/view/pathtracing_demo.cpp:214-229
 #include "cbq_internal.h"
 
+extern "C" const char* cbq_dag_error(void);     // host_shim.cpp: why the last cbq_dag_load / cbq_dag_save on this thread failed
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -22,6 +24,7 @@
 namespace {
 
 thread_local std::string g_lastError;
+void (*g_logHandler)(const char*) = nullptr;
 
 int fail(int code, const char* fmt, ...)
 {
@@ -31,6 +34,7 @@ int fail(int code, const char* fmt, ...)
 	vsnprintf(buf, sizeof(buf), fmt, ap);
 	va_end(ap);
 	g_lastError = buf;
+	if (g_logHandler) g_logHandler(buf);
 	return code;
 }
 
@@ -90,6 +94,12 @@ bool childrenInRange(const uint32_t* nodes, uint64_t begin, uint64_t end, uint64
 	return worst < limit || nodeCount > 0xffffffffull;
 }
 
+uint32_t fmix32Host(uint32_t h)   // glsl/pathtracing.frag:287-296 (bitMix)
+{
+	h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+	return h;
+}
+
 bool findSubDags(const uint32_t* nodes, uint64_t nodeCount, uint32_t root, cbq::SubDag out[8])
 {
 	for (uint32_t c = 0; c < 8; c++) if (!findOneSubDag(nodes, nodeCount, root, c, out[c])) return false;
@@ -137,6 +147,12 @@ struct cbq_context {
 	// cbq_raycast_frame_device: primary rays of the frame in 8x4-tile order
 	cbq::Ray* frameRays = nullptr;
 	size_t frameRayCapacity = 0;
+
+	// tile-group rendering (cbq_pt_params::tile_group_count) and the progressive pass
+	uint32_t* tileList = nullptr;
+	size_t tileListCapacity = 0;
+	float* progressiveScratch = nullptr;      // width x height x 3, all zeros between passes
+	size_t progressiveScratchPixels = 0;
 
 	// cbq_render staging
 	float* stageAccum = nullptr;
@@ -540,6 +556,8 @@ void cbq_destroy(cbq_context* ctx)
 		if (ctx->evOut[i]) cudaEventDestroy(ctx->evOut[i]);
 	}
 	cudaFree(ctx->stageAccum);
+	cudaFree(ctx->tileList);
+	cudaFree(ctx->progressiveScratch);
 	cudaFree(ctx->frameRays);
 	cudaFree(ctx->ticketCost); cudaFree(ctx->ticketHist); cudaFree(ctx->ticketOrder[0]); cudaFree(ctx->ticketOrder[1]);
 	if (ctx->orderEvent) cudaEventDestroy(ctx->orderEvent);
@@ -1077,6 +1095,11 @@ int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_para
 		return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad image rectangle");
 	if (p->variant > 1 || p->bounces > 5) return fail(CBQ_ERROR_INVALID_ARGUMENT, "variant must be 0/1 and bounces <= 5 (the viewer's F2 limit, pathtracing_demo.cpp:280)");
 	if (p->band_count > 1 && p->band_index >= p->band_count) return fail(CBQ_ERROR_INVALID_ARGUMENT, "band_index must be < band_count");
+	if (p->tile_group_count > 1) {
+		if (p->tile_group_index >= p->tile_group_count) return fail(CBQ_ERROR_INVALID_ARGUMENT, "tile_group_index must be < tile_group_count");
+		if (p->band_count > 1 || p->x0 != 0 || p->y0 != 0 || p->x1 != p->width || p->y1 != p->height)
+			return fail(CBQ_ERROR_INVALID_ARGUMENT, "tile groups need the whole image as the rectangle and no bands");
+	}
 	if (p->x0 == p->x1 || p->y0 == p->y1 || p->spp == 0) return CBQ_OK;
 	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
 	cbq::RenderArgs a;
@@ -1084,7 +1107,27 @@ int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_para
 	a.volume = ctx->view(); a.colours = ctx->coloursPtr();
 	a.camera = *cam; a.params = *p; a.accum = d_accum; a.abandoned = ctx->abandonedPtr();
 	applyL2Window(ctx, s);
-	const size_t pixels = (size_t)(p->x1 - p->x0) * cbq::bandedRowCount(p->y1 - p->y0, p->band_count, p->band_index);
+	size_t pixels = (size_t)(p->x1 - p->x0) * cbq::bandedRowCount(p->y1 - p->y0, p->band_count, p->band_index);
+	if (p->tile_group_count > 1) {
+		// The tiles of this group, in row-major tile order (glsl/pathtracing.frag:792-799: group = bitMix(tile id) % count).
+		std::vector<uint32_t> tiles;
+		const uint32_t tilesX = (p->width + 63u) / 64u, tilesY = (p->height + 63u) / 64u;
+		for (uint32_t ty = 0; ty < tilesY; ty++) for (uint32_t tx = 0; tx < tilesX; tx++)
+			if (fmix32Host((tx << 16) | (ty & 0xffffu)) % p->tile_group_count == p->tile_group_index) tiles.push_back(tx | (ty << 16));
+		if (tiles.empty()) return CBQ_OK;
+		if (tiles.size() > ctx->tileListCapacity) {
+			CBQ_CUDA(cudaDeviceSynchronize());
+			cudaFree(ctx->tileList); ctx->tileList = nullptr; ctx->tileListCapacity = 0;
+			const size_t cap = std::max<size_t>(1024, tiles.size() * 2);
+			CBQ_CUDA(cudaMalloc(&ctx->tileList, cap * sizeof(uint32_t)));
+			ctx->tileListCapacity = cap;
+		}
+		CBQ_CUDA(cudaStreamSynchronize(s));     // the previous call's kernels may still be reading the list
+		CBQ_CUDA(cudaMemcpyAsync(ctx->tileList, tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+		CBQ_CUDA(cudaStreamSynchronize(s));     // `tiles` is on our stack
+		a.tiles = ctx->tileList; a.tileCount = (uint32_t)tiles.size();
+		pixels = tiles.size() * 4096;
+	}
 	if (pixels == 0) return CBQ_OK;
 	// Samples traced together. 0 = auto: aim at ~16 M paths per wave (8 samples of a 1080p frame, 16 of a
 	// 1/8 share), between 1 and 16; an explicit value is still capped at 32 M paths (~8.5 GB of buffers).
@@ -1119,6 +1162,66 @@ int cbq_render(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_params* p, 
 	ctx->bytesH2D += bytes; ctx->bytesD2H += bytes;
 	return CBQ_OK;
 }
+
+int cbq_progressive_pass_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_params* p, uint32_t frame, float* d_rgba, void* stream)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!cam || !p || !d_rgba || !p->width || !p->height) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad argument");
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	const size_t pixels = (size_t)p->width * p->height;
+	if (pixels > ctx->progressiveScratchPixels) {
+		CBQ_CUDA(cudaDeviceSynchronize());
+		cudaFree(ctx->progressiveScratch); ctx->progressiveScratch = nullptr; ctx->progressiveScratchPixels = 0;
+		CBQ_CUDA(cudaMalloc(&ctx->progressiveScratch, pixels * 3 * sizeof(float)));
+		CBQ_CUDA(cudaMemset(ctx->progressiveScratch, 0, pixels * 3 * sizeof(float)));
+		ctx->progressiveScratchPixels = pixels;
+	}
+	const uint32_t kGroups = 16;      // glsl/pathtracing.frag:796
+	cbq_pt_params q = *p;
+	q.x0 = 0; q.y0 = 0; q.x1 = p->width; q.y1 = p->height; q.band_count = 0; q.band_index = 0;
+	q.tile_group_count = kGroups; q.tile_group_index = frame % kGroups;
+	q.frame_id = frame * p->spp;
+	rc = cbq_render_device(ctx, cam, &q, ctx->progressiveScratch, s); if (rc) return rc;
+	CBQ_CUDA(cbq::launchProgressiveAdd(ctx->progressiveScratch, d_rgba, p->width, p->height, kGroups, q.tile_group_index, (float)p->spp, s));
+	ctx->launches++;
+	return CBQ_OK;
+}
+
+int cbq_normalise_device(cbq_context* ctx, const float* d_rgba, uint32_t width, uint32_t height, float* d_rgb, void* stream)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!d_rgba || !d_rgb || !width || !height) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad argument");
+	CBQ_CUDA(cbq::launchNormalise(d_rgba, width, height, d_rgb, stream ? (cudaStream_t)stream : ctx->stream));
+	ctx->launches++;
+	return CBQ_OK;
+}
+
+int cbq_blur_device(cbq_context* ctx, float* d_rgba, uint32_t width, uint32_t height, float* d_scratch_rgba, int passes, void* stream)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!d_rgba || !d_scratch_rgba || !width || !height || passes < 0) return fail(CBQ_ERROR_INVALID_ARGUMENT, "bad argument");
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	for (int i = 0; i < passes; i++) {
+		CBQ_CUDA(cbq::launchBlur(d_rgba, d_scratch_rgba, width, height, 0, s));     // hBlurProgram: accTexture -> blurTexture
+		CBQ_CUDA(cbq::launchBlur(d_scratch_rgba, d_rgba, width, height, 1, s));     // vBlurProgram: blurTexture -> accTexture
+		ctx->launches += 2;
+	}
+	return CBQ_OK;
+}
+
+int cbq_upload_dag(cbq_context* ctx, const char* path, const float* colours_rgb)
+{
+	uint32_t* nodes = nullptr;
+	uint64_t count = 0;
+	uint32_t root = 0;
+	int rc = cbq_dag_load(path, &nodes, &count, &root);
+	if (rc) return fail(rc, "cbq_upload_dag: %s", cbq_dag_error());
+	rc = cbq_upload(ctx, nodes, count, root, colours_rgb);
+	cbq_dag_free(nodes);
+	return rc;
+}
+
+void cbq_set_log_callback(void (*handler)(const char* message)) { g_logHandler = handler; }
 
 int cbq_rng_points_device(cbq_context* ctx, const uint32_t* d_seeds, uint64_t n, int draws, float* d_points, uint32_t* d_states, void* stream)
 {

@@ -47,6 +47,26 @@ inline uint32_t bandedRowCount(uint32_t rectH, uint32_t bandCount, uint32_t band
 	return rows;
 }
 
+// Which image pixel a rectangle-local pixel (lx, ly) is. Three layouts share the path tracer's kernels:
+//   plain rectangle    x = x0 + lx, y = y0 + ly
+//   64-row bands       every bandCount-th band of the rectangle's rows (tile sharding over GPUs)
+//   tile list          `tiles` != nullptr: the local image is a column of 64x64-pixel tiles, tile t = ly / 64 sits at
+//                      image tile (tiles[t] & 0xffff, tiles[t] >> 16) -- the progressive renderer's tile groups
+//                      (glsl/pathtracing.frag:789-803). Tiles may overhang the image: such pixels are invalid.
+struct PixelMap {
+	uint32_t x0, y0, bandCount, bandIndex;
+	const uint32_t* tiles;
+	uint32_t imgW, imgH;
+};
+CBQ_HD bool pixelAt(const PixelMap& m, uint32_t lx, uint32_t ly, uint32_t& x, uint32_t& y)
+{
+	if (m.tiles == nullptr) { x = m.x0 + lx; y = bandedRow(m.y0, ly, m.bandCount, m.bandIndex); return true; }
+	const uint32_t tile = m.tiles[ly >> 6];
+	x = (tile & 0xffffu) * 64u + lx;
+	y = (tile >> 16) * 64u + (ly & 63u);
+	return x < m.imgW && y < m.imgH;
+}
+
 struct LaunchConfig {
 	int blockThreads;      // threads per CTA
 	int blocksPerSm;       // resident CTAs per SM the grid is sized for
@@ -76,6 +96,7 @@ struct TraceArgs {
 	uint32_t width, height;
 	uint32_t x0, y0, rectW, rectH;   // rectH counts the rows actually traced (owned rows when banded)
 	uint32_t bandCount, bandIndex;   // 64-row band interleave (cbq_pt_params::band_count / band_index)
+	const uint32_t* tiles;           // camera source: tile-list layout (PixelMap), rectW = 64, rectH = 64 x tiles
 	// optional: batch size read on the device (count = *countPtr * countScale), flag-only results
 	const unsigned long long* countPtr;
 	uint32_t countScale;
@@ -96,6 +117,8 @@ cudaError_t launchRandomRays(uint64_t seed, const float lower[3], const float up
 struct RenderArgs {
 	VolumeView volume;
 	const float4* colours;
+	const uint32_t* tiles;           // != nullptr: render this list of 64x64-pixel image tiles (device array) ...
+	uint32_t tileCount;              // ... instead of the rectangle / bands of `params`
 	cbq_camera camera;
 	cbq_pt_params params;
 	float* accum;
@@ -117,6 +140,10 @@ struct WavefrontBuffers {
 	float* radiance = nullptr;     // finished radiance of each path, SoA [3][pixels]
 	unsigned long long* counters = nullptr;     // live paths per depth             [8]
 };
+// Viewer passes (viewer_kernels.cu): progressive accumulation, normalise, edge-stopping blur.
+cudaError_t launchProgressiveAdd(float* scratchRgb, float* rgba, uint32_t width, uint32_t height, uint32_t groupCount, uint32_t groupIndex, float samples, cudaStream_t stream);
+cudaError_t launchNormalise(const float* rgba, uint32_t width, uint32_t height, float* rgb, cudaStream_t stream);
+cudaError_t launchBlur(const float* in, float* out, uint32_t width, uint32_t height, int vertical, cudaStream_t stream);
 cudaError_t launchRngPoints(const uint32_t* seeds, uint64_t n, int draws, float* points, uint32_t* states, cudaStream_t stream);
 int wavefrontReserve(WavefrontBuffers& b, size_t paths);       // cudaError_t as int
 void wavefrontRelease(WavefrontBuffers& b);

@@ -100,7 +100,7 @@ struct CameraSource {
 	cbq_camera cam;
 	uint32_t width, height;            // the image the camera is defined for
 	uint32_t x0, y0, rectW, rectH;     // the pixel rectangle traced; results are indexed rect-locally
-	uint32_t bandCount, bandIndex;     // 64-row band interleave of the rectangle's rows (1, 0 = all rows)
+	PixelMap map;                      // rectangle-local pixel -> image pixel (bands, tile lists)
 	uint32_t tilesX;
 	// Tickets enumerate 8x4-pixel tiles row by row, 32 tickets per tile, so the 32 lanes of a warp
 	// start on one compact tile. Tiles overhanging the rectangle produce slot = ~0 (skipped).
@@ -109,8 +109,9 @@ struct CameraSource {
 		const uint32_t tile = (uint32_t)(ticket >> 5), within = (uint32_t)ticket & 31u;
 		const uint32_t tx = tile % tilesX, ty = tile / tilesX;
 		const uint32_t x = tx * 8u + (within & 7u), y = ty * 4u + (within >> 3);
-		if (x < rectW && y < rectH) {
-			cameraRay(cam, (int)(x0 + x), (int)bandedRow(y0, y, bandCount, bandIndex), (int)width, (int)height, r);
+		uint32_t px, py;
+		if (x < rectW && y < rectH && pixelAt(map, x, y, px, py)) {
+			cameraRay(cam, (int)px, (int)py, (int)width, (int)height, r);
 			slot = (uint64_t)y * rectW + x;
 		} else {
 			slot = ~0ull;
@@ -463,7 +464,7 @@ cudaError_t launchTrace(const TraceArgs& a, bool surface, const LaunchConfig& cf
 		CameraSource src;
 		src.cam = a.camera; src.width = a.width; src.height = a.height;
 		src.x0 = a.x0; src.y0 = a.y0; src.rectW = a.rectW ? a.rectW : a.width; src.rectH = a.rectH ? a.rectH : a.height;
-		src.bandCount = a.bandCount; src.bandIndex = a.bandIndex;
+		src.map = PixelMap{ a.x0, a.y0, a.bandCount, a.bandIndex, a.tiles, a.width, a.height };
 		src.tilesX = (src.rectW + 7u) / 8u;
 		const uint64_t tickets = (uint64_t)src.tilesX * ((src.rectH + 3u) / 4u) * 32u;
 		return launchPersistent(a, surface, src, tickets, cfg, stream);

@@ -48,6 +48,7 @@ struct WaveParams {
 	int depth;
 	int lastDepth;            // paths alive after the lighting of this depth end here
 	uint32_t shadowsPerPath;  // include_sun + include_sky
+	PixelMap map;             // rectangle-local pixel -> image pixel
 };
 
 // Fold a finished path back to front (pathtracing_demo.cpp:143, :182-185) into its radiance slot.
@@ -85,7 +86,8 @@ accumulateKernel(WaveParams w, const float* __restrict__ radiance, float* __rest
 	const size_t n = w.paths;
 	const uint32_t samples = w.paths / w.pixels;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < w.pixels; i += gridDim.x * blockDim.x) {
-		const uint32_t x = w.p.x0 + i % w.rectW, y = bandedRow(w.p.y0, i / w.rectW, w.p.band_count, w.p.band_index);
+		uint32_t x, y;
+		if (!pixelAt(w.map, i % w.rectW, i / w.rectW, x, y)) continue;        // a tile overhanging the image
 		float* px = accum + 3ull * ((uint64_t)y * w.p.width + x);
 		float r = px[0], g = px[1], b = px[2];
 		for (uint32_t s = 0; s < samples; s++) {
@@ -122,16 +124,22 @@ shadeKernel(WaveParams w, const float4* __restrict__ colours, const Hit* __restr
 			h.hit = a.x; h.distance = __uint_as_float(a.y); h.material = b.x;
 			h.position[0] = __uint_as_float(b.y); h.position[1] = __uint_as_float(c.x); h.position[2] = __uint_as_float(c.y);
 			h.normal[0] = __uint_as_float(d.x); h.normal[1] = __uint_as_float(d.y); h.normal[2] = __uint_as_float(e.x);
+			bool onImage = true;
 			if (w.depth == 0) {
 				const uint32_t pix = pixel % w.pixels, sample = pixel / w.pixels;
-				Ray r;
-				cameraRay(w.cam, (int)(w.p.x0 + pix % w.rectW), (int)bandedRow(w.p.y0, pix / w.rectW, w.p.band_count, w.p.band_index),
-					(int)w.p.width, (int)w.p.height, r);
-				rng = pixelSeed(r, w.sampleIndex + sample);
+				uint32_t x, y;
+				onImage = pixelAt(w.map, pix % w.rectW, pix / w.rectW, x, y);
+				if (onImage) {
+					Ray r;
+					cameraRay(w.cam, (int)x, (int)y, (int)w.p.width, (int)w.p.height, r);
+					rng = pixelSeed(r, w.sampleIndex + sample);
+				}
 			} else {
 				rng = pathRng[i];
 			}
-			if (h.hit) {
+			if (!onImage) {
+				// a pixel of a tile that overhangs the image: no ray was cast, no hit record exists, nothing to fold
+			} else if (h.hit) {
 				live = true;
 			} else if (w.p.variant == CBQ_VARIANT_ONE_BOUNCE && w.depth == 1) {
 				finishPath(w, colour, direct, accum, pixel, 1, 0.0f, 0.0f, 0.0f);      // a missed bounce adds nothing (:168-180)
@@ -278,6 +286,11 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 	WaveParams w;
 	w.cam = a.camera; w.p = p;
 	w.rectW = p.x1 - p.x0; w.rectH = bandedRowCount(p.y1 - p.y0, p.band_count, p.band_index);
+	w.map = PixelMap{ p.x0, p.y0, p.band_count, p.band_index, nullptr, p.width, p.height };
+	if (a.tiles) {
+		w.rectW = 64; w.rectH = 64 * a.tileCount;
+		w.map.tiles = a.tiles;
+	}
 	if (w.rectW == 0 || w.rectH == 0) return cudaSuccess;
 	w.pixels = w.rectW * w.rectH;
 	w.shadowsPerPath = (p.include_sun ? 1u : 0u) + (p.include_sky ? 1u : 0u);
@@ -307,7 +320,7 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 				// one primary ray per PIXEL: the samples of the group share it
 				t.rays = nullptr; t.camera = a.camera; t.width = p.width; t.height = p.height;
 				t.x0 = p.x0; t.y0 = p.y0; t.rectW = w.rectW; t.rectH = w.rectH; t.count = w.pixels;
-				t.bandCount = p.band_count; t.bandIndex = p.band_index;
+				t.bandCount = p.band_count; t.bandIndex = p.band_index; t.tiles = a.tiles;
 				surfaceCfg.refillThreshold = 32;           // coherent tiles
 			} else {
 				t.rays = b.rays[cur]; t.countPtr = b.counters + (d - 1); t.countScale = 1; t.count = w.paths;

@@ -98,6 +98,10 @@ typedef struct cbq_pt_params {
 	uint32_t band_index;       /* 64-row bands (the GLSL renderer's tile size, glsl/pathtracing.frag:789-803) and
 	                              this call renders bands b with b % band_count == band_index -- one call per GPU
 	                              for a round-robin tile-sharded frame */
+	uint32_t tile_group_count; /* 0 or 1: every tile. N > 1: only the 64x64-pixel tiles whose fmix32(tile id) % N ==     */
+	uint32_t tile_group_index; /* tile_group_index are rendered -- the GLSL viewer's progressive schedule (tile id =
+	                              (tile x << 16) | tile y, glsl/pathtracing.frag:792-799; tile rows counted from the top
+	                              of the image). Needs the rectangle to be the whole image and band_count <= 1. */
 } cbq_pt_params;
 
 #define CBQ_VARIANT_ONE_BOUNCE 0u
@@ -254,6 +258,38 @@ int cbq_raycast_frame_device(cbq_context* ctx, const cbq_camera* cam, uint32_t w
 int cbq_render(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_params* p, float* accum);
 int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_params* p, float* d_accum,
                       void* stream);
+
+/* ---- the viewer's screen-space passes (GPUPathtracingViewer::onUpdate, gpu_pathtracing_viewer.cpp:121-222) ---- */
+
+/* One progressive frame: `frame` is the viewer's frameId. The 64x64-pixel tiles of group frame % 16 (glsl/pathtracing.frag:
+ * 789-803, groupCount 16) receive p->spp more samples (sample s is seeded with frame * spp + s), added into d_rgba --
+ * width x height x 4 floats, alpha counting the samples of each pixel, as the viewer's additive blending into its RGBA32F
+ * target does (gpu_pathtracing_viewer.cpp:152-161). p->frame_id, rectangle, bands and tile group fields are ignored. */
+int cbq_progressive_pass_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_params* p, uint32_t frame,
+                                float* d_rgba, void* stream);
+/* glsl/normalise.frag: rgb = rgba.rgb / rgba.a (a pixel that has no sample yet comes out 0/0 = NaN, as in the shader). */
+int cbq_normalise_device(cbq_context* ctx, const float* d_rgba, uint32_t width, uint32_t height, float* d_rgb, void* stream);
+/* glsl/horz_blur.frag then glsl/vert_blur.frag, `passes` times, in place (d_scratch_rgba is the viewer's blurTexture): 9 taps
+ * along the axis, a tap counts only if its alpha differs from the centre's by less than 0.5, coordinates wrap (GL_REPEAT). The
+ * viewer has these passes compiled but switched off (`blurPasses = 0`, gpu_pathtracing_viewer.cpp:168-192). */
+int cbq_blur_device(cbq_context* ctx, float* d_rgba, uint32_t width, uint32_t height, float* d_scratch_rgba, int passes,
+                    void* stream);
+
+/* ---- .dag files (Volume::load / Volume::save, src/library/storage.cpp:505-542, NodeStore::read / write :192-206) ---- */
+
+/* The file is u32 rootIndex, u32 nodeCount, nodeCount x 32 bytes (the non-material nodes; indices in the file already count the
+ * 256 material nodes). The reference reads it unchecked and sizes it with 32-bit byte counts (storage.h:102); these do the
+ * arithmetic in 64 bits and refuse a file whose length is not exactly 8 + 32 x nodeCount, whose root or any child index is past
+ * the end, or that cannot be read in full. cbq_dag_load returns the array INCLUDING the 256 material nodes (what cbq_upload
+ * takes), malloc'ed: release it with cbq_dag_free. cbq_dag_save writes next to the target and renames. */
+int  cbq_dag_load(const char* path, uint32_t** nodes, uint64_t* node_count, uint32_t* root_index);
+void cbq_dag_free(uint32_t* nodes);
+int  cbq_dag_save(const char* path, const uint32_t* nodes, uint64_t node_count, uint32_t root_index);
+int  cbq_upload_dag(cbq_context* ctx, const char* path, const float* colours_rgb);
+
+/* Messages of failed calls also go to this callback (same shape as the reference's MessageHandlerPtr, base.h:102-107);
+ * NULL switches it off. Process-wide. */
+void cbq_set_log_callback(void (*handler)(const char* message));
 
 /* Self-test hook: `draws` successive randomPointInUnitSphere results (pathtracing_demo.cpp:62-79) of the
  * stream that starts at each seed: d_points is n x draws x 3 floats, d_states the n final states. */

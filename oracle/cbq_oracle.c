@@ -479,6 +479,7 @@ typedef struct {
 	const cbqo_pt_params* p;
 	uint32_t rng;        /* per-sample stream; the reference's is one process-global (pathtracing_demo.cpp:33) */
 	uint64_t rays;
+	cbqo_stats stats;    /* node visits of every ray cast by this worker (the path tracer's roofline, SURVEY 8d B_spp) */
 } pt_state;
 
 static inline float dot3(const float a[3], const float b[3])
@@ -526,7 +527,7 @@ static void cast(pt_state* s, const float o[3], const float d[3], int surf, cbqo
 {
 	cbqo_ray r;
 	for (int a = 0; a < 3; a++) { r.o[a] = o[a]; r.d[a] = d[a]; }
-	cbqo_intersect(s->nodes, s->sd, &r, surf, s->p->max_footprint, h, NULL);
+	cbqo_intersect(s->nodes, s->sd, &r, surf, s->p->max_footprint, h, &s->stats);
 	s->rays++;
 }
 
@@ -664,6 +665,8 @@ static void* render_worker(void* arg)
 	return NULL;
 }
 
+static cbqo_stats g_lastRenderStats;
+
 double cbqo_render(const uint32_t* nodes, const cbqo_subdag sd[8], const float* colours,
 	const cbqo_camera* cam, const cbqo_pt_params* p, float* accum, int threads, uint64_t* raysOut)
 {
@@ -688,9 +691,19 @@ double cbqo_render(const uint32_t* nodes, const cbqo_subdag sd[8], const float* 
 	uint64_t rays = 0;
 	for (int t = 0; t < threads; t++) rays += jobs[t].st.rays;
 	if (raysOut) *raysOut = rays;
+	memset(&g_lastRenderStats, 0, sizeof(g_lastRenderStats));
+	for (int t = 0; t < threads; t++) {
+		g_lastRenderStats.rays += jobs[t].st.stats.rays; g_lastRenderStats.hits += jobs[t].st.stats.hits;
+		g_lastRenderStats.subdag_entries += jobs[t].st.stats.subdag_entries; g_lastRenderStats.iterations += jobs[t].st.stats.iterations;
+		g_lastRenderStats.descents += jobs[t].st.stats.descents; g_lastRenderStats.pops += jobs[t].st.stats.pops;
+		g_lastRenderStats.material_steps += jobs[t].st.stats.material_steps;
+	}
 	free(jobs); free(tids);
 	return t1 - t0;
 }
+
+/* Traversal statistics of the last cbqo_render in this process (instrumentation only). */
+void cbqo_last_render_stats(cbqo_stats* out) { *out = g_lastRenderStats; }
 
 
 /* Per-ray trip counts (iterations of the ESVO loop summed over the ray's sub-DAGs): workload-shape

@@ -99,6 +99,7 @@ uint32_t cbqo_pixel_seed(const cbqo_ray* primary, uint32_t sample_index);
  * Returns seconds. */
 double cbqo_render(const uint32_t* nodes, const cbqo_subdag sd[8], const float* colours,
 	const cbqo_camera* cam, const cbqo_pt_params* p, float* accum, int threads, uint64_t* rays_out);
+void cbqo_last_render_stats(cbqo_stats* out);   /* node visits etc. of the last cbqo_render (instrumentation) */
 
 uint64_t cbqo_bit_mix64(uint64_t x);
 uint64_t cbqo_fnv1a(const void* data, int64_t len);

@@ -155,6 +155,12 @@ class Port:
                                     _ptr(accum), int(threads), C.byref(rays))
         return accum, secs, int(rays.value)
 
+    def last_render_stats(self):
+        """Traversal statistics (Stats) of the last render() call: the path tracer's node visits."""
+        st = Stats()
+        self.lib.cbqo_last_render_stats(C.byref(st))
+        return st
+
 
 class Ref:
     """The unmodified reference library behind oracle/ref_shim.cpp."""

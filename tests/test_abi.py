@@ -31,7 +31,7 @@ def test_library_is_in_tree(api):
 
 def test_record_layouts_match_header(api):
     assert api.RAY_DTYPE.itemsize == 24 and api.HIT_DTYPE.itemsize == 40 and api.SUBDAG_DTYPE.itemsize == 32
-    assert C.sizeof(api.Camera) == 104 and C.sizeof(api.PtParams) == 64
+    assert C.sizeof(api.Camera) == 104 and C.sizeof(api.PtParams) == 72 and api.COMPACT_DTYPE.itemsize == 8
 
 
 def test_find_subdags_matches_oracle(api, port, scenes):
