@@ -39,6 +39,10 @@ class Camera(C.Structure):
                 ("right", C.c_double * 3), ("scale", C.c_float), ("pad", C.c_float)]
 
 
+class MeshInfo(C.Structure):
+    _fields_ = [("lower", C.c_float * 3), ("upper", C.c_float * 3), ("is_closed", C.c_uint32), ("is_inside_out", C.c_uint32)]
+
+
 class PtParams(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("spp", C.c_uint32), ("bounces", C.c_uint32),
                 ("variant", C.c_uint32), ("include_sun", C.c_uint32), ("include_sky", C.c_uint32),
@@ -69,6 +73,7 @@ EXPORTS = [
     "cbq_raycast_frame_device",
     "cbq_render", "cbq_render_device", "cbq_rng_points_device",
     "cbq_progressive_pass_device", "cbq_normalise_device", "cbq_blur_device",
+    "cbq_mesh_analyse", "cbq_voxelize",
     "cbq_dag_load", "cbq_dag_free", "cbq_dag_save", "cbq_upload_dag", "cbq_set_log_callback",
     "cbq_shared_alloc", "cbq_shared_open", "cbq_shared_close", "cbq_shared_free", "cbq_copy_device",
     "cbq_host_alloc", "cbq_host_free", "cbq_set_option", "cbq_get_option", "cbq_get_counter", "cbq_reset_counters",
@@ -128,6 +133,8 @@ def load_library():
     L.cbq_progressive_pass_device.argtypes = [vp, C.POINTER(Camera), C.POINTER(PtParams), u32, vp, vp]
     L.cbq_normalise_device.argtypes = [vp, vp, u32, u32, vp, vp]
     L.cbq_blur_device.argtypes = [vp, vp, u32, u32, vp, i32, vp]
+    L.cbq_mesh_analyse.argtypes = [vp, u64, C.POINTER(MeshInfo)]
+    L.cbq_voxelize.argtypes = [vp, vp, vp, u64, C.c_uint8, C.c_uint8, i32, u32, C.POINTER(C.c_int32), vp, C.POINTER(MeshInfo), C.POINTER(u64), C.POINTER(u32)]
     L.cbq_dag_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(u32)), C.POINTER(u64), C.POINTER(u32)]
     L.cbq_dag_free.argtypes = [C.POINTER(u32)]
     L.cbq_dag_free.restype = None
@@ -300,6 +307,14 @@ class Editable:
         if colours is not None:
             colours = np.ascontiguousarray(colours, dtype=np.float32).reshape(256, 3)
         _check(self.L.cbq_editable_sync(self._h, ctx._h, int(bool(first_upload)), _ptr(colours)))
+
+
+def mesh_analyse(triangles):
+    """cbq_mesh_analyse: Mesh::build's verdict (bounds, closed, inside-out) on (n, 9) float32 triangles. Host only."""
+    tris = np.ascontiguousarray(triangles, dtype=np.float32).reshape(-1, 9)
+    info = MeshInfo()
+    _check(load_library().cbq_mesh_analyse(_ptr(tris), len(tris), C.byref(info)))
+    return info
 
 
 def dag_load(path):
@@ -517,6 +532,22 @@ class Context:
     def render_device(self, cam, params, d_accum, stream=None):
         _check(self.L.cbq_render_device(self._h, C.byref(cam), C.byref(params), C.c_void_p(int(d_accum)),
                                         _stream(stream)))
+
+    def voxelize(self, triangles, materials, fill, size_log2, origin, background=0, thin=False, colours=None):
+        """voxelize(volume, mesh, fill, background) (reference voxelization.cpp:692-744) on the device; the result becomes the
+        context's volume. Returns (node_count, root, MeshInfo)."""
+        tris = np.ascontiguousarray(triangles, dtype=np.float32).reshape(-1, 9)
+        mats = np.ascontiguousarray(materials, dtype=np.uint8)
+        assert len(mats) == len(tris)
+        if colours is not None:
+            colours = np.ascontiguousarray(colours, dtype=np.float32).reshape(256, 3)
+        org = (C.c_int32 * 3)(*[int(v) for v in origin])
+        info = MeshInfo()
+        n = C.c_uint64()
+        root = C.c_uint32()
+        _check(self.L.cbq_voxelize(self._h, _ptr(tris), _ptr(mats), len(tris), int(fill), int(background), int(bool(thin)), int(size_log2), org,
+                                   _ptr(colours), C.byref(info), C.byref(n), C.byref(root)))
+        return int(n.value), int(root.value), info
 
     def upload_dag(self, path, colours=None):
         if colours is not None:

@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libcubiquity_b200.so")
-SOURCES = ["api.cu", "trace_kernels.cu", "wavefront_kernels.cu", "viewer_kernels.cu", "bake_kernels.cu", "edit_kernels.cu", "edit.cpp", "host_shim.cpp"]
-HEADERS = ["traverse.cuh", "shading.cuh", "cbq_internal.h", os.path.join("..", "..", "include", "cubiquity_b200.h")]
+SOURCES = ["api.cu", "trace_kernels.cu", "wavefront_kernels.cu", "viewer_kernels.cu", "voxelize_kernels.cu", "bake_kernels.cu", "edit_kernels.cu", "edit.cpp", "host_shim.cpp", "voxelize_host.cpp"]
+HEADERS = ["traverse.cuh", "shading.cuh", "meshmath.cuh", "cbq_internal.h", os.path.join("..", "..", "include", "cubiquity_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -11,6 +11,14 @@
 #include "cbq_internal.h"
 
 extern "C" const char* cbq_dag_error(void);     // host_shim.cpp: why the last cbq_dag_load / cbq_dag_save on this thread failed
+#include "meshmath.cuh"
+namespace cbq {                                  // voxelize_host.cpp
+void analyseMesh(const Tri* tris, uint64_t n, cbq_mesh_info* info);
+}
+#include <vector>
+namespace cbq {
+void splitTriangles(const Tri* tris, const uint8_t* materials, uint64_t n, std::vector<Tri>& out, std::vector<uint8_t>& mats);
+}
 
 #include <algorithm>
 #include <cmath>
@@ -181,6 +189,7 @@ struct cbq_context {
 	// Counters
 	uint64_t launches = 0, raysTraced = 0, bytesH2D = 0, bytesD2H = 0;
 	uint64_t bakeReachable = 0;   // nodes the root reached in the last cbq_bake, before merging
+	uint64_t voxelizeLeaves = 0, voxelizePieces = 0;   // octree leaves classified / triangle pieces scan-converted by the last cbq_voxelize
 	bool deviceDiverged = false;  // a device-side edit / bake / build made the device copy differ from any host array
 
 	const uint32_t* nodesPtr() const { return reinterpret_cast<const uint32_t*>(volume + cbq::kNodeOffset); }
@@ -807,6 +816,123 @@ int cbq_build_dense(cbq_context* ctx, const uint8_t* voxels, uint32_t size_log2,
 	return rc;
 }
 
+int cbq_voxelize(cbq_context* ctx, const float* triangles, const uint8_t* materials, uint64_t triangle_count,
+	uint8_t fill, uint8_t background, int thin, uint32_t size_log2, const int32_t origin[3],
+	const float* colours_rgb, cbq_mesh_info* info_out, uint64_t* node_count, uint32_t* root_index)
+{
+	int rc = bind(ctx); if (rc) return rc;
+	if (!triangles || !materials || !origin || triangle_count == 0) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null or empty mesh");
+	if (size_log2 < 2 || size_log2 > 10) return fail(CBQ_ERROR_INVALID_ARGUMENT, "size_log2 %u out of range (2..10: 4^3 .. 1024^3 voxels)", size_log2);
+	if (background != 0) return fail(CBQ_ERROR_INVALID_ARGUMENT, "background must be material 0: everything outside the grid is empty");
+	if (triangle_count > 0x7fffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "too many triangles");
+	const uint32_t S = 1u << size_log2;
+	bool aligned = true;
+	for (int a = 0; a < 3; a++) {
+		if (((uint32_t)origin[a] & (S / 2 - 1u)) != 0) return fail(CBQ_ERROR_INVALID_ARGUMENT, "origin[%d] = %d is not a multiple of half the grid side (%u)", a, origin[a], S / 2);
+		if ((int64_t)origin[a] + (int64_t)S > 0x80000000ll) return fail(CBQ_ERROR_INVALID_ARGUMENT, "the grid leaves the volume along axis %d", a);
+		aligned = aligned && (((uint32_t)origin[a] & (S - 1u)) == 0);
+	}
+	const cbq::Tri* tris = reinterpret_cast<const cbq::Tri*>(triangles);
+	cbq_mesh_info info;
+	cbq::analyseMesh(tris, triangle_count, &info);            // Mesh::build (voxelization.cpp:765-823)
+	if (info_out) *info_out = info;
+	for (int a = 0; a < 3; a++) {
+		if (!(info.lower[a] - 2.0f >= (float)origin[a]) || !(info.upper[a] + 2.0f <= (float)((int64_t)origin[a] + S - 1)))
+			return fail(CBQ_ERROR_INVALID_ARGUMENT, "the mesh (dilated by 2 voxels) does not fit the grid along axis %d: [%g, %g] vs [%d, %lld]", a,
+				info.lower[a], info.upper[a], origin[a], (long long)origin[a] + S - 1);
+	}
+	if (info.is_inside_out) return fail(CBQ_ERROR_INVALID_ARGUMENT, "the mesh is inside-out (exclusively negative winding numbers): flip its triangles");
+	const bool solid = info.is_closed && fill != background;
+
+	// drawLargeTriangle's subdivision, on the host: the pieces are what gets scan-converted, in the user's order.
+	std::vector<cbq::Tri> pieces;
+	std::vector<uint8_t> pieceMaterials;
+	cbq::splitTriangles(tris, materials, triangle_count, pieces, pieceMaterials);
+	if (pieces.size() > 0x7ffffff0ull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "too many triangle pieces");
+
+	const size_t voxels = (size_t)1 << (3 * size_log2);
+	size_t pyramid = 0;
+	for (uint32_t l = 1; l <= size_log2; l++) pyramid += (size_t)1 << (3 * (size_log2 - l));
+	uint8_t *dVoxels = nullptr, *dOrder = nullptr, *dPyramid = nullptr, *dPieces = nullptr, *dTris = nullptr, *dMisc = nullptr, *dLeaves = nullptr, *dInside = nullptr;
+	cudaStream_t s = ctx->stream;
+	CBQ_CUDA(cudaStreamSynchronize(s));
+	auto cleanup = [&]() { poolFree(ctx, dVoxels); poolFree(ctx, dOrder); poolFree(ctx, dPyramid); poolFree(ctx, dPieces); poolFree(ctx, dTris); poolFree(ctx, dMisc); poolFree(ctx, dLeaves); poolFree(ctx, dInside); };
+#define CBQ_VOX(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cleanup(); return fail(e_ == cudaErrorMemoryAllocation ? CBQ_ERROR_OUT_OF_MEMORY : CBQ_ERROR_CUDA, "cbq_voxelize: %s failed: %s", #expr, cudaGetErrorString(e_)); } } while (0)
+	CBQ_VOX(poolAlloc(ctx, &dVoxels, voxels));
+	CBQ_VOX(poolAlloc(ctx, &dOrder, voxels * sizeof(unsigned int)));
+	CBQ_VOX(poolAlloc(ctx, &dPieces, pieces.size() * sizeof(cbq::Tri) + pieces.size()));
+	CBQ_VOX(poolAlloc(ctx, &dMisc, 256));
+	uint8_t* dPieceMaterials = dPieces + pieces.size() * sizeof(cbq::Tri);
+	CBQ_VOX(cudaMemsetAsync(dVoxels, background, voxels, s));
+	CBQ_VOX(cudaMemsetAsync(dOrder, 0, voxels * sizeof(unsigned int), s));
+	CBQ_VOX(cudaMemcpyAsync(dPieces, pieces.data(), pieces.size() * sizeof(cbq::Tri), cudaMemcpyHostToDevice, s));
+	CBQ_VOX(cudaMemcpyAsync(dPieceMaterials, pieceMaterials.data(), pieces.size(), cudaMemcpyHostToDevice, s));
+	ctx->bytesH2D += pieces.size() * (sizeof(cbq::Tri) + 1);
+	const int sm = ctx->cfg.smCount;
+	uint64_t leafCount = 0;
+	if (!solid) {
+		// the shell only, in the user's order (voxelization.cpp:738-743)
+		CBQ_VOX(cbq::launchShell(dPieces, (uint32_t)pieces.size(), dVoxels, size_log2, origin, 1, background, thin, reinterpret_cast<unsigned int*>(dOrder), sm, s));
+		CBQ_VOX(cbq::launchResolve(dVoxels, reinterpret_cast<unsigned int*>(dOrder), dPieceMaterials, voxels, sm, s));
+		ctx->launches += 2;
+	} else {
+		// (a) the checkerboard shell
+		CBQ_VOX(cbq::launchShell(dPieces, (uint32_t)pieces.size(), dVoxels, size_log2, origin, 0, background, thin, reinterpret_cast<unsigned int*>(dOrder), sm, s));
+		// (b) occupancy pyramid + bounds, leaves, classification, fill
+		CBQ_VOX(poolAlloc(ctx, &dPyramid, pyramid));
+		CBQ_VOX(poolAlloc(ctx, &dTris, triangle_count * sizeof(cbq::Tri)));
+		CBQ_VOX(cudaMemcpyAsync(dTris, tris, triangle_count * sizeof(cbq::Tri), cudaMemcpyHostToDevice, s));
+		ctx->bytesH2D += triangle_count * sizeof(cbq::Tri);
+		int* dBounds = reinterpret_cast<int*>(dMisc);
+		unsigned long long* dCounter = reinterpret_cast<unsigned long long*>(dMisc + 64);
+		const int boundsInit[6] = { 0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000 };
+		CBQ_VOX(cudaMemcpyAsync(dBounds, boundsInit, sizeof(boundsInit), cudaMemcpyHostToDevice, s));
+		CBQ_VOX(cudaMemsetAsync(dCounter, 0, 8, s));
+		std::vector<uint8_t*> level(size_log2 + 1, nullptr);      // level[l]: occupancy of the cells of 2^l voxels
+		{
+			size_t at = 0;
+			for (uint32_t l = 1; l <= size_log2; l++) { level[l] = dPyramid + at; at += (size_t)1 << (3 * (size_log2 - l)); }
+		}
+		CBQ_VOX(cbq::launchOccupancy(dVoxels, size_log2, background, 1, level[1], dBounds, sm, s));
+		for (uint32_t l = 2; l <= size_log2; l++) CBQ_VOX(cbq::launchOccupancy(level[l - 1], size_log2 - (l - 1), background, 0, level[l], dBounds, sm, s));
+		ctx->launches += 1 + size_log2;
+		// Leaves per level: level 0 (voxels of occupied 2x2x2 blocks) ... level size_log2 - 1 (the grid's eight half-side cubes, whose
+		// octree parent is the whole grid only if the grid is aligned to its own size).
+		auto collect = [&](void* out) -> cudaError_t {
+			cudaError_t e = cudaMemsetAsync(dCounter, 0, 8, s);
+			for (uint32_t l = 0; l < size_log2 && e == cudaSuccess; l++) {
+				const uint8_t* parent = (l + 1 == size_log2 && !aligned) ? nullptr : level[l + 1];
+				if (l == 0 && size_log2 == 1) parent = nullptr;
+				e = cbq::launchCollect(l == 0 ? nullptr : level[l], l == 0 ? level[1] : parent, size_log2, l, dBounds, dCounter, out, sm, s);
+			}
+			return e;
+		};
+		CBQ_VOX(collect(nullptr));
+		CBQ_VOX(cudaMemcpyAsync(&leafCount, dCounter, 8, cudaMemcpyDeviceToHost, s));
+		CBQ_VOX(cudaStreamSynchronize(s));
+		ctx->launches += 2 * size_log2;
+		if (leafCount) {
+			CBQ_VOX(poolAlloc(ctx, &dLeaves, leafCount * 16));
+			CBQ_VOX(poolAlloc(ctx, &dInside, leafCount));
+			CBQ_VOX(collect(dLeaves));
+			CBQ_VOX(cbq::launchClassify(dLeaves, leafCount, dTris, (uint32_t)triangle_count, origin, dInside, s));
+			CBQ_VOX(cbq::launchFill(dLeaves, dInside, leafCount, dVoxels, size_log2, fill, background, sm, s));
+			ctx->launches += 2;
+		}
+		// (c) surface materials: the last triangle within distance 1 of every voxel that is not background (or of every voxel, thin)
+		CBQ_VOX(cbq::launchShell(dPieces, (uint32_t)pieces.size(), dVoxels, size_log2, origin, 2, background, thin, reinterpret_cast<unsigned int*>(dOrder), sm, s));
+		CBQ_VOX(cbq::launchResolve(dVoxels, reinterpret_cast<unsigned int*>(dOrder), dPieceMaterials, voxels, sm, s));
+		ctx->launches += 3;
+	}
+	CBQ_VOX(cudaStreamSynchronize(s));
+#undef CBQ_VOX
+	ctx->voxelizeLeaves = leafCount;
+	ctx->voxelizePieces = pieces.size();
+	rc = cbq_build_dense_device(ctx, dVoxels, size_log2, origin, colours_rgb, node_count, root_index);
+	cleanup();
+	return rc;
+}
+
 int cbq_fill_sphere(cbq_context* ctx, float x, float y, float z, float radius, uint8_t material, uint32_t* root_index, uint64_t* node_count)
 {
 	int rc = bind(ctx); if (rc) return rc;
@@ -1367,6 +1493,8 @@ int cbq_get_counter(cbq_context* ctx, const char* key, uint64_t* value)
 	else if (k == "bytes_h2d") *value = ctx->bytesH2D;
 	else if (k == "bytes_d2h") *value = ctx->bytesD2H;
 	else if (k == "bake_reachable") *value = ctx->bakeReachable;
+	else if (k == "voxelize_leaves") *value = ctx->voxelizeLeaves;
+	else if (k == "voxelize_pieces") *value = ctx->voxelizePieces;
 	else if (k == "abandoned_rays") {
 		unsigned long long v = 0;
 		CBQ_CUDA(cudaDeviceSynchronize());

@@ -166,6 +166,16 @@ uint64_t denseNodeCount(uint32_t sizeLog2);   // upper bound: what to allocate
 cudaError_t launchBuildDense(const uint8_t* voxels, uint32_t sizeLog2, const int32_t origin[3], uint32_t* nodes, uint32_t* root, uint64_t* nodeCount,
 	int smCount, cudaStream_t stream, uint64_t* launches);
 
+// Mesh voxeliser (voxelize_kernels.cu; host helpers in voxelize_host.cpp). Leaf records are 16 bytes.
+cudaError_t launchShell(const void* tris, uint32_t count, uint8_t* voxels, uint32_t gridLog2, const int32_t origin[3], int mode, uint8_t background, int thin,
+	unsigned int* order, int smCount, cudaStream_t stream);
+cudaError_t launchResolve(uint8_t* voxels, unsigned int* order, const uint8_t* materials, size_t n, int smCount, cudaStream_t stream);
+cudaError_t launchOccupancy(const uint8_t* below, uint32_t belowLog2, uint8_t background, int fromVoxels, uint8_t* out, int* bounds, int smCount, cudaStream_t stream);
+cudaError_t launchCollect(const uint8_t* self, const uint8_t* parent, uint32_t gridLog2, uint32_t log2, const int* bounds, unsigned long long* counter, void* out,
+	int smCount, cudaStream_t stream);
+cudaError_t launchClassify(const void* leaves, uint64_t count, const void* tris, uint32_t triCount, const int32_t origin[3], uint8_t* inside, cudaStream_t stream);
+cudaError_t launchFill(const void* leaves, const uint8_t* inside, uint64_t count, uint8_t* voxels, uint32_t gridLog2, uint8_t fill, uint8_t background, int smCount, cudaStream_t stream);
+
 // Device-side sphere brush (edit_kernels.cu). Work-list entries are 32 bytes; state is fillSphereStateBytes() bytes.
 cudaError_t launchFillSphere(uint32_t* nodes, uint32_t capacity, uint32_t root, float x, float y, float z, float radius, uint32_t material,
 	void* itemList, uint32_t itemCapacity, unsigned int* state, int smCount, cudaStream_t stream, uint64_t* launches);

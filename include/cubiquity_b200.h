@@ -182,6 +182,28 @@ int cbq_build_dense(cbq_context* ctx, const uint8_t* voxels, uint32_t size_log2,
 int cbq_build_dense_device(cbq_context* ctx, const uint8_t* d_voxels, uint32_t size_log2, const int32_t origin[3],
                            const float* colours_rgb, uint64_t* node_count, uint32_t* root_index);
 
+/* ---- mesh voxeliser ---- */
+
+/* What Mesh::build decides about a triangle list (src/library/voxelization.cpp:765-823): bounds, and from 100 winding-number
+ * samples whether the mesh is closed and whether it is inside-out. Host only. */
+typedef struct cbq_mesh_info { float lower[3], upper[3]; uint32_t is_closed, is_inside_out; } cbq_mesh_info;
+int cbq_mesh_analyse(const float* triangles, uint64_t triangle_count, cbq_mesh_info* info);
+
+/* voxelize(volume, mesh, fill, background) (voxelization.cpp:692-744, with Mesh::build :765-823) on the device, into a grid of
+ * S = 2^size_log2 voxels a side at `origin` (a multiple of S / 2 per axis, as for cbq_build_dense; 2 <= size_log2 <= 10) that
+ * becomes the context's volume, hash-consed like Volume::bake. triangles: triangle_count x 9 floats in voxel coordinates, user
+ * order (later triangles win where several touch a voxel); materials: one id per triangle; thin = Mesh::isThin. A closed mesh is
+ * filled: 6-separating shell by the topological test, every octree leaf next to or between the shells classified by the
+ * generalized winding number at its centre (|w| > 0.501), surface materials from the triangles within distance 1. An open mesh
+ * yields the shell only. background must be 0 (everything outside the grid is empty) and the mesh, dilated by 2 voxels, must fit
+ * the grid; an inside-out mesh is refused (flip it: the reference would swap fill and background, i.e. fill the universe).
+ * *info (nullable) receives Mesh::build's verdict. Voxel-for-voxel equal to the reference on the test meshes; the reference sums
+ * the winding number through a patch hierarchy, here it is the flat sum -- the same number up to float rounding, which the
+ * threshold's margin is there to absorb (voxelization.cpp:362-366). */
+int cbq_voxelize(cbq_context* ctx, const float* triangles, const uint8_t* materials, uint64_t triangle_count,
+                 uint8_t fill, uint8_t background, int thin, uint32_t size_log2, const int32_t origin[3],
+                 const float* colours_rgb, cbq_mesh_info* info, uint64_t* node_count, uint32_t* root_index);
+
 /* The reference's runtime edit -- Volume::checkpoint() + fillBrush(volume, SphereBrush(centre, radius), material)
  * (viewer.cpp:165-168; voxelization.cpp:825-915, voxelization.h:91-127) -- applied to the DEVICE copy: no host
  * editor, no PCIe transfer of a dirty tail. Same voxels change as in the reference (same contains() arithmetic and

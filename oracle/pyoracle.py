@@ -199,6 +199,8 @@ class Ref:
         L.ref_pt_render.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_float,
                                     C.c_int, C.c_void_p]
         L.ref_camera_rays.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p]
+        L.ref_voxelize.restype = C.c_double
+        L.ref_voxelize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint8, C.c_uint8, C.c_int, C.c_void_p]
         L.ref_bit_mix.restype = C.c_uint64
         L.ref_bit_mix.argtypes = [C.c_uint64]
         L.ref_fnv1a.restype = C.c_uint64
@@ -291,6 +293,24 @@ class RefVolume:
 
     def fill_sphere(self, x, y, z, radius, material):
         self.L.ref_volume_fill_sphere(self.h, float(x), float(y), float(z), float(radius), int(material))
+
+    def voxelize(self, triangles, materials, fill, background=0, thin=False):
+        """The reference's voxelize(volume, mesh, fill, background) with Mesh::build (voxelization.cpp:692-823); the result
+        replaces this volume's content. triangles: (n, 9) float32, materials: (n,) uint8. Returns (is_closed,
+        is_inside_out, seconds). Runs in a process of its own (oracle/ref_voxelize_helper.py explains why) and comes back
+        through the reference's own .dag writer and reader."""
+        import sys
+        tris = np.ascontiguousarray(triangles, dtype=np.float32).reshape(-1, 9)
+        mats = np.ascontiguousarray(materials, dtype=np.uint8)
+        with tempfile.TemporaryDirectory() as d:
+            tris.tofile(os.path.join(d, "t.f32"))
+            mats.tofile(os.path.join(d, "m.u8"))
+            out = os.path.join(d, "v.dag")
+            r = subprocess.run([sys.executable, os.path.join(HERE, "ref_voxelize_helper.py"), REF_SO, os.path.join(d, "t.f32"), os.path.join(d, "m.u8"),
+                                str(int(fill)), str(int(background)), str(int(bool(thin))), out], capture_output=True, text=True, check=True)
+            closed, inside_out, secs = r.stdout.split()
+            self.load(out)
+        return closed == "1", inside_out == "1", float(secs)
 
     def nodes(self):
         """Copy of the raw node array including the 256 material nodes, shape (n, 8)."""

@@ -230,6 +230,26 @@ void ref_trace_ray_ref(void* v, const void* rays, uint64_t n, void* hitsOut)
 }
 
 // Known-answer hashes of test_base.cpp:14-35, exposed so tests can pin the port's copies.
+// The reference's mesh voxeliser: Mesh::addTriangle for every triangle, Mesh::build, voxelize (voxelization.cpp:692-823).
+// flags[0] = isClosed, flags[1] = isInsideOut as Mesh::build decided them. Returns seconds spent in voxelize().
+double ref_voxelize(void* v, const float* tris9, const uint8_t* mats, uint64_t n, uint8_t fill, uint8_t background, int thin, uint32_t* flags)
+{
+	RefVolume* rv = static_cast<RefVolume*>(v);
+	Mesh mesh;
+	for (uint64_t i = 0; i < n; i++) {
+		const float* t = tris9 + 9 * i;
+		mesh.addTriangle(Triangle(vec3f(t[0], t[1], t[2]), vec3f(t[3], t[4], t[5]), vec3f(t[6], t[7], t[8])), mats[i]);
+	}
+	mesh.isThin = thin != 0;
+	mesh.build();
+	if (flags) { flags[0] = mesh.isClosed ? 1u : 0u; flags[1] = mesh.isInsideOut ? 1u : 0u; }
+	const auto t0 = std::chrono::steady_clock::now();
+	voxelize(rv->volume, mesh, fill, background);
+	const auto t1 = std::chrono::steady_clock::now();
+	rv->subdagsValid = false;
+	return std::chrono::duration<double>(t1 - t0).count();
+}
+
 uint64_t ref_bit_mix(uint64_t x) { return Internals::bit_mix(x); }
 uint64_t ref_fnv1a(const void* data, int64_t len) { return Internals::fnv1a(data, len); }
 
