@@ -26,7 +26,10 @@ namespace cbq {
 namespace {
 
 constexpr unsigned kFullMask = 0xffffffffu;
-constexpr int kChunk = 32;            // rays claimed per atomic ticket (small: ~14 claims per warp per frame keeps the tail short)
+#ifndef CBQ_CHUNK
+#define CBQ_CHUNK 32
+#endif
+constexpr int kChunk = CBQ_CHUNK;     // rays claimed per atomic ticket (small: ~14 claims per warp per frame keeps the tail short)
 #ifndef CBQ_STEPS_PER_ROUND
 #define CBQ_STEPS_PER_ROUND 8
 #endif

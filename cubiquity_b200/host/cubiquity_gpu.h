@@ -94,6 +94,24 @@ public:
 	}
 	bool download(uint64_t begin, uint64_t count, void* nodesOut) { return cbq_download_nodes(mCtx, begin, count, static_cast<uint32_t*>(nodesOut)) == CBQ_OK; }
 
+	// Volume::load(filename) + upload (storage.cpp:505-528), with the file checked against its header.
+	bool load(const std::string& filename, const float* coloursRgb = nullptr) { return cbq_upload_dag(mCtx, filename.c_str(), coloursRgb) == CBQ_OK; }
+
+	// voxelize(volume, mesh, fill, background) after mesh.build() (voxelization.cpp:692-744, 765-823): triangles = 9 floats each in
+	// voxel coordinates, user order; the result becomes this volume. closed / insideOut report Mesh::build's verdict.
+	bool voxelize(const std::vector<float>& triangles, const std::vector<uint8_t>& materials, uint8_t fill, bool thin,
+		uint32_t sizeLog2, const int32_t origin[3], bool* closed = nullptr, bool* insideOut = nullptr, const float* coloursRgb = nullptr)
+	{
+		cbq_mesh_info info{};
+		uint64_t count = 0; uint32_t root = 0;
+		const bool ok = cbq_voxelize(mCtx, triangles.data(), materials.data(), materials.size(), fill, 0, thin ? 1 : 0, sizeLog2, origin,
+			coloursRgb, &info, &count, &root) == CBQ_OK;
+		if (closed) *closed = info.is_closed != 0;
+		if (insideOut) *insideOut = info.is_inside_out != 0;
+		if (ok) mSynced = count;
+		return ok;
+	}
+
 	SubDAGArray subDAGs() const
 	{
 		SubDAGArray a{};
@@ -133,6 +151,23 @@ inline bool intersectVolume(const GpuVolume& volume, const std::vector<cbq_ray>&
 	out.assign(rays.size(), cbq_hit{});
 	return cbq_trace(volume.context(), rays.data(), rays.size(), computeSurfaceProperties ? CBQ_TRACE_SURFACE : 0u,
 		maxFootprint, out.data()) == CBQ_OK;
+}
+
+// Batch form with 8-byte results (24 + 8 bytes per ray over PCIe instead of 24 + 40): everything RayVolumeIntersection carries
+// except position. expand() re-forms the full records, position = origin + dir * distance as raytracing.cpp:463-466 computes it.
+inline bool intersectVolumeCompact(const GpuVolume& volume, const std::vector<cbq_ray>& rays, bool computeSurfaceProperties,
+	float maxFootprint, std::vector<cbq_hit_compact>& out)
+{
+	out.assign(rays.size(), cbq_hit_compact{});
+	return cbq_trace_compact(volume.context(), rays.data(), rays.size(), computeSurfaceProperties ? CBQ_TRACE_SURFACE : 0u,
+		maxFootprint, out.data()) == CBQ_OK;
+}
+
+inline bool expand(const std::vector<cbq_ray>& rays, const std::vector<cbq_hit_compact>& compact, std::vector<cbq_hit>& out, int threads = 0)
+{
+	if (rays.size() != compact.size()) return false;
+	out.assign(rays.size(), cbq_hit{});
+	return cbq_expand_hits(rays.data(), compact.data(), rays.size(), out.data(), threads) == CBQ_OK;
 }
 
 } // namespace CubiquityGPU

@@ -71,7 +71,8 @@ for f in range(args.frames):
 hits = torch.zeros(n * 10, dtype=torch.int32, device=dev)
 out = {"tag": args.tag, "opts": args.opt, "frames": args.frames}
 
-ctx.set_option("refill_threshold", 32)
+thr0 = [o for o in args.opt if o.startswith("refill_threshold=")]
+ctx.set_option("refill_threshold", int(thr0[0].split("=")[1]) if thr0 else 32)
 ctx.set_option("adaptive_order", 0)
 ms, best = timed(lambda: ctx.trace_device(rays.data_ptr(), n, hits.data_ptr(), True, -1.0, stream))
 out["primary_cold_grays"] = n / ms / 1e6
