@@ -548,7 +548,7 @@ int cbq_create(int device, cbq_context** out)
 	ctx->cfg.refillThreshold = 8;    // robust default: +68 % on incoherent rays, -7 % on coherent ones (profiles/r01_sweeps.md)
 	ctx->cfg.refillQuantum = 1;
 	ctx->cfg.stackLevels = 33;
-	ctx->cfg.sampleGroup = 0;    // auto; 1080p, 4 bounces: 512 / 734 / 789 / 812 M spp/s for groups of 1 / 4 / 8 / 16 (profiles/r01_analysis.md)
+	ctx->cfg.sampleGroup = 0;    // auto; 1080p, 4 bounces: 915 / 965 M spp/s for groups of 8 / 16 (profiles/r02_analysis.md)
 	*out = ctx;
 	return CBQ_OK;
 }
@@ -1255,15 +1255,15 @@ int cbq_render_device(cbq_context* ctx, const cbq_camera* cam, const cbq_pt_para
 		pixels = tiles.size() * 4096;
 	}
 	if (pixels == 0) return CBQ_OK;
-	// Samples traced together. 0 = auto: aim at ~16 M paths per wave (8 samples of a 1080p frame, 16 of a
-	// 1/8 share), between 1 and 16; an explicit value is still capped at 32 M paths (~8.5 GB of buffers).
+	// Samples traced together. 0 = auto: as many as fit ~32 M paths per wave (16 samples of a 1080p frame, ~12 GB of
+	// path buffers), between 1 and 16: what the samples share (primary ray, depth-0 sun ray) is traced once per wave.
 	cbq::LaunchConfig renderCfg = ctx->cfg;
-	if (ctx->cfg.sampleGroup <= 0) renderCfg.sampleGroup = (int)std::max<size_t>(1, std::min<size_t>(16, (16u << 20) / pixels));
+	if (ctx->cfg.sampleGroup <= 0) renderCfg.sampleGroup = (int)std::max<size_t>(1, std::min<size_t>(16, (32u << 20) / pixels));
 	else renderCfg.sampleGroup = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->cfg.sampleGroup, (32u << 20) / pixels));
 	const size_t paths = pixels * std::min<size_t>(p->spp, (size_t)renderCfg.sampleGroup);
 	if (paths > 0xffffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "rectangle too large for 32-bit path ids");
-	if (paths > ctx->wavefront.pixelCapacity) CBQ_CUDA(cudaDeviceSynchronize());   // buffers may still be in use
-	CBQ_CUDA((cudaError_t)cbq::wavefrontReserve(ctx->wavefront, paths));
+	if (paths > ctx->wavefront.pathCapacity || pixels > ctx->wavefront.pixelCapacity) CBQ_CUDA(cudaDeviceSynchronize());   // buffers may still be in use
+	CBQ_CUDA((cudaError_t)cbq::wavefrontReserve(ctx->wavefront, paths, pixels));
 	struct Adaptor { static int next(void* user, cudaStream_t st, unsigned long long** out) { return nextQueue(static_cast<cbq_context*>(user), st, out); } };
 	CBQ_CUDA(cbq::launchRenderWavefront(a, ctx->wavefront, renderCfg, s, &Adaptor::next, ctx, &ctx->launches));
 	return CBQ_OK;

@@ -127,25 +127,27 @@ struct RenderArgs {
 
 // Wavefront path tracer (wavefront_kernels.cu): per-bounce kernels around the ray-cast kernel.
 struct WavefrontBuffers {
-	size_t pixelCapacity = 0;      // PATHS (pixels x samples per group) of the largest wave so far; all sizes below are in paths
-	Hit* hits = nullptr;           // surface hits of the current depth            [pixels]
-	Ray* rays[2] = { nullptr, nullptr };        // bounce rays, ping-pong           [pixels]
-	uint32_t* pixel[2] = { nullptr, nullptr };  // rect-local pixel id of each path [pixels]
-	uint32_t* rng[2] = { nullptr, nullptr };    // RNG state of each path           [pixels]
-	float* sunTerm = nullptr;      // 0.1 * max(dot(sun, n), 0) of each live path  [pixels]
-	Ray* shadowRays = nullptr;     // sun + sky shadow rays of the live paths      [2 * pixels]
-	uint8_t* shadowFlags = nullptr;//                                              [2 * pixels]
-	float* colour = nullptr;       // c[k] per depth, SoA [depth][3][pixels]
-	float* direct = nullptr;       // D[k] per depth (grey), [depth][pixels]
-	float* radiance = nullptr;     // finished radiance of each path, SoA [3][pixels]
-	unsigned long long* counters = nullptr;     // live paths per depth             [8]
+	size_t pathCapacity = 0;       // PATHS (pixels x samples per group) of the largest wave so far
+	size_t pixelCapacity = 0;      // pixels of the largest rectangle so far
+	Hit* hits = nullptr;           // surface hits of the current depth            [paths]
+	Ray* rays[2] = { nullptr, nullptr };        // bounce rays, ping-pong           [paths]
+	uint32_t* pixel[2] = { nullptr, nullptr };  // path id of each compacted slot   [paths]
+	uint32_t* rng[2] = { nullptr, nullptr };    // RNG state of each path           [paths]
+	float4* hist[2] = { nullptr, nullptr };     // {c[k].rgb, D[k]} of each path, plane k at [k * pathCapacity]  [6 * paths]
+	Ray* shadowRays = nullptr;     // sun + sky shadow rays of the live paths      [2 * paths]
+	uint8_t* shadowFlags = nullptr;//                                              [2 * paths]
+	Ray* sunRays = nullptr;        // depth 0: one sun ray per lit pixel           [pixels]
+	uint8_t* sunFlags = nullptr;   //                                              [pixels]
+	uint32_t* sunSlot = nullptr;   // which of them belongs to a pixel             [pixels]
+	float4* radiance = nullptr;    // finished radiance of each path id            [paths]
+	unsigned long long* counters = nullptr;     // [0..5] live paths per depth, [7] depth-0 sun rays
 };
 // Viewer passes (viewer_kernels.cu): progressive accumulation, normalise, edge-stopping blur.
 cudaError_t launchProgressiveAdd(float* scratchRgb, float* rgba, uint32_t width, uint32_t height, uint32_t groupCount, uint32_t groupIndex, float samples, cudaStream_t stream);
 cudaError_t launchNormalise(const float* rgba, uint32_t width, uint32_t height, float* rgb, cudaStream_t stream);
 cudaError_t launchBlur(const float* in, float* out, uint32_t width, uint32_t height, int vertical, cudaStream_t stream);
 cudaError_t launchRngPoints(const uint32_t* seeds, uint64_t n, int draws, float* points, uint32_t* states, cudaStream_t stream);
-int wavefrontReserve(WavefrontBuffers& b, size_t paths);       // cudaError_t as int
+int wavefrontReserve(WavefrontBuffers& b, size_t paths, size_t pixels);       // cudaError_t as int
 void wavefrontRelease(WavefrontBuffers& b);
 // nextQueue hands out zeroed ticket counters for the trace launches.
 typedef int (*QueueFn)(void* user, cudaStream_t stream, unsigned long long** out);
