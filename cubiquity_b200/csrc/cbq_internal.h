@@ -100,7 +100,8 @@ struct TraceArgs {
 	// optional: batch size read on the device (count = *countPtr * countScale), flag-only results
 	const unsigned long long* countPtr;
 	uint32_t countScale;
-	uint8_t* flags;
+	uint8_t* flags;                  // alone: one byte per ray instead of a record (shadow rays); with `hits`: both
+	const uint32_t* flagIndex;       // flag-only results go to flags[flagIndex[slot]]
 	cbq_hit_compact* compact;        // != nullptr: 8-byte results (cbq_trace_compact) instead of `hits`
 	bool remoteResults;              // `compact` lives in another GPU's memory: coalesce the stores per warp (ParkedCompactSink)
 	uint32_t untileWidth;            // != 0: rays are in 8x4-tile order of an image this wide; write hits row-major
@@ -136,11 +137,14 @@ struct WavefrontBuffers {
 	float4* hist[2] = { nullptr, nullptr };     // {c[k].rgb, D[k]} of each path, plane k at [k * pathCapacity]  [6 * paths]
 	Ray* shadowRays = nullptr;     // sun + sky shadow rays of the live paths      [2 * paths]
 	uint8_t* shadowFlags = nullptr;//                                              [2 * paths]
-	Ray* sunRays = nullptr;        // depth 0: one sun ray per lit pixel           [pixels]
-	uint8_t* sunFlags = nullptr;   //                                              [pixels]
-	uint32_t* sunSlot = nullptr;   // which of them belongs to a pixel             [pixels]
+	uint8_t* hitFlags = nullptr;   // hit or miss of each surface ray of the current depth [paths]
+	Ray* sunRays = nullptr;        // depth 0: one sun ray per lit pixel, compacted [pixels]
+	uint32_t* sunPixel = nullptr;  // the pixel each of them belongs to            [pixels]
+	uint8_t* sunFlags = nullptr;   // their results, by pixel                      [pixels]
+	uint32_t* pixelHash = nullptr; // per-pixel part of the RNG seed               [pixels]
+	uint8_t* onImage = nullptr;    // the pixel exists (tile lists may overhang)   [pixels]
 	float4* radiance = nullptr;    // finished radiance of each path id            [paths]
-	unsigned long long* counters = nullptr;     // [0..5] live paths per depth, [7] depth-0 sun rays
+	unsigned long long* counters = nullptr;     // [0..5] live paths per depth, [7] depth-0 sun rays, [8..13] run tickets of the shade kernels
 };
 // Viewer passes (viewer_kernels.cu): progressive accumulation, normalise, edge-stopping blur.
 cudaError_t launchProgressiveAdd(float* scratchRgb, float* rgba, uint32_t width, uint32_t height, uint32_t groupCount, uint32_t groupIndex, float samples, cudaStream_t stream);

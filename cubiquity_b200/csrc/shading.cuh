@@ -48,13 +48,14 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t h)   // glsl/pathtracing.fra
 }
 
 // Per-sample RNG seed: hashRay(primary ray) ^ bitMix(frameId) (glsl/pathtracing.frag:770-780,786,816).
-__device__ __forceinline__ uint32_t pixelSeed(const Ray& r, uint32_t sampleIndex)
+__device__ __forceinline__ uint32_t rayHash(const Ray& r)
 {
 	uint32_t h = 0;
 	h ^= fmix32(__float_as_uint(r.o[0])); h ^= fmix32(__float_as_uint(r.o[1])); h ^= fmix32(__float_as_uint(r.o[2]));
 	h ^= fmix32(__float_as_uint(r.d[0])); h ^= fmix32(__float_as_uint(r.d[1])); h ^= fmix32(__float_as_uint(r.d[2]));
-	return h ^ fmix32(sampleIndex);
+	return h;
 }
+__device__ __forceinline__ uint32_t pixelSeed(const Ray& r, uint32_t sampleIndex) { return rayHash(r) ^ fmix32(sampleIndex); }
 
 __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz)
 {
@@ -66,13 +67,21 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
 // (about one seed in 4e8) and the reference's loop would then spin for ever; after kMaxBallTries
 // rejected candidates the last one is returned as it is. Same rule as the CPU checker.
 constexpr int kMaxBallTries = 64;
-__device__ __forceinline__ void unitBallPoint(uint32_t& rng, float& x, float& y, float& z)
+// A coordinate takes one of 1024 values, (k - 511.5f) / 511.5f: the kernels keep them in a shared-memory table, filled
+// with the reference's own expression, instead of three IEEE divisions per candidate (half of the shade kernel's
+// instructions went there, profiles/r02_analysis.md).
+constexpr int kBallLutSize = 1024;
+__device__ __forceinline__ void fillBallLut(float* lut)   // every thread of the CTA; ends with a barrier
+{
+	for (int k = threadIdx.x; k < kBallLutSize; k += blockDim.x) lut[k] = ((float)k - 511.5f) / 511.5f;
+	__syncthreads();
+}
+__device__ __forceinline__ void unitBallPoint(const float* __restrict__ lut, uint32_t& rng, float& x, float& y, float& z)
 {
 	int tries = 0;
 	do {
 		rng = (uint32_t)bitMix64((uint64_t)rng);
-		x = (float)(rng & 0x3FFu); y = (float)((rng >> 10) & 0x3FFu); z = (float)((rng >> 20) & 0x3FFu);
-		x = (x - 511.5f) / 511.5f; y = (y - 511.5f) / 511.5f; z = (z - 511.5f) / 511.5f;
+		x = lut[rng & 0x3FFu]; y = lut[(rng >> 10) & 0x3FFu]; z = lut[(rng >> 20) & 0x3FFu];
 	} while (dot3(x, y, z, x, y, z) >= 1.0f && ++tries < kMaxBallTries);
 }
 

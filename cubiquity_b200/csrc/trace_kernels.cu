@@ -174,6 +174,23 @@ struct FlagSink {
 	static constexpr bool kNeedsPosition = false;
 	__device__ __forceinline__ void write(uint64_t slot, const Hit& h) const { flags[slot] = (uint8_t)h.hit; }
 };
+// Path tracer, surface rays: the record plus a byte per ray that says hit or miss, so that the shade kernel can count
+// its survivors from one coalesced byte per path before it touches the records (wavefront_kernels.cu, pass 1).
+struct FullFlagSink {
+	static constexpr bool kParked = false;
+	Hit* __restrict__ hits;
+	uint8_t* __restrict__ flags;
+	static constexpr bool kNeedsPosition = true;
+	__device__ __forceinline__ void write(uint64_t slot, const Hit& h) const { storeHit(hits, slot, h); flags[slot] = (uint8_t)(h.hit != 0u); }
+};
+// Path tracer, depth-0 sun rays (one per lit pixel, compacted): the flag goes to the ray's PIXEL.
+struct ScatterFlagSink {
+	static constexpr bool kParked = false;
+	uint8_t* __restrict__ flags;
+	const uint32_t* __restrict__ index;
+	static constexpr bool kNeedsPosition = false;
+	__device__ __forceinline__ void write(uint64_t slot, const Hit& h) const { flags[index[slot]] = (uint8_t)h.hit; }
+};
 
 #ifndef CBQ_TRACE_MIN_BLOCKS
 #define CBQ_TRACE_MIN_BLOCKS 4
@@ -439,8 +456,10 @@ cudaError_t launchPersistentLod(const TraceArgs& a, const Source& src, const Sin
 template <typename Source>
 cudaError_t launchPersistent(const TraceArgs& a, bool surface, const Source& src, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
 {
+	if (a.flags && a.hits) return launchPersistentLod<true>(a, src, FullFlagSink{ a.hits, a.flags }, tickets, cfg, stream);   // path tracer, surface rays
 	if (a.flags) {
 		// Flag-only results are for shadow rays, which never ask for surface properties.
+		if (a.flagIndex) return launchPersistentLod<false>(a, src, ScatterFlagSink{ a.flags, a.flagIndex }, tickets, cfg, stream);
 		return launchPersistentLod<false>(a, src, FlagSink{ a.flags }, tickets, cfg, stream);
 	}
 	if (a.compact && a.remoteResults) {

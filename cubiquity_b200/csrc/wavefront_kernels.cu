@@ -71,14 +71,25 @@ struct ShadeIo {
 	size_t capacity;                         // slots per history plane
 	const unsigned long long* pathCount;     // batch size (nullptr at depth 0: w.paths)
 	unsigned long long* liveCount;           // survivors
+	unsigned long long* tickets;             // runs handed out so far (zero at launch)
 	Ray* shadowRays;                         // written for this depth ...
 	const uint8_t* shadowFlags;              // ... read for the previous one
-	unsigned long long* sunCount;            // depth-0 sun rays: one per lit pixel
+	const uint8_t* hitFlags;                 // one byte per surface ray of this depth: hit or miss
+	const uint32_t* pixelHash;               // depth 0: per-pixel part of the RNG seed
+	const uint8_t* onImage;                  // depth 0: the pixel exists (tile lists may overhang the image)
+	unsigned long long* sunCount;            // depth-0 sun rays: one per lit pixel, compacted ...
 	Ray* sunRays;
-	uint32_t* sunSlot;                       // [pixels]: which of them is this pixel's
-	const uint8_t* sunFlags;
+	uint32_t* sunPixel;                      // ... with the pixel each belongs to,
+	const uint8_t* sunFlags;                 // which is where its flag goes [pixels]
 	float4* radiance;                        // finished radiance of each path id
 };
+
+// A 24-byte ray as three 8-byte stores (rays sit at multiples of 24 bytes in 256-byte aligned buffers).
+__device__ __forceinline__ void storeRay(Ray* __restrict__ rays, uint64_t index, float ox, float oy, float oz, float dx, float dy, float dz)
+{
+	float2* p = reinterpret_cast<float2*>(rays + index);
+	p[0] = make_float2(ox, oy); p[1] = make_float2(oz, dx); p[2] = make_float2(dy, dz);
+}
 
 // gatherLighting's sum for depth kDepth - 1 (pathtracing_demo.cpp:96-99, :111-114) from that depth's shadow flags.
 template <int kDepth>
@@ -86,7 +97,7 @@ __device__ __forceinline__ float directLight(const WaveParams& w, const ShadeIo&
 {
 	float d = 0.0f;
 	if (kDepth == 1 && w.sunShared) {
-		if (!io.sunFlags[io.sunSlot[pathId % w.pixels]]) d += sunTerm;
+		if (!io.sunFlags[pathId % w.pixels]) d += sunTerm;
 		if (w.p.include_sky) { if (!io.shadowFlags[slot]) d += 1.5f; }
 	} else {
 		uint32_t k = 0;
@@ -96,33 +107,23 @@ __device__ __forceinline__ float directLight(const WaveParams& w, const ShadeIo&
 	return d;
 }
 
-// Fold a finished path back to front (pathtracing_demo.cpp:143, :182-185). `lastD` is D[kLevels - 1], which the
-// history plane does not hold yet.
+// Fold a finished path back to front (pathtracing_demo.cpp:143, :182-185) from its history {c[k].rgb, D[k]}, k < kLevels.
 template <int kLevels>
-__device__ __forceinline__ float4 foldPath(int variant, const float4* __restrict__ hist, size_t capacity, uint64_t slot, float lastD,
-	float r, float g, float b)
+__device__ __forceinline__ float4 foldPath(int variant, const float4 (&h)[kMaxDepth], float r, float g, float b)
 {
 	if (variant == CBQ_VARIANT_RECURSIVE) {
 #pragma unroll
 		for (int k = kLevels - 1; k >= 0; k--) {
-			const float4 v = hist[(size_t)k * capacity + slot];
-			const float d = (k == kLevels - 1) ? lastD : v.w;
-			r = v.x * (d + r);
-			g = v.y * (d + g);
-			b = v.z * (d + b);
+			r = h[k].x * (h[k].w + r);
+			g = h[k].y * (h[k].w + g);
+			b = h[k].z * (h[k].w + b);
 		}
 	} else if (kLevels > 0) {
 		float ir = 0.0f, ig = 0.0f, ib = 0.0f;
-		if (kLevels > 1) {
-			const float4 v1 = hist[capacity + slot];
-			const float d1 = (kLevels == 2) ? lastD : v1.w;
-			ir = v1.x * d1; ig = v1.y * d1; ib = v1.z * d1;
-		}
-		const float4 v0 = hist[slot];
-		const float d0 = (kLevels == 1) ? lastD : v0.w;
-		r = v0.x * (d0 + ir);
-		g = v0.y * (d0 + ig);
-		b = v0.z * (d0 + ib);
+		if (kLevels > 1) { ir = h[1].x * h[1].w; ig = h[1].y * h[1].w; ib = h[1].z * h[1].w; }
+		r = h[0].x * (h[0].w + ir);
+		g = h[0].y * (h[0].w + ig);
+		b = h[0].z * (h[0].w + ib);
 		const float gamma = (float)(1.0 / 2.2);
 		r = powf(r, gamma); g = powf(g, gamma); b = powf(b, gamma);
 	}
@@ -147,134 +148,210 @@ accumulateKernel(WaveParams w, const float4* __restrict__ radiance, float* __res
 	}
 }
 
+// Per pixel, once per wave: hashRay(primary ray) of the per-sample RNG seed (glsl/pathtracing.frag:770-780); the
+// sample index is mixed in per path. Pixels of a tile that overhangs the image get no ray and no path.
+__global__ void __launch_bounds__(256)
+seedKernel(WaveParams w, uint32_t* __restrict__ pixelHash, uint8_t* __restrict__ onImage)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < w.pixels; i += gridDim.x * blockDim.x) {
+		uint32_t x, y, hash = 0;
+		const bool valid = pixelAt(w.map, i % w.rectW, i / w.rectW, x, y);
+		if (valid) {
+			Ray r;
+			cameraRay(w.cam, (int)x, (int)y, (int)w.p.width, (int)w.p.height, r);
+			hash = rayHash(r);
+		}
+		pixelHash[i] = hash;
+		onImage[i] = valid ? 1 : 0;
+	}
+}
+
+// Is path i of the batch a survivor? One byte per path: the surface-ray trace leaves it next to the record.
+template <int kDepth>
+__device__ __forceinline__ bool survives(const WaveParams& w, const ShadeIo& io, uint64_t i)
+{
+	if (kDepth == 0) {
+		const uint32_t pix = (uint32_t)(i % w.pixels);
+		return io.onImage[pix] != 0 && io.hitFlags[pix] != 0;
+	}
+	return io.hitFlags[i] != 0;
+}
+
+// Records and rays are 40- and 24-byte structures; a lane reading or writing its own costs the load/store unit one
+// sector request per lane and word, and that -- not DRAM, not instruction issue -- is what bounds this kernel
+// (profiles/r02_analysis.md, "Path tracer"). The 32 paths of a step are consecutive and so are the slots of their
+// survivors, so both move through a per-warp shared-memory stage: whole 8-byte words, consecutive lanes, consecutive addresses.
+constexpr int kStageWords = 32 * 2 * 3 + 32 * 3;   // uint2 words per warp: 32 x 2 shadow rays + 32 bounce rays (the 32 x 5 words of the hit records fit inside)
+
+__device__ __forceinline__ void stageRay(uint2* __restrict__ stage, uint32_t index, float ox, float oy, float oz, float dx, float dy, float dz)
+{
+	stage[index * 3u + 0u] = make_uint2(__float_as_uint(ox), __float_as_uint(oy));
+	stage[index * 3u + 1u] = make_uint2(__float_as_uint(oz), __float_as_uint(dx));
+	stage[index * 3u + 2u] = make_uint2(__float_as_uint(dy), __float_as_uint(dz));
+}
+
 template <int kDepth>
 __global__ void __launch_bounds__(256)
 shadeKernel(WaveParams w, ShadeIo io)
 {
+	__shared__ float ballLut[kBallLutSize];
+	__shared__ uint2 stageAll[8][kStageWords];
+	fillBallLut(ballLut);
+	uint2* const stage = stageAll[threadIdx.x >> 5];
 	const uint64_t count = (kDepth == 0) ? (uint64_t)w.paths : (uint64_t)(*io.pathCount);
 	const unsigned lane = threadIdx.x & 31u;
+	const unsigned below = (1u << lane) - 1u;
 	float sunX, sunY, sunZ;
 	sunDirection(sunX, sunY, sunZ);
-	// Whole warps iterate together so the ballots below are convergent.
-	const uint64_t warpStride = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += warpStride) {
-		const uint64_t i = base + lane;
-		bool live = false, finished = false;
-		uint32_t pixel = 0, rng = 0;
-		float lastD = 0.0f;
-		Hit h;
-		h.hit = 0;
-		if (i < count) {
-			pixel = (kDepth == 0) ? (uint32_t)i : io.cur.pixel[i];   // the path id
-			// depth 0: every sample of a pixel shares the pixel's primary hit
-			const uint2* hp = reinterpret_cast<const uint2*>(io.hits + ((kDepth == 0) ? (i % w.pixels) : i));
-			const uint2 a = hp[0], b = hp[1], c = hp[2], d = hp[3], e = hp[4];
-			h.hit = a.x; h.distance = __uint_as_float(a.y); h.material = b.x;
-			h.position[0] = __uint_as_float(b.y); h.position[1] = __uint_as_float(c.x); h.position[2] = __uint_as_float(c.y);
-			h.normal[0] = __uint_as_float(d.x); h.normal[1] = __uint_as_float(d.y); h.normal[2] = __uint_as_float(e.x);
-			bool onImage = true;
-			if (kDepth == 0) {
-				const uint32_t pix = pixel % w.pixels, sample = pixel / w.pixels;
-				uint32_t x, y;
-				onImage = pixelAt(w.map, pix % w.rectW, pix / w.rectW, x, y);
-				if (onImage) {
-					Ray r;
-					cameraRay(w.cam, (int)x, (int)y, (int)w.p.width, (int)w.p.height, r);
-					rng = pixelSeed(r, w.sampleIndex + sample);
-				}
-			} else {
-				rng = io.cur.rng[i];
-				lastD = directLight<kDepth>(w, io, i, pixel, io.cur.hist[(size_t)(kDepth - 1) * io.capacity + i].w);
+	const bool sharedSun = (kDepth == 0) && w.sunShared;
+	const uint32_t perPath = sharedSun ? (w.shadowsPerPath - 1u) : w.shadowsPerPath;     // shadow rays a survivor adds to io.shadowRays
+	const bool bounces = (kDepth != w.lastDepth) && ((w.p.variant == CBQ_VARIANT_RECURSIVE) || kDepth == 0);
+	// A warp takes RUNS of kRun consecutive paths from a ticket counter until the batch is used up (sky and terrain
+	// cost very different amounts of work per path).
+	constexpr uint64_t kRun = 512;
+	for (;;) {
+		unsigned long long ticket = 0;
+		if (lane == 0) ticket = atomicAdd(io.tickets, 1ull);
+		ticket = __shfl_sync(kFullMask, ticket, 0);
+		const uint64_t begin = ticket * kRun;
+		if (begin >= count) break;
+		const uint64_t end = (begin + kRun < count) ? begin + kRun : count;
+
+		// ---- pass 1: count the run's survivors (and, at depth 0, its sun rays: the first sample of each lit pixel) and
+		// reserve their slots with ONE atomic per run, from one byte per path.
+		uint32_t liveTotal = 0, sunTotal = 0;
+#pragma unroll 16
+		for (uint64_t i = begin + lane; i < end; i += 32u) {
+			const bool live = survives<kDepth>(w, io, i);
+			liveTotal += live ? 1u : 0u;
+			sunTotal += (sharedSun && live && i < (uint64_t)w.pixels) ? 1u : 0u;
+		}
+		liveTotal = __reduce_add_sync(kFullMask, liveTotal);
+		if (sharedSun) sunTotal = __reduce_add_sync(kFullMask, sunTotal);
+		unsigned long long slot = 0, sunSlot = 0;
+		if (lane == 0) {
+			if (liveTotal) slot = atomicAdd(io.liveCount, (unsigned long long)liveTotal);
+			if (sunTotal) sunSlot = atomicAdd(io.sunCount, (unsigned long long)sunTotal);
+		}
+		slot = __shfl_sync(kFullMask, slot, 0);
+		if (sharedSun) sunSlot = __shfl_sync(kFullMask, sunSlot, 0);
+
+		// ---- pass 2: light the previous depth, fold the paths that end here, shade and spawn the survivors
+		for (uint64_t base = begin; base < end; base += 32u) {
+			const uint64_t i = base + lane;
+			const uint32_t valid = (uint32_t)((end - base < 32u) ? (end - base) : 32u);
+			// the step's hit records: depth 0 shares the pixel's primary hit between its samples
+			const uint64_t firstRecord = (kDepth == 0) ? base % w.pixels : base;
+			const bool contiguous = (kDepth != 0) || (firstRecord + valid <= (uint64_t)w.pixels);
+			if (contiguous) {
+				const uint2* __restrict__ src = reinterpret_cast<const uint2*>(io.hits + firstRecord);
+				for (uint32_t t = lane; t < valid * 5u; t += 32u) stage[t] = src[t];
 			}
-			// a pixel of a tile that overhangs the image: no ray was cast, no hit record exists, nothing to fold
-			live = onImage && h.hit != 0;
-			finished = onImage && h.hit == 0;
-		}
-		// ---- compaction of the survivors: warp ballot, one atomic per warp, rank by popc. The atomics are issued here
-		// and their results picked up after the arithmetic below: every warp of the grid queues on the same counter.
-		const unsigned liveMask = __ballot_sync(kFullMask, live);
-		const int leader = (liveMask != 0u) ? (__ffs(liveMask) - 1) : 0;
-		unsigned long long slotBase = 0, sunBase = 0;
-		if (liveMask != 0u && lane == (unsigned)leader) slotBase = atomicAdd(io.liveCount, (unsigned long long)__popc(liveMask));
-		unsigned sunMask = 0u;
-		if (kDepth == 0 && w.sunShared) {
-			sunMask = __ballot_sync(kFullMask, live && i < (uint64_t)w.pixels);      // the pixel's first sample casts its sun ray
-			if (sunMask != 0u && lane == (unsigned)(__ffs(sunMask) - 1)) sunBase = atomicAdd(io.sunCount, (unsigned long long)__popc(sunMask));
-		}
-
-		if (finished) {
-			// a missed bounce adds nothing in traceSingleRay (:168-180); everywhere else a miss is the sky (:124, :152)
-			const bool dark = (w.p.variant == CBQ_VARIANT_ONE_BOUNCE) && kDepth == 1;
-			io.radiance[pixel] = foldPath<kDepth>((int)w.p.variant, io.cur.hist, io.capacity, i, lastD, dark ? 0.0f : 0.8f, dark ? 0.0f : 0.8f, dark ? 0.0f : 1.0f);
-		}
-
-		float cr = 0.0f, cg = 0.0f, cb = 0.0f, sunTerm = 0.0f;
-		float skyX = 0.0f, skyY = 0.0f, skyZ = 0.0f, bncX = 0.0f, bncY = 0.0f, bncZ = 0.0f;
-		const float nx = h.normal[0], ny = h.normal[1], nz = h.normal[2];
-		if (live) {
-			surfaceColour(io.colours, h.material, h.position, w.p.add_noise != 0, cr, cg, cb);   // :45-60
-			if (w.p.include_sun) sunTerm = 0.1f * maxStd(dot3(sunX, sunY, sunZ, nx, ny, nz), 0.0f);
-			if (w.p.include_sky) {
-				float rx, ry, rz;
-				unitBallPoint(rng, rx, ry, rz);
-				const float vx = nx + rx, vy = ny + ry, vz = nz + rz;
-				const float len = sqrtf(dot3(vx, vy, vz, vx, vy, vz));
-				skyX = vx / len; skyY = vy / len; skyZ = vz / len;
-			}
-			// The bounce direction is drawn whenever the reference draws it: always in the recursive variant
-			// (before its depth check, :138-141 then :122), only at depth 0 in traceSingleRay (:165).
-			if ((w.p.variant == CBQ_VARIANT_RECURSIVE) || kDepth == 0) {
-				float rx, ry, rz;
-				unitBallPoint(rng, rx, ry, rz);
-				const float vx = nx + rx, vy = ny + ry, vz = nz + rz;
-				const float len = sqrtf(dot3(vx, vy, vz, vx, vy, vz));
-				bncX = vx / len; bncY = vy / len; bncZ = vz / len;
-			}
-		}
-
-		slotBase = __shfl_sync(kFullMask, slotBase, leader);
-		if (kDepth == 0 && w.sunShared) sunBase = __shfl_sync(kFullMask, sunBase, (sunMask != 0u) ? (__ffs(sunMask) - 1) : 0);
-		if (!live) continue;
-		const uint64_t j = slotBase + (uint64_t)__popc(liveMask & ((1u << lane) - 1u));
-
-		// the path's history moves to its new slot; D[kDepth - 1] is complete now, D[kDepth] waits for its flags
+			bool live = false, finished = false;
+			uint32_t pixel = 0, rng = 0;
+			float4 hst[kMaxDepth];       // only [0, kDepth) is touched
+			Hit h;
+			h.hit = 0;
+			bool onImage = false;
+			if (i < end) {
+				pixel = (kDepth == 0) ? (uint32_t)i : io.cur.pixel[i];   // the path id
+				onImage = true;
+				if (kDepth == 0) {
+					const uint32_t pix = (uint32_t)(i % w.pixels);
+					onImage = io.onImage[pix] != 0;     // a pixel of a tile that overhangs the image: no ray was cast, nothing to fold
+					rng = io.pixelHash[pix] ^ fmix32(w.sampleIndex + pixel / w.pixels);
+				} else {
+					rng = io.cur.rng[i];
 #pragma unroll
-		for (int k = 0; k < kDepth; k++) {
-			float4 v = io.cur.hist[(size_t)k * io.capacity + i];
-			if (k == kDepth - 1) v.w = lastD;
-			io.nxt.hist[(size_t)k * io.capacity + j] = v;
-		}
-		io.nxt.hist[(size_t)kDepth * io.capacity + j] = make_float4(cr, cg, cb, sunTerm);
-
-		// gatherLighting (:81-118): both shadow rays leave from position + normal * 0.001
-		const float sx = h.position[0] + nx * 0.001f, sy = h.position[1] + ny * 0.001f, sz = h.position[2] + nz * 0.001f;
-		const bool sharedSun = (kDepth == 0) && w.sunShared;
-		const uint32_t perPath = sharedSun ? (w.shadowsPerPath - 1u) : w.shadowsPerPath;
-		uint32_t k = 0;
-		if (w.p.include_sun) {
-			if (sharedSun) {
-				if (i < (uint64_t)w.pixels) {
-					const uint64_t s = sunBase + (uint64_t)__popc(sunMask & ((1u << lane) - 1u));
-					Ray& r = io.sunRays[s];
-					r.o[0] = sx; r.o[1] = sy; r.o[2] = sz; r.d[0] = sunX; r.d[1] = sunY; r.d[2] = sunZ;
-					io.sunSlot[i] = (uint32_t)s;
+					for (int k = 0; k < kDepth; k++) hst[k] = io.cur.hist[(size_t)k * io.capacity + i];
+					hst[kDepth > 0 ? kDepth - 1 : 0].w = directLight<kDepth>(w, io, i, pixel, hst[kDepth > 0 ? kDepth - 1 : 0].w);   // D[kDepth - 1] is complete now
 				}
-			} else {
-				Ray& r = io.shadowRays[j * perPath + k++];
-				r.o[0] = sx; r.o[1] = sy; r.o[2] = sz; r.d[0] = sunX; r.d[1] = sunY; r.d[2] = sunZ;
 			}
+			__syncwarp();
+			if (onImage) {
+				const uint2* hp = contiguous ? stage + lane * 5u : reinterpret_cast<const uint2*>(io.hits + i % w.pixels);
+				const uint2 a = hp[0], b = hp[1], c = hp[2], d = hp[3], e = hp[4];
+				h.hit = a.x; h.distance = __uint_as_float(a.y); h.material = b.x;
+				h.position[0] = __uint_as_float(b.y); h.position[1] = __uint_as_float(c.x); h.position[2] = __uint_as_float(c.y);
+				h.normal[0] = __uint_as_float(d.x); h.normal[1] = __uint_as_float(d.y); h.normal[2] = __uint_as_float(e.x);
+				live = h.hit != 0;
+				finished = !live;
+			}
+			__syncwarp();                                        // the stage turns from input to output
+			const unsigned liveMask = __ballot_sync(kFullMask, live);
+			const uint32_t rank = (uint32_t)__popc(liveMask & below), survivors = (uint32_t)__popc(liveMask);
+			const uint64_t j = slot + rank;
+			unsigned sunMask = 0u;
+			if (sharedSun && base < (uint64_t)w.pixels) {
+				const uint64_t left = (uint64_t)w.pixels - base;
+				sunMask = left >= 32u ? liveMask : (liveMask & ((1u << (unsigned)left) - 1u));
+			}
+			const uint64_t sunJ = sunSlot + (uint64_t)__popc(sunMask & below);
+
+			if (finished) {
+				// a missed bounce adds nothing in traceSingleRay (:168-180); everywhere else a miss is the sky (:124, :152)
+				const bool dark = (w.p.variant == CBQ_VARIANT_ONE_BOUNCE) && kDepth == 1;
+				io.radiance[pixel] = foldPath<kDepth>((int)w.p.variant, hst, dark ? 0.0f : 0.8f, dark ? 0.0f : 0.8f, dark ? 0.0f : 1.0f);
+			}
+			if (live) {
+				float cr, cg, cb;
+				surfaceColour(io.colours, h.material, h.position, w.p.add_noise != 0, cr, cg, cb);   // :45-60
+				const float nx = h.normal[0], ny = h.normal[1], nz = h.normal[2];
+				const float sunTerm = w.p.include_sun ? 0.1f * maxStd(dot3(sunX, sunY, sunZ, nx, ny, nz), 0.0f) : 0.0f;
+
+				// the path's history moves to its new slot; D[kDepth] waits for its flags
+#pragma unroll
+				for (int k = 0; k < kDepth; k++) io.nxt.hist[(size_t)k * io.capacity + j] = hst[k];
+				io.nxt.hist[(size_t)kDepth * io.capacity + j] = make_float4(cr, cg, cb, sunTerm);
+
+				// gatherLighting (:81-118): both shadow rays leave from position + normal * 0.001
+				const float sx = h.position[0] + nx * 0.001f, sy = h.position[1] + ny * 0.001f, sz = h.position[2] + nz * 0.001f;
+				uint32_t k = 0;
+				if (w.p.include_sun) {
+					if (sharedSun) {
+						if ((sunMask >> lane) & 1u) {
+							storeRay(io.sunRays, sunJ, sx, sy, sz, sunX, sunY, sunZ);
+							io.sunPixel[sunJ] = (uint32_t)i;
+						}
+					} else {
+						stageRay(stage, rank * perPath + k++, sx, sy, sz, sunX, sunY, sunZ);
+					}
+				}
+				if (w.p.include_sky) {
+					float rx, ry, rz;
+					unitBallPoint(ballLut, rng, rx, ry, rz);
+					const float vx = nx + rx, vy = ny + ry, vz = nz + rz;
+					const float len = sqrtf(dot3(vx, vy, vz, vx, vy, vz));
+					stageRay(stage, rank * perPath + k++, sx, sy, sz, vx / len, vy / len, vz / len);
+				}
+				// The bounce direction is drawn whenever the reference draws it: always in the recursive variant
+				// (before its depth check, :138-141 then :122), only at depth 0 in traceSingleRay (:165).
+				if ((w.p.variant == CBQ_VARIANT_RECURSIVE) || kDepth == 0) {
+					float rx, ry, rz;
+					unitBallPoint(ballLut, rng, rx, ry, rz);
+					if (bounces) {
+						const float vx = nx + rx, vy = ny + ry, vz = nz + rz;
+						const float len = sqrtf(dot3(vx, vy, vz, vx, vy, vz));
+						stageRay(stage + 32 * 2 * 3, rank, h.position[0] + (nx * 0.01f), h.position[1] + (ny * 0.01f), h.position[2] + (nz * 0.01f), vx / len, vy / len, vz / len);
+					}
+				}
+				io.nxt.pixel[j] = pixel;
+				io.nxt.rng[j] = rng;
+			}
+			__syncwarp();
+			// the survivors' rays leave for their consecutive slots
+			{
+				uint2* __restrict__ dst = reinterpret_cast<uint2*>(io.shadowRays + slot * perPath);
+				for (uint32_t t = lane; t < survivors * perPath * 3u; t += 32u) dst[t] = stage[t];
+			}
+			if (bounces) {
+				uint2* __restrict__ dst = reinterpret_cast<uint2*>(io.nxt.rays + slot);
+				for (uint32_t t = lane; t < survivors * 3u; t += 32u) dst[t] = stage[32 * 2 * 3 + t];
+			}
+			__syncwarp();
+			slot += survivors;
+			sunSlot += (uint64_t)__popc(sunMask);
 		}
-		if (w.p.include_sky) {
-			Ray& r = io.shadowRays[j * perPath + k++];
-			r.o[0] = sx; r.o[1] = sy; r.o[2] = sz; r.d[0] = skyX; r.d[1] = skyY; r.d[2] = skyZ;
-		}
-		if (kDepth != w.lastDepth && ((w.p.variant == CBQ_VARIANT_RECURSIVE) || kDepth == 0)) {
-			Ray& r = io.nxt.rays[j];
-			r.o[0] = h.position[0] + (nx * 0.01f); r.o[1] = h.position[1] + (ny * 0.01f); r.o[2] = h.position[2] + (nz * 0.01f);
-			r.d[0] = bncX; r.d[1] = bncY; r.d[2] = bncZ;
-		}
-		io.nxt.pixel[j] = pixel;
-		io.nxt.rng[j] = rng;
 	}
 }
 
@@ -287,8 +364,11 @@ lightKernel(WaveParams w, ShadeIo io)
 	const uint64_t count = (uint64_t)(*io.pathCount);
 	for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (uint64_t)gridDim.x * blockDim.x) {
 		const uint32_t pixel = io.cur.pixel[j];
-		const float d = directLight<kLevels>(w, io, j, pixel, io.cur.hist[(size_t)(kLevels - 1) * io.capacity + j].w);
-		io.radiance[pixel] = foldPath<kLevels>((int)w.p.variant, io.cur.hist, io.capacity, j, d, 0.0f, 0.0f, 0.0f);
+		float4 hst[kMaxDepth];
+#pragma unroll
+		for (int k = 0; k < kLevels; k++) hst[k] = io.cur.hist[(size_t)k * io.capacity + j];
+		hst[kLevels - 1].w = directLight<kLevels>(w, io, j, pixel, hst[kLevels - 1].w);
+		io.radiance[pixel] = foldPath<kLevels>((int)w.p.variant, hst, 0.0f, 0.0f, 0.0f);
 	}
 }
 
@@ -296,11 +376,13 @@ lightKernel(WaveParams w, ShadeIo io)
 __global__ void __launch_bounds__(256)
 rngPointsKernel(const uint32_t* __restrict__ seeds, uint64_t n, int draws, float* __restrict__ points, uint32_t* __restrict__ states)
 {
+	__shared__ float ballLut[kBallLutSize];
+	fillBallLut(ballLut);
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
 		uint32_t rng = seeds[i];
 		for (int d = 0; d < draws; d++) {
 			float x, y, z;
-			unitBallPoint(rng, x, y, z);
+			unitBallPoint(ballLut, rng, x, y, z);
 			float* p = points + 3 * (i * (uint64_t)draws + d);
 			p[0] = x; p[1] = y; p[2] = z;
 		}
@@ -342,11 +424,14 @@ int wavefrontReserve(WavefrontBuffers& b, size_t paths, size_t pixels)
 	}
 	CBQ_TRY(grow(b.shadowRays, 2 * paths));
 	CBQ_TRY(grow(b.shadowFlags, 2 * paths));
+	CBQ_TRY(grow(b.hitFlags, paths));
 	CBQ_TRY(grow(b.sunRays, pixels));
 	CBQ_TRY(grow(b.sunFlags, pixels));
-	CBQ_TRY(grow(b.sunSlot, pixels));
+	CBQ_TRY(grow(b.sunPixel, pixels));
+	CBQ_TRY(grow(b.pixelHash, pixels));
+	CBQ_TRY(grow(b.onImage, pixels));
 	CBQ_TRY(grow(b.radiance, paths));
-	if (!b.counters) CBQ_TRY(cudaMalloc(&b.counters, 8 * sizeof(unsigned long long)));
+	if (!b.counters) CBQ_TRY(cudaMalloc(&b.counters, 16 * sizeof(unsigned long long)));
 #undef CBQ_TRY
 	b.pathCapacity = paths;
 	b.pixelCapacity = pixels;
@@ -357,22 +442,32 @@ void wavefrontRelease(WavefrontBuffers& b)
 {
 	cudaFree(b.hits);
 	for (int i = 0; i < 2; i++) { cudaFree(b.rays[i]); cudaFree(b.pixel[i]); cudaFree(b.rng[i]); cudaFree(b.hist[i]); }
-	cudaFree(b.shadowRays); cudaFree(b.shadowFlags); cudaFree(b.sunRays); cudaFree(b.sunFlags); cudaFree(b.sunSlot);
+	cudaFree(b.shadowRays); cudaFree(b.shadowFlags); cudaFree(b.hitFlags); cudaFree(b.sunRays); cudaFree(b.sunFlags); cudaFree(b.sunPixel); cudaFree(b.pixelHash); cudaFree(b.onImage);
 	cudaFree(b.radiance); cudaFree(b.counters);
 	b = WavefrontBuffers();
 }
 
 namespace {
 
-void launchShade(int depth, int grid, cudaStream_t stream, const WaveParams& w, const ShadeIo& io)
+// One resident wave exactly: every CTA gets the same share of the batch, so a partial second wave would run at a
+// fraction of the machine for as long as the first.
+template <int kDepth>
+void launchShadeAt(int smCount, cudaStream_t stream, const WaveParams& w, const ShadeIo& io)
+{
+	static int perSm = 0;
+	if (perSm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, shadeKernel<kDepth>, 256, 0) != cudaSuccess || perSm <= 0)) perSm = 4;
+	shadeKernel<kDepth><<<smCount * perSm, 256, 0, stream>>>(w, io);
+}
+
+void launchShade(int depth, int smCount, cudaStream_t stream, const WaveParams& w, const ShadeIo& io)
 {
 	switch (depth) {
-	case 0: shadeKernel<0><<<grid, 256, 0, stream>>>(w, io); break;
-	case 1: shadeKernel<1><<<grid, 256, 0, stream>>>(w, io); break;
-	case 2: shadeKernel<2><<<grid, 256, 0, stream>>>(w, io); break;
-	case 3: shadeKernel<3><<<grid, 256, 0, stream>>>(w, io); break;
-	case 4: shadeKernel<4><<<grid, 256, 0, stream>>>(w, io); break;
-	default: shadeKernel<5><<<grid, 256, 0, stream>>>(w, io); break;
+	case 0: launchShadeAt<0>(smCount, stream, w, io); break;
+	case 1: launchShadeAt<1>(smCount, stream, w, io); break;
+	case 2: launchShadeAt<2>(smCount, stream, w, io); break;
+	case 3: launchShadeAt<3>(smCount, stream, w, io); break;
+	case 4: launchShadeAt<4>(smCount, stream, w, io); break;
+	default: launchShadeAt<5>(smCount, stream, w, io); break;
 	}
 }
 
@@ -421,14 +516,20 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 		w.sampleIndex = p.frame_id + s0;
 		w.paths = w.pixels * group;
 		if ((size_t)w.paths > b.pathCapacity || (size_t)w.pixels > b.pixelCapacity) return cudaErrorInvalidValue;
-		e = cudaMemsetAsync(b.counters, 0, 8 * sizeof(unsigned long long), stream);
+		e = cudaMemsetAsync(b.counters, 0, 16 * sizeof(unsigned long long), stream);
 		if (e != cudaSuccess) return e;
+		if (s0 == 0) {
+			seedKernel<<<shadeGrid, 256, 0, stream>>>(w, b.pixelHash, b.onImage);     // the same for every wave of the call
+			e = cudaGetLastError();
+			if (e != cudaSuccess) return e;
+			*launches += 1;
+		}
 		for (int d = 0; d <= w.lastDepth; d++) {
 			const int cur = d & 1, nxt = cur ^ 1;   // path sets ping-pong: depth d reads [cur], writes [nxt]
 			// ---- surface rays of this depth
 			TraceArgs t;
 			memset(&t, 0, sizeof(t));
-			t.volume = a.volume; t.hits = b.hits; t.maxFootprint = p.max_footprint; t.abandoned = a.abandoned;
+			t.volume = a.volume; t.hits = b.hits; t.flags = b.hitFlags; t.maxFootprint = p.max_footprint; t.abandoned = a.abandoned;
 			if (nextQueue(user, stream, &t.queue) != 0) return cudaErrorUnknown;
 			if (d == 0) {
 				// one primary ray per PIXEL: the samples of the group share it
@@ -450,10 +551,12 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 			io.capacity = b.pathCapacity;
 			io.pathCount = d ? b.counters + (d - 1) : nullptr;
 			io.liveCount = b.counters + d;
+			io.tickets = b.counters + 8 + d;
 			io.shadowRays = b.shadowRays; io.shadowFlags = b.shadowFlags;
-			io.sunCount = sunCount; io.sunRays = b.sunRays; io.sunSlot = b.sunSlot; io.sunFlags = b.sunFlags;
+			io.hitFlags = b.hitFlags; io.pixelHash = b.pixelHash; io.onImage = b.onImage;
+			io.sunCount = sunCount; io.sunRays = b.sunRays; io.sunPixel = b.sunPixel; io.sunFlags = b.sunFlags;
 			io.radiance = b.radiance;
-			launchShade(d, shadeGrid, stream, w, io);
+			launchShade(d, cfg.smCount, stream, w, io);
 			e = cudaGetLastError();
 			if (e != cudaSuccess) return e;
 			*launches += 2;
@@ -463,7 +566,7 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 			if (sharedSun) {
 				TraceArgs sh;
 				memset(&sh, 0, sizeof(sh));
-				sh.volume = a.volume; sh.rays = b.sunRays; sh.flags = b.sunFlags;
+				sh.volume = a.volume; sh.rays = b.sunRays; sh.flags = b.sunFlags; sh.flagIndex = b.sunPixel;
 				sh.maxFootprint = p.max_footprint; sh.abandoned = a.abandoned;
 				sh.countPtr = sunCount; sh.countScale = 1; sh.count = w.pixels;
 				if (nextQueue(user, stream, &sh.queue) != 0) return cudaErrorUnknown;
