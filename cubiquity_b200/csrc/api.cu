@@ -126,6 +126,7 @@ struct cbq_context {
 	// Volume buffers and bake work space come from a private stream-ordered pool that keeps what is freed
 	// (release threshold = max): a re-upload or a bake of a multi-GB DAG does not pay cudaMalloc/cudaFree each time.
 	cudaMemPool_t pool = nullptr;
+	int denseBrickLog2 = 0;              // cbq_build_dense: 0 = one piece up to 1024^3, bricks of 512^3 beyond; else always bricks of this size
 
 	// The volume: one linear device buffer.
 	uint8_t* volume = nullptr;
@@ -771,28 +772,144 @@ int cbq_bake(cbq_context* ctx, uint64_t* node_count, uint32_t* root_index)
 	return CBQ_OK;
 }
 
+namespace {
+
+// cbq_build_dense past 1024^3 (the complete octree of a 2048^3 grid has more nodes than a 32-bit index reaches, that
+// of a 4096^3 grid would not fit the memory either): the grid is cut into bricks of 2^brickLog2 voxels a side. Every
+// brick is built and merged on its own with the kernels of the one-piece build, its merged nodes are appended to one
+// collection (child indices shifted), and what is left above the bricks -- a complete octree over (side / brick)^3
+// references plus the chains to the height-32 root -- is a few hundred nodes made on the host. One last merge over the
+// collection removes what the bricks have in common. Same result as the one-piece build: the merged DAG of a voxel
+// set does not depend on the order it was assembled in (tests/test_gpu_update.py builds one grid both ways).
+int buildDenseBricked(cbq_context* ctx, const uint8_t* dVoxels, uint32_t k, const int32_t origin[3], uint32_t brickLog2)
+{
+	const uint32_t perAxisLog2 = k - brickLog2, perAxis = 1u << perAxisLog2;
+	const size_t side = (size_t)1 << k, brickSide = (size_t)1 << brickLog2;
+	const uint64_t treeNodes = cbq::denseNodeCount(brickLog2);
+	uint64_t slots = 0;
+	const size_t scratchBytes = cbq::bakeScratchBytes(treeNodes, &slots);
+	cudaStream_t s = ctx->stream;
+	uint8_t *dBrick = nullptr, *dTree = nullptr, *dScratch = nullptr, *dMerged = nullptr, *dAll = nullptr;
+	auto cleanup = [&]() { poolFree(ctx, dBrick); poolFree(ctx, dTree); poolFree(ctx, dScratch); poolFree(ctx, dMerged); poolFree(ctx, dAll); };
+#define CBQ_BRICK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cleanup(); return fail(e_ == cudaErrorMemoryAllocation ? CBQ_ERROR_OUT_OF_MEMORY : CBQ_ERROR_CUDA, "cbq_build_dense: %s failed: %s", #expr, cudaGetErrorString(e_)); } } while (0)
+	CBQ_BRICK(poolAlloc(ctx, &dBrick, brickSide * brickSide * brickSide));
+	CBQ_BRICK(poolAlloc(ctx, &dTree, (size_t)treeNodes * 32));
+	CBQ_BRICK(poolAlloc(ctx, &dScratch, scratchBytes + 256));
+	CBQ_BRICK(poolAlloc(ctx, &dMerged, (size_t)treeNodes * 32));
+	unsigned long long* dResults = reinterpret_cast<unsigned long long*>(dScratch + scratchBytes);   // [0..3] launchBake's, [4] the brick's own node
+	uint64_t capacity = std::max<uint64_t>(treeNodes, 1u << 22), count = cbq::kMaterialCount;      // [0, 256) of a merge input is never read
+	CBQ_BRICK(poolAlloc(ctx, &dAll, (size_t)capacity * 32));
+
+	std::vector<uint32_t> level((size_t)perAxis * perAxis * perAxis);      // what stands for each brick: a node of the collection, or a material
+	for (uint32_t bz = 0; bz < perAxis; bz++) for (uint32_t by = 0; by < perAxis; by++) for (uint32_t bx = 0; bx < perAxis; bx++) {
+		cudaMemcpy3DParms cp;
+		std::memset(&cp, 0, sizeof(cp));
+		cp.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(dVoxels), side, side, side);
+		cp.srcPos = make_cudaPos(bx * brickSide, by * brickSide, bz * brickSide);
+		cp.dstPtr = make_cudaPitchedPtr(dBrick, brickSide, brickSide, brickSide);
+		cp.extent = make_cudaExtent(brickSide, brickSide, brickSide);
+		cp.kind = cudaMemcpyDeviceToDevice;
+		CBQ_BRICK(cudaMemcpy3DAsync(&cp, s));
+		const int32_t brickOrigin[3] = { (int32_t)(origin[0] + (int64_t)(bx * brickSide)), (int32_t)(origin[1] + (int64_t)(by * brickSide)), (int32_t)(origin[2] + (int64_t)(bz * brickSide)) };
+		uint32_t root = 0;
+		uint64_t n = treeNodes;
+		CBQ_BRICK(cbq::launchBuildDense(dBrick, brickLog2, brickOrigin, reinterpret_cast<uint32_t*>(dTree), &root, &n, ctx->cfg.smCount, s, &ctx->launches));
+		CBQ_BRICK(cbq::launchBake(reinterpret_cast<const uint32_t*>(dTree), n, root, dScratch, slots, reinterpret_cast<uint32_t*>(dMerged), dResults, ctx->cfg.smCount, s, &ctx->launches));
+		CBQ_BRICK(cbq::launchBrickTop(reinterpret_cast<const uint32_t*>(dMerged), dResults, brickOrigin, brickLog2, reinterpret_cast<uint32_t*>(dResults + 4), s));
+		unsigned long long host[5];
+		CBQ_BRICK(cudaMemcpyAsync(host, dResults, sizeof(host), cudaMemcpyDeviceToHost, s));
+		CBQ_BRICK(cudaStreamSynchronize(s));
+		ctx->launches += 1; ctx->bytesD2H += sizeof(host);
+		if (host[0] != 0) { cleanup(); return fail(CBQ_ERROR_CORRUPT_VOLUME, "cbq_build_dense: brick (%u, %u, %u) did not merge", bx, by, bz); }
+		const uint64_t merged = host[1];
+		const uint32_t top = (uint32_t)host[4];
+		if (count + merged + 4096 > 0xffffffffull) { cleanup(); return fail(CBQ_ERROR_OUT_OF_MEMORY, "cbq_build_dense: more than 2^32 nodes before the last merge"); }
+		if (count + merged > capacity) {
+			const uint64_t bigger = std::max<uint64_t>(capacity * 2, count + merged);
+			uint8_t* grown = nullptr;
+			CBQ_BRICK(poolAlloc(ctx, &grown, (size_t)bigger * 32));
+			CBQ_BRICK(cudaMemcpyAsync(grown, dAll, (size_t)count * 32, cudaMemcpyDeviceToDevice, s));
+			poolFree(ctx, dAll);
+			dAll = grown; capacity = bigger;
+		}
+		const uint32_t delta = (uint32_t)(count - cbq::kMaterialCount);
+		CBQ_BRICK(cbq::launchAppendNodes(reinterpret_cast<const uint32_t*>(dMerged) + (size_t)cbq::kMaterialCount * 8, merged, delta,
+			reinterpret_cast<uint32_t*>(dAll) + (size_t)count * 8, ctx->cfg.smCount, s));
+		ctx->launches += 1;
+		level[((size_t)bz * perAxis + by) * perAxis + bx] = (top >= cbq::kMaterialCount) ? top + delta : top;
+		count += merged;
+	}
+	poolFree(ctx, dBrick); dBrick = nullptr;
+	poolFree(ctx, dTree); dTree = nullptr;
+	poolFree(ctx, dScratch); dScratch = nullptr;
+	poolFree(ctx, dMerged); dMerged = nullptr;
+
+	// The octree over the bricks, level by level until eight cubes are left, then their chains to the root.
+	std::vector<uint32_t> words;
+	uint32_t next = (uint32_t)count;                     // index the next host-made node gets
+	for (uint32_t cells = perAxis; cells > 2; cells /= 2) {
+		const uint32_t half = cells / 2;
+		std::vector<uint32_t> above((size_t)half * half * half);
+		for (uint32_t z = 0; z < half; z++) for (uint32_t y = 0; y < half; y++) for (uint32_t x = 0; x < half; x++) {
+			for (uint32_t c = 0; c < 8; c++)
+				words.push_back(level[((size_t)(2 * z + (c >> 2)) * cells + (2 * y + ((c >> 1) & 1u))) * cells + (2 * x + (c & 1u))]);
+			above[((size_t)z * half + y) * half + x] = next++;
+		}
+		level.swap(above);
+	}
+	uint32_t cubes[8];
+	for (uint32_t c = 0; c < 8; c++) cubes[c] = level[c];         // (z * 2 + y) * 2 + x, the order topTrie expects
+	std::vector<uint32_t> trie;
+	const uint32_t rootAt = cbq::topTrie(k, origin, cubes, next, trie);
+	const uint32_t root = next + rootAt;
+	words.insert(words.end(), trie.begin(), trie.end());
+	const uint64_t total = count + words.size() / 8;
+	if (total > capacity) {
+		uint8_t* grown = nullptr;
+		CBQ_BRICK(poolAlloc(ctx, &grown, (size_t)total * 32));
+		CBQ_BRICK(cudaMemcpyAsync(grown, dAll, (size_t)count * 32, cudaMemcpyDeviceToDevice, s));
+		poolFree(ctx, dAll);
+		dAll = grown; capacity = total;
+	}
+	CBQ_BRICK(cudaMemcpyAsync(dAll + (size_t)count * 32, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+	CBQ_BRICK(cudaStreamSynchronize(s));                          // `words` is ours
+#undef CBQ_BRICK
+	const int rc = bakeAndInstall(ctx, reinterpret_cast<const uint32_t*>(dAll), total, root, "cbq_build_dense");
+	poolFree(ctx, dAll);
+	return rc;
+}
+
+} // namespace
+
 int cbq_build_dense_device(cbq_context* ctx, const uint8_t* d_voxels, uint32_t size_log2, const int32_t origin[3],
 	const float* colours_rgb, uint64_t* node_count, uint32_t* root_index)
 {
 	int rc = bind(ctx); if (rc) return rc;
 	if (!d_voxels || !origin) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");
-	if (size_log2 < 2 || size_log2 > 10) return fail(CBQ_ERROR_INVALID_ARGUMENT, "size_log2 %u out of range (2..10: 4^3 .. 1024^3 voxels)", size_log2);
+	if (size_log2 < 2 || size_log2 > 12) return fail(CBQ_ERROR_INVALID_ARGUMENT, "size_log2 %u out of range (2..12: 4^3 .. 4096^3 voxels)", size_log2);
 	const uint32_t side = 1u << size_log2;
 	for (int a = 0; a < 3; a++) {
 		if (((uint32_t)origin[a] & (side / 2 - 1u)) != 0) return fail(CBQ_ERROR_INVALID_ARGUMENT, "origin[%d] = %d is not a multiple of half the grid side (%u)", a, origin[a], side / 2);
 		if ((int64_t)origin[a] + (int64_t)side > 0x80000000ll) return fail(CBQ_ERROR_INVALID_ARGUMENT, "the grid leaves the volume along axis %d", a);
 	}
-	uint64_t n = cbq::denseNodeCount(size_log2);
-	uint8_t* tree = nullptr;
-	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
-	CBQ_CUDA(poolAlloc(ctx, &tree, (size_t)n * 32));
-	uint32_t root = 0;
-	cudaError_t e = cbq::launchBuildDense(d_voxels, size_log2, origin, reinterpret_cast<uint32_t*>(tree), &root, &n, ctx->cfg.smCount, ctx->stream, &ctx->launches);
-	if (e != cudaSuccess) { poolFree(ctx, tree); return fail(CBQ_ERROR_CUDA, "cbq_build_dense: %s", cudaGetErrorString(e)); }
 	const bool hadVolume = ctx->volume != nullptr;
-	rc = bakeAndInstall(ctx, reinterpret_cast<const uint32_t*>(tree), n, root, "cbq_build_dense");
-	poolFree(ctx, tree);
-	if (rc) return rc;
+	// In one piece up to 1024^3; in bricks of 512^3 beyond, or of 2^dense_brick_log2 when that option asks for it.
+	const uint32_t brickLog2 = ctx->denseBrickLog2 ? (uint32_t)ctx->denseBrickLog2 : 9u;
+	CBQ_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (size_log2 > 10 || (ctx->denseBrickLog2 && brickLog2 < size_log2)) {
+		rc = buildDenseBricked(ctx, d_voxels, size_log2, origin, brickLog2);
+		if (rc) return rc;
+	} else {
+		uint64_t n = cbq::denseNodeCount(size_log2);
+		uint8_t* tree = nullptr;
+		CBQ_CUDA(poolAlloc(ctx, &tree, (size_t)n * 32));
+		uint32_t root = 0;
+		cudaError_t e = cbq::launchBuildDense(d_voxels, size_log2, origin, reinterpret_cast<uint32_t*>(tree), &root, &n, ctx->cfg.smCount, ctx->stream, &ctx->launches);
+		if (e != cudaSuccess) { poolFree(ctx, tree); return fail(CBQ_ERROR_CUDA, "cbq_build_dense: %s", cudaGetErrorString(e)); }
+		rc = bakeAndInstall(ctx, reinterpret_cast<const uint32_t*>(tree), n, root, "cbq_build_dense");
+		poolFree(ctx, tree);
+		if (rc) return rc;
+	}
 	if (colours_rgb || !hadVolume) { rc = cbq_set_colours(ctx, colours_rgb); if (rc) return rc; }
 	if (node_count) *node_count = ctx->nodeCount;
 	if (root_index) *root_index = ctx->root;
@@ -804,7 +921,7 @@ int cbq_build_dense(cbq_context* ctx, const uint8_t* voxels, uint32_t size_log2,
 {
 	int rc = bind(ctx); if (rc) return rc;
 	if (!voxels) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null argument");
-	if (size_log2 < 2 || size_log2 > 10) return fail(CBQ_ERROR_INVALID_ARGUMENT, "size_log2 %u out of range (2..10)", size_log2);
+	if (size_log2 < 2 || size_log2 > 12) return fail(CBQ_ERROR_INVALID_ARGUMENT, "size_log2 %u out of range (2..12)", size_log2);
 	const size_t bytes = (size_t)1 << (3 * size_log2);
 	uint8_t* d = nullptr;
 	CBQ_CUDA(poolAlloc(ctx, &d, bytes));
@@ -1448,6 +1565,9 @@ int cbq_set_option(cbq_context* ctx, const char* key, int64_t value)
 	} else if (k == "order_refresh") {
 		if (value < 1 || value > 1024) return fail(CBQ_ERROR_INVALID_ARGUMENT, "order_refresh must be in [1, 1024]");
 		ctx->orderRefresh = (int)value;
+	} else if (k == "dense_brick_log2") {
+		if (value != 0 && (value < 3 || value > 10)) return fail(CBQ_ERROR_INVALID_ARGUMENT, "dense_brick_log2 must be 0 (bricks of 512^3, past 1024^3 only) or in [3, 10]");
+		ctx->denseBrickLog2 = (int)value;
 	} else if (k == "park_results") {
 		ctx->parkResults = value ? 1 : 0;
 	} else if (k == "adaptive_order") {
@@ -1473,6 +1593,7 @@ int cbq_get_option(cbq_context* ctx, const char* key, int64_t* value)
 	else if (k == "l2_persist") *value = ctx->l2Persist;
 	else if (k == "adaptive_order") *value = ctx->adaptiveOrder;
 	else if (k == "park_results") *value = ctx->parkResults;
+	else if (k == "dense_brick_log2") *value = ctx->denseBrickLog2;
 	else if (k == "order_refresh") *value = ctx->orderRefresh;
 	else if (k == "sample_group") *value = ctx->cfg.sampleGroup;
 	else if (k == "sm_count") *value = ctx->cfg.smCount;

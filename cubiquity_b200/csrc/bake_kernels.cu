@@ -476,11 +476,43 @@ uint64_t denseNodeCount(uint32_t k)
 	return n + 8 * (33 - k);                                  // room for the host-built top of the tree
 }
 
+// The ancestors of a 2^k grid's eight height-(k-1) cubes up to the height-32 root: at most 8 chains of 33 - k nodes,
+// shared where the cubes share a parent (one chain when the origin is a multiple of the side, up to eight when the
+// grid straddles 0). A tiny trie built on the host, slot = next bit of the unsigned position (make_position_unsigned /
+// extract_next_child_id, storage.cpp:45-67). `cubes[c]` is what stands for cube c = (z * 2 + y) * 2 + x (a node index
+// or a material); the trie's node i will live at index base + i; returns the root's i.
+uint32_t topTrie(uint32_t k, const int32_t origin[3], const uint32_t cubes[8], uint32_t base, std::vector<uint32_t>& words)
+{
+	struct Top { int h; uint64_t x, y, z; uint32_t child[8]; };
+	std::vector<Top> top;
+	auto nodeFor = [&](int h, uint64_t x, uint64_t y, uint64_t z) -> uint32_t {
+		for (size_t i = 0; i < top.size(); i++) if (top[i].h == h && top[i].x == x && top[i].y == y && top[i].z == z) return (uint32_t)i;
+		Top t; t.h = h; t.x = x; t.y = y; t.z = z;
+		for (int c = 0; c < 8; c++) t.child[c] = 0;
+		top.push_back(t);
+		return (uint32_t)(top.size() - 1);
+	};
+	const uint64_t u[3] = { (uint64_t)((uint32_t)origin[0] + 0x80000000u), (uint64_t)((uint32_t)origin[1] + 0x80000000u), (uint64_t)((uint32_t)origin[2] + 0x80000000u) };
+	const uint32_t rootAt = nodeFor(32, 0, 0, 0);
+	for (uint32_t c = 0; c < 8; c++) {
+		const uint64_t U[3] = { (u[0] >> (k - 1)) + (c & 1u), (u[1] >> (k - 1)) + ((c >> 1) & 1u), (u[2] >> (k - 1)) + (c >> 2) };
+		uint32_t cur = rootAt;
+		for (int h = 32; h >= (int)k; h--) {
+			const int bit = h - (int)k;
+			const uint32_t slot = (uint32_t)((U[0] >> bit) & 1u) | (uint32_t)(((U[1] >> bit) & 1u) << 1) | (uint32_t)(((U[2] >> bit) & 1u) << 2);
+			if (h == (int)k) { top[cur].child[slot] = cubes[c]; break; }
+			const uint32_t next = nodeFor(h - 1, U[0] >> bit, U[1] >> bit, U[2] >> bit);
+			top[cur].child[slot] = base + next;
+			cur = next;
+		}
+	}
+	words.resize(top.size() * 8);
+	for (size_t i = 0; i < top.size(); i++) for (int c = 0; c < 8; c++) words[i * 8 + c] = top[i].child[c];
+	return rootAt;
+}
+
 // Levels 1 .. k-1 are written on the device; what is left are the eight height-(k-1) cubes the grid consists of.
-// Their ancestors up to the height-32 root (at most 8 chains of 33 - k nodes, shared where the cubes share a
-// parent: one chain when the origin is a multiple of the side, up to eight when the grid straddles 0) are a tiny
-// trie built here on the host, slot = next bit of the unsigned position (make_position_unsigned /
-// extract_next_child_id, storage.cpp:45-67).
+// Their ancestors up to the height-32 root are topTrie's.
 cudaError_t launchBuildDense(const uint8_t* voxels, uint32_t k, const int32_t origin[3], uint32_t* nodes, uint32_t* root, uint64_t* nodeCount,
 	int smCount, cudaStream_t stream, uint64_t* launches)
 {
@@ -501,37 +533,53 @@ cudaError_t launchBuildDense(const uint8_t* voxels, uint32_t k, const int32_t or
 		base += (uint32_t)cells;
 	}
 	// childBase .. childBase + 8: the height-(k-1) cubes, index (z * 2 + y) * 2 + x within the grid.
-	struct Top { int h; uint64_t x, y, z; uint32_t child[8]; };
-	std::vector<Top> top;
-	auto nodeFor = [&](int h, uint64_t x, uint64_t y, uint64_t z) -> uint32_t {
-		for (size_t i = 0; i < top.size(); i++) if (top[i].h == h && top[i].x == x && top[i].y == y && top[i].z == z) return (uint32_t)i;
-		Top t; t.h = h; t.x = x; t.y = y; t.z = z;
-		for (int c = 0; c < 8; c++) t.child[c] = 0;
-		top.push_back(t);
-		return (uint32_t)(top.size() - 1);
-	};
-	const uint64_t u[3] = { (uint64_t)((uint32_t)origin[0] + 0x80000000u), (uint64_t)((uint32_t)origin[1] + 0x80000000u), (uint64_t)((uint32_t)origin[2] + 0x80000000u) };
-	const uint32_t rootAt = nodeFor(32, 0, 0, 0);
-	for (uint32_t c = 0; c < 8; c++) {
-		const uint64_t U[3] = { (u[0] >> (k - 1)) + (c & 1u), (u[1] >> (k - 1)) + ((c >> 1) & 1u), (u[2] >> (k - 1)) + (c >> 2) };
-		uint32_t cur = rootAt;
-		for (int h = 32; h >= (int)k; h--) {
-			const int bit = h - (int)k;
-			const uint32_t slot = (uint32_t)((U[0] >> bit) & 1u) | (uint32_t)(((U[1] >> bit) & 1u) << 1) | (uint32_t)(((U[2] >> bit) & 1u) << 2);
-			if (h == (int)k) { top[cur].child[slot] = childBase + c; break; }
-			const uint32_t next = nodeFor(h - 1, U[0] >> bit, U[1] >> bit, U[2] >> bit);
-			top[cur].child[slot] = base + next;
-			cur = next;
-		}
-	}
-	std::vector<uint32_t> words(top.size() * 8);
-	for (size_t i = 0; i < top.size(); i++) for (int c = 0; c < 8; c++) words[i * 8 + c] = top[i].child[c];
+	uint32_t cubes[8];
+	for (uint32_t c = 0; c < 8; c++) cubes[c] = childBase + c;
+	std::vector<uint32_t> words;
+	const uint32_t rootAt = topTrie(k, origin, cubes, base, words);
 	cudaError_t e = cudaMemcpyAsync(nodes + (size_t)base * 8, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream);
 	if (e != cudaSuccess) return e;
 	if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;     // `words` is on our stack frame
 	*root = base + rootAt;
-	*nodeCount = (uint64_t)base + top.size();
+	*nodeCount = (uint64_t)base + words.size() / 8;
 	if (launches) *launches += count;
+	return cudaGetLastError();
+}
+
+// Brick-wise dense build (cbq_build_dense past 1024^3): where does the merged DAG of ONE brick keep the brick itself?
+// Follow the position bits from the height-32 root (results[2]) down to height brickLog2; stops early at a material.
+__global__ void brickTopKernel(const uint32_t* __restrict__ nodes, const unsigned long long* __restrict__ results, uint32_t ux, uint32_t uy, uint32_t uz,
+	uint32_t brickLog2, uint32_t* top)
+{
+	uint32_t cur = (uint32_t)results[2];
+	for (int h = 32; h > (int)brickLog2 && cur >= kMaterialCount; h--) {
+		const int bit = h - 1;
+		const uint32_t slot = ((ux >> bit) & 1u) | (((uy >> bit) & 1u) << 1) | (((uz >> bit) & 1u) << 2);
+		cur = nodes[(size_t)cur * 8 + slot];
+	}
+	*top = cur;
+}
+
+// Append a brick's merged nodes [256, 256 + count) to the collection: child indices move by `delta`, materials stay.
+__global__ void __launch_bounds__(256) appendNodesKernel(const uint32_t* __restrict__ src, uint64_t words, uint32_t delta, uint32_t* __restrict__ dst)
+{
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint32_t c = src[i];
+		dst[i] = (c >= kMaterialCount) ? c + delta : c;
+	}
+}
+
+cudaError_t launchBrickTop(const uint32_t* nodes, const unsigned long long* results, const int32_t brickOrigin[3], uint32_t brickLog2, uint32_t* top, cudaStream_t stream)
+{
+	brickTopKernel<<<1, 1, 0, stream>>>(nodes, results, (uint32_t)brickOrigin[0] + 0x80000000u, (uint32_t)brickOrigin[1] + 0x80000000u,
+		(uint32_t)brickOrigin[2] + 0x80000000u, brickLog2, top);
+	return cudaGetLastError();
+}
+
+cudaError_t launchAppendNodes(const uint32_t* src, uint64_t count, uint32_t delta, uint32_t* dst, int smCount, cudaStream_t stream)
+{
+	if (count == 0) return cudaSuccess;
+	appendNodesKernel<<<gridFor(count * 8, smCount), 256, 0, stream>>>(src, count * 8, delta, dst);
 	return cudaGetLastError();
 }
 

@@ -1,5 +1,6 @@
 // Internal host-side declarations shared by api.cu and the kernel translation units.
 #pragma once
+#include <vector>
 
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -169,6 +170,11 @@ cudaError_t launchSubdags(const uint32_t* nodes, uint32_t nodeCount, uint32_t ro
 
 // Dense voxel grid -> complete (un-merged) octree below a height-32 root; launchBake then merges it.
 uint64_t denseNodeCount(uint32_t sizeLog2);   // upper bound: what to allocate
+// Host-built chains from a grid's eight half-side cubes up to the height-32 root (bake_kernels.cu).
+uint32_t topTrie(uint32_t sizeLog2, const int32_t origin[3], const uint32_t cubes[8], uint32_t base, std::vector<uint32_t>& words);
+// Brick-wise build: the brick's own node (or material) inside its merged DAG; re-indexed append of merged nodes.
+cudaError_t launchBrickTop(const uint32_t* nodes, const unsigned long long* results, const int32_t brickOrigin[3], uint32_t brickLog2, uint32_t* top, cudaStream_t stream);
+cudaError_t launchAppendNodes(const uint32_t* src, uint64_t count, uint32_t delta, uint32_t* dst, int smCount, cudaStream_t stream);
 cudaError_t launchBuildDense(const uint8_t* voxels, uint32_t sizeLog2, const int32_t origin[3], uint32_t* nodes, uint32_t* root, uint64_t* nodeCount,
 	int smCount, cudaStream_t stream, uint64_t* launches);
 

@@ -97,3 +97,49 @@ def test_build_argument_checks(gpu, api):
         gpu.build_dense(np.zeros((8, 8, 4), dtype=np.uint8), (0, 0, 0))
     with pytest.raises(api.CubiquityError):
         gpu.build_dense(np.zeros((2, 2, 2), dtype=np.uint8), (0, 0, 0))
+
+
+@pytest.mark.parametrize("side,origin,brick_log2", [(64, (-64, 0, 64), 4), (64, (-32, -32, -32), 5), (128, (0, 0, 0), 5), (32, (-2 ** 31, 0, 2 ** 31 - 32), 3)])
+def test_bricked_build_equals_setvoxel_plus_bake(gpu, ref, side, origin, brick_log2):
+    """The path cbq_build_dense takes past 1024^3 -- bricks built and merged one by one, a host-made top, one last merge --
+    forced onto small grids: the same canonical DAG as the reference's setVoxel + bake, empty and uniform bricks included."""
+    grid = blobs(side, seed=side + brick_log2)
+    grid[: side // 2, : side // 4, :] = 0                   # whole bricks of nothing ...
+    grid[side // 2:, side // 2:, side // 2:] = 5            # ... and of one material
+    gpu.set_option("dense_brick_log2", brick_log2)
+    try:
+        count, root = gpu.build_dense(grid, origin)
+    finally:
+        gpu.set_option("dense_brick_log2", 0)
+    nodes = gpu.download_nodes()
+    v = reference_volume(ref, grid, origin)
+    assert count == len(nodes) == len(v.nodes())
+    assert pyoracle.dag_signature(nodes, root) == pyoracle.dag_signature(v.nodes(), v.root())
+    one_piece, root1 = gpu.build_dense(grid, origin)
+    assert one_piece == count
+    assert pyoracle.dag_signature(gpu.download_nodes(), root1) == pyoracle.dag_signature(nodes, root)
+
+
+def test_build_2048_cubed(gpu, port):
+    """Past the one-piece limit: a 2048^3 grid (8.6 GB of voxels, 64 bricks of 512^3) that holds a 1024^3 model in one octant
+    is the same volume as the model built in one piece at the same place -- equal node count, equal signature, identical hits."""
+    import torch
+    dev = torch.device("cuda", 0)
+    small = torch.from_numpy(blobs(256, seed=11)).to(dev)
+    model = small.repeat_interleave(4, 0).repeat_interleave(4, 1).repeat_interleave(4, 2).contiguous()      # 1024^3
+    origin = (0, 0, -2048)
+    count1, root1 = gpu.build_dense(None, (0, 0, -1024), device_ptr=model.data_ptr(), size_log2=10)
+    nodes1 = gpu.download_nodes()
+    big = torch.zeros((2048, 2048, 2048), dtype=torch.uint8, device=dev)
+    big[1024:, :1024, :1024] = model                        # [z, y, x]: x, y in [0, 1024), z in [-1024, 0)
+    del model
+    count2, root2 = gpu.build_dense(None, origin, device_ptr=big.data_ptr(), size_log2=11)
+    del big
+    nodes2 = gpu.download_nodes()
+    assert count2 == count1
+    assert pyoracle.dag_signature(nodes2, root2) == pyoracle.dag_signature(nodes1, root1)
+    rays = mixed_rays(np.array([0.0, 0.0, -1024.0]), np.array([1024.0, 1024.0, 0.0]), 30000, seed=5)
+    sub = port.find_subdags(nodes2, root2)
+    assert gpu.subdags().tobytes() == sub.tobytes()
+    want_hits, _, _ = port.trace(nodes2, sub, rays, True, -1.0, threads=8)
+    assert_hits_identical(gpu.intersect_volume(rays, True, -1.0), want_hits, "2048^3 build")
