@@ -939,7 +939,7 @@ int cbq_voxelize(cbq_context* ctx, const float* triangles, const uint8_t* materi
 {
 	int rc = bind(ctx); if (rc) return rc;
 	if (!triangles || !materials || !origin || triangle_count == 0) return fail(CBQ_ERROR_INVALID_ARGUMENT, "null or empty mesh");
-	if (size_log2 < 2 || size_log2 > 10) return fail(CBQ_ERROR_INVALID_ARGUMENT, "size_log2 %u out of range (2..10: 4^3 .. 1024^3 voxels)", size_log2);
+	if (size_log2 < 2 || size_log2 > 11) return fail(CBQ_ERROR_INVALID_ARGUMENT, "size_log2 %u out of range (2..11: 4^3 .. 2048^3 voxels; the work space is 5 bytes per voxel)", size_log2);
 	if (background != 0) return fail(CBQ_ERROR_INVALID_ARGUMENT, "background must be material 0: everything outside the grid is empty");
 	if (triangle_count > 0x7fffffffull) return fail(CBQ_ERROR_INVALID_ARGUMENT, "too many triangles");
 	const uint32_t S = 1u << size_log2;

@@ -79,3 +79,19 @@ def test_thin_mesh_and_argument_checks(gpu, api, ref):
         gpu.voxelize(tris, mats, 2, log2, origin, background=1)
     with pytest.raises(api.CubiquityError):                      # origin not a multiple of S / 2
         gpu.voxelize(tris, mats, 2, log2, (8, 0, 0))
+
+
+def test_2048_grid_gives_the_voxels_of_the_1024_grid(gpu):
+    """Voxels are decided one by one from the mesh alone, so a mesh that fits [0, 1024)^3 voxelises to the same volume in a
+    2048^3 grid (43 GB of work space, dense build in bricks) as in a 1024^3 grid at the same origin: the canonical DAGs are equal."""
+    from oracle import pyoracle
+    k = 8.0
+    parts = [meshes.icosphere(np.array([40.3, 44.1, 50.7]) * k, 21.4 * k, 3, 3), meshes.icosphere(np.array([78.2, 70.9, 60.2]) * k, 17.8 * k, 3, 7),
+             meshes.box(np.array([20.25, 80.5, 30.75]) * k, np.array([100.6, 95.1, 41.2]) * k, 5)]
+    tris, mats = np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+    count1, root1, _ = gpu.voxelize(tris, mats, 11, 10, (0, 0, 0))
+    nodes1 = gpu.download_nodes()
+    count2, root2, _ = gpu.voxelize(tris, mats, 11, 11, (0, 0, 0))
+    nodes2 = gpu.download_nodes()
+    assert count2 == count1 > 10000
+    assert pyoracle.dag_signature(nodes2, root2) == pyoracle.dag_signature(nodes1, root1)
