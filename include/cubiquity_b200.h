@@ -171,7 +171,7 @@ int cbq_bake(cbq_context* ctx, uint64_t* node_count, uint32_t* root_index);
 
 /* Build the volume from a dense grid of material ids ON THE DEVICE: what the reference does one voxel at a time
  * with Volume::setVoxel (storage.cpp:396-438) followed by Volume::bake (:388-395). voxels[(z * S + y) * S + x],
- * S = 2^size_log2 (2 <= size_log2 <= 10), is the material of voxel origin + (x, y, z); origin must be a multiple
+ * S = 2^size_log2 (2 <= size_log2 <= 12: up to 4096^3; past 1024^3 the grid is built in bricks of 512^3, same result), is the material of voxel origin + (x, y, z); origin must be a multiple
  * of S / 2 per axis (so a grid centred on 0 is fine); everything outside the grid is empty (material 0). The complete octree over the grid is written
  * level by level (no per-voxel inserts), chained up to the height-32 root and hash-consed with the same kernels
  * as cbq_bake; the result -- the canonical DAG, i.e. the same node count and content as the reference's bake of
@@ -190,7 +190,7 @@ typedef struct cbq_mesh_info { float lower[3], upper[3]; uint32_t is_closed, is_
 int cbq_mesh_analyse(const float* triangles, uint64_t triangle_count, cbq_mesh_info* info);
 
 /* voxelize(volume, mesh, fill, background) (voxelization.cpp:692-744, with Mesh::build :765-823) on the device, into a grid of
- * S = 2^size_log2 voxels a side at `origin` (a multiple of S / 2 per axis, as for cbq_build_dense; 2 <= size_log2 <= 10) that
+ * S = 2^size_log2 voxels a side at `origin` (a multiple of S / 2 per axis, as for cbq_build_dense; 2 <= size_log2 <= 11: the work space is 5 bytes per voxel) that
  * becomes the context's volume, hash-consed like Volume::bake. triangles: triangle_count x 9 floats in voxel coordinates, user
  * order (later triangles win where several touch a voxel); materials: one id per triangle; thin = Mesh::isThin. A closed mesh is
  * filled: 6-separating shell by the topological test, every octree leaf next to or between the shells classified by the
