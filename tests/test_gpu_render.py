@@ -162,3 +162,22 @@ def test_band_interleaved_shares_tile_the_frame_exactly(gpu, port, api, scenes):
     part = gpu.render(cam, api.pt_params(w, h, spp=2, bounces=2, variant=1, rect=(10, 30, 80, 190), bands=(2, 1)))
     rows = np.array([30 <= y < 190 and (((y - 30) // 64) % 2) == 1 for y in range(h)])
     assert np.array_equal(part[rows][:, 10:80], whole[rows][:, 10:80]) and not part[~rows].any() and not part[:, :10].any()
+
+
+@pytest.mark.parametrize("sun,sky,bounces,spp", [(1, 0, 3, 5), (1, 1, 0, 3), (1, 1, 5, 2), (0, 1, 0, 2), (1, 0, 0, 17)])
+def test_shared_sun_ray_and_depth_limits(gpu, port, ref, api, scenes, sun, sky, bounces, spp):
+    """The depth-0 sun ray is traced once per pixel for all samples of a wave: sun only (no per-path shadow ray at depth 0,
+    one deeper), no bounces at all (the first shade kernel is also the last), the deepest recursion the API takes, more samples
+    than one wave holds, an odd image size (runs of 512 paths straddle sample boundaries) -- bit for bit the oracle's and the
+    reference's image."""
+    from oracle import pyoracle
+    sc = scenes("sphere_noise", 7)
+    gpu.upload(sc.nodes, sc.root, sc.colours)
+    cam, ocam = both_cameras(api, port, sc)
+    p = api.pt_params(83, 61, spp=spp, bounces=bounces, variant=api.VARIANT_RECURSIVE, include_sun=sun, include_sky=sky)
+    sd = port.find_subdags(sc.nodes, sc.root)
+    want, _, _ = port.render(sc.nodes, sd, sc.colours, ocam, oracle_params(pyoracle, p), threads=4)
+    got = gpu.render(cam, p)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    direct = reference_image(ref, sc, cam, p)
+    assert np.array_equal(got.view(np.uint32), direct.view(np.uint32))
