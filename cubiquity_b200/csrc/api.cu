@@ -549,6 +549,7 @@ int cbq_create(int device, cbq_context** out)
 	ctx->cfg.refillThreshold = 8;    // robust default: +68 % on incoherent rays, -7 % on coherent ones (profiles/r01_sweeps.md)
 	ctx->cfg.refillQuantum = 1;
 	ctx->cfg.stackLevels = 33;
+	ctx->cfg.secondaryRefill = 4; // 1080p, 16 spp, 4 bounces: 994-999 M spp/s for 1..6, 990 at 8, 967 at 12 (profiles/r02_analysis.md)
 	ctx->cfg.sampleGroup = 0;    // auto; 1080p, 4 bounces: 915 / 965 M spp/s for groups of 8 / 16 (profiles/r02_analysis.md)
 	*out = ctx;
 	return CBQ_OK;
@@ -1559,6 +1560,9 @@ int cbq_set_option(cbq_context* ctx, const char* key, int64_t value)
 	} else if (k == "refill_quantum") {
 		if (value < 1 || value > 32 || (value & (value - 1)) != 0) return fail(CBQ_ERROR_INVALID_ARGUMENT, "refill_quantum must be a power of two in [1, 32]");
 		ctx->cfg.refillQuantum = (int)value;
+	} else if (k == "pt_refill_threshold") {
+		if (value < 1 || value > 32) return fail(CBQ_ERROR_INVALID_ARGUMENT, "pt_refill_threshold must be in [1, 32]");
+		ctx->cfg.secondaryRefill = (int)value;
 	} else if (k == "sample_group") {
 		if (value < 0 || value > 16) return fail(CBQ_ERROR_INVALID_ARGUMENT, "sample_group must be 0 (auto) or in [1, 16]");
 		ctx->cfg.sampleGroup = (int)value;
@@ -1596,6 +1600,7 @@ int cbq_get_option(cbq_context* ctx, const char* key, int64_t* value)
 	else if (k == "dense_brick_log2") *value = ctx->denseBrickLog2;
 	else if (k == "order_refresh") *value = ctx->orderRefresh;
 	else if (k == "sample_group") *value = ctx->cfg.sampleGroup;
+	else if (k == "pt_refill_threshold") *value = ctx->cfg.secondaryRefill;
 	else if (k == "sm_count") *value = ctx->cfg.smCount;
 	else if (k == "stack_levels") *value = ctx->cfg.stackLevels;
 	else if (k == "l2_bytes") *value = ctx->prop.l2CacheSize;

@@ -76,6 +76,7 @@ struct LaunchConfig {
 	int refillQuantum;     // tickets are dealt in whole groups of this many (1, 2, 4, 8, 16 or 32)
 	int stackLevels;       // entries per lane in the shared-memory stack (max sub-DAG height + 1)
 	int sampleGroup;       // wavefront path tracer: samples of a pixel traced together (1..16)
+	int secondaryRefill;   // wavefront path tracer: refill threshold of the shadow- and bounce-ray casts (1..32)
 };
 
 // What a kernel needs to know about the uploaded volume (device pointers into the volume buffer).

@@ -508,6 +508,8 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 
 	const int shadeGrid = cfg.smCount * 8;
 	LaunchConfig surfaceCfg = cfg, shadowCfg = cfg;
+	const int secondaryRefill = cfg.secondaryRefill > 0 ? cfg.secondaryRefill : cfg.refillThreshold;
+	shadowCfg.refillThreshold = secondaryRefill;
 	unsigned long long* const sunCount = b.counters + 7;
 	cudaError_t e;
 	const uint32_t kGroup = (uint32_t)(cfg.sampleGroup > 0 ? cfg.sampleGroup : 1);
@@ -539,7 +541,7 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 				surfaceCfg.refillThreshold = 32;           // coherent tiles
 			} else {
 				t.rays = b.rays[cur]; t.countPtr = b.counters + (d - 1); t.countScale = 1; t.count = w.paths;
-				surfaceCfg.refillThreshold = cfg.refillThreshold;
+				surfaceCfg.refillThreshold = secondaryRefill;
 			}
 			e = launchTrace(t, true, surfaceCfg, stream);
 			if (e != cudaSuccess) return e;

@@ -340,6 +340,8 @@ int cbq_host_free(void* p);
 /* Options: "block_threads", "blocks_per_sm", "refill_threshold" (idle lanes of a warp that trigger a
  * mid-flight refill, 1..32), "l2_persist" (0/1), "sample_group" (samples of a
  * pixel the wavefront tracer traces together, 1..16; 0 = choose from the size of the rectangle),
+ * "pt_refill_threshold" (the refill threshold of the path tracer's shadow- and bounce-ray casts, 1..32, default 4),
+ * "dense_brick_log2" (cbq_build_dense: 0 = one piece up to 1024^3 and bricks of 512^3 beyond; 3..10 = always bricks of that size),
  * "adaptive_order" (0/1, default 1: coherent batches -- refill_threshold 32, cbq_raycast_frame_device -- record how
  * long each 32-ray ticket took, and the next launch over the same ray buffer, size and stream deals the tickets
  * longest first; a scheduling hint only, results do not depend on it), "park_results" (0/1, default 0: cbq_trace_compact_device already coalesces a warp's result stores when the result
