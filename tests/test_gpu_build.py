@@ -143,3 +143,22 @@ def test_build_2048_cubed(gpu, port):
     assert gpu.subdags().tobytes() == sub.tobytes()
     want_hits, _, _ = port.trace(nodes2, sub, rays, True, -1.0, threads=8)
     assert_hits_identical(gpu.intersect_volume(rays, True, -1.0), want_hits, "2048^3 build")
+
+
+def test_baseline_terrain_built_from_its_voxels(gpu, scenes):
+    """BASELINE configs[1]'s scene family at 512^3: every voxel evaluated on the device (tests/terrain_voxels.py, checked against the
+    scene library on the CPU), cbq_build_dense in bricks of 128^3 -> the DAG the host scene builder makes, node for node.
+    scripts/build_baseline_scene.py does the same at 4096^3."""
+    import torch
+    import terrain_voxels
+    k = 9
+    sc = scenes("terrain", k, 1)
+    n = 1 << k
+    grid = terrain_voxels.fill(torch.empty((n, n, n), dtype=torch.uint8, device="cuda"), k, 1)
+    gpu.set_option("dense_brick_log2", 7)
+    try:
+        count, root = gpu.build_dense(None, (-n // 2,) * 3, device_ptr=grid.data_ptr(), size_log2=k, colours=sc.colours)
+    finally:
+        gpu.set_option("dense_brick_log2", 0)
+    assert count == len(sc.nodes)
+    assert pyoracle.dag_signature(gpu.download_nodes(), root) == pyoracle.dag_signature(sc.nodes, sc.root)
