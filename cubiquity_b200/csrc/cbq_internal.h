@@ -102,7 +102,8 @@ struct TraceArgs {
 	// optional: batch size read on the device (count = *countPtr * countScale), flag-only results
 	const unsigned long long* countPtr;
 	uint32_t countScale;
-	uint8_t* flags;                  // alone: one byte per ray instead of a record (shadow rays); with `hits`: both
+	uint8_t* flags;                  // alone: one byte per ray instead of a record (shadow rays); with `pathHits`: both
+	uint4* pathHits;                 // path tracer: 16-byte records {position, material | normal bits | hit} (PathHitSink)
 	const uint32_t* flagIndex;       // flag-only results go to flags[flagIndex[slot]]
 	cbq_hit_compact* compact;        // != nullptr: 8-byte results (cbq_trace_compact) instead of `hits`
 	bool remoteResults;              // `compact` lives in another GPU's memory: coalesce the stores per warp (ParkedCompactSink)
@@ -132,7 +133,7 @@ struct RenderArgs {
 struct WavefrontBuffers {
 	size_t pathCapacity = 0;       // PATHS (pixels x samples per group) of the largest wave so far
 	size_t pixelCapacity = 0;      // pixels of the largest rectangle so far
-	Hit* hits = nullptr;           // surface hits of the current depth            [paths]
+	uint4* hits = nullptr;         // surface hits of the current depth, 16 bytes each (PathHitSink) [paths]
 	Ray* rays[2] = { nullptr, nullptr };        // bounce rays, ping-pong           [paths]
 	uint32_t* pixel[2] = { nullptr, nullptr };  // path id of each compacted slot   [paths]
 	uint32_t* rng[2] = { nullptr, nullptr };    // RNG state of each path           [paths]

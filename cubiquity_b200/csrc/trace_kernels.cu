@@ -174,14 +174,20 @@ struct FlagSink {
 	static constexpr bool kNeedsPosition = false;
 	__device__ __forceinline__ void write(uint64_t slot, const Hit& h) const { flags[slot] = (uint8_t)h.hit; }
 };
-// Path tracer, surface rays: the record plus a byte per ray that says hit or miss, so that the shade kernel can count
-// its survivors from one coalesced byte per path before it touches the records (wavefront_kernels.cu, pass 1).
-struct FullFlagSink {
+// Path tracer, surface rays: what the shade kernel needs of a hit in ONE 16-byte word -- position and compactRecord's code
+// (material, the six normal bits, hit) -- plus a byte per ray that says hit or miss, so that the shade kernel can count its
+// survivors from one coalesced byte per path before it touches the records (wavefront_kernels.cu, pass 1). One 128-bit
+// store per finished ray instead of five 64-bit ones, one coalesced 128-bit load per path on the other side.
+struct PathHitSink {
 	static constexpr bool kParked = false;
-	Hit* __restrict__ hits;
+	uint4* __restrict__ records;
 	uint8_t* __restrict__ flags;
 	static constexpr bool kNeedsPosition = true;
-	__device__ __forceinline__ void write(uint64_t slot, const Hit& h) const { storeHit(hits, slot, h); flags[slot] = (uint8_t)(h.hit != 0u); }
+	__device__ __forceinline__ void write(uint64_t slot, const Hit& h) const
+	{
+		records[slot] = make_uint4(__float_as_uint(h.position[0]), __float_as_uint(h.position[1]), __float_as_uint(h.position[2]), compactRecord(h).y);
+		flags[slot] = (uint8_t)(h.hit != 0u);
+	}
 };
 // Path tracer, depth-0 sun rays (one per lit pixel, compacted): the flag goes to the ray's PIXEL.
 struct ScatterFlagSink {
@@ -456,7 +462,7 @@ cudaError_t launchPersistentLod(const TraceArgs& a, const Source& src, const Sin
 template <typename Source>
 cudaError_t launchPersistent(const TraceArgs& a, bool surface, const Source& src, uint64_t tickets, const LaunchConfig& cfg, cudaStream_t stream)
 {
-	if (a.flags && a.hits) return launchPersistentLod<true>(a, src, FullFlagSink{ a.hits, a.flags }, tickets, cfg, stream);   // path tracer, surface rays
+	if (a.flags && a.pathHits) return launchPersistentLod<true>(a, src, PathHitSink{ a.pathHits, a.flags }, tickets, cfg, stream);   // path tracer, surface rays
 	if (a.flags) {
 		// Flag-only results are for shadow rays, which never ask for surface properties.
 		if (a.flagIndex) return launchPersistentLod<false>(a, src, ScatterFlagSink{ a.flags, a.flagIndex }, tickets, cfg, stream);

@@ -66,7 +66,7 @@ struct PathSet {
 };
 struct ShadeIo {
 	const float4* colours;
-	const Hit* hits;
+	const uint4* hits;                       // {position, material | normal bits << 8 | hit << 14} per surface ray
 	PathSet cur, nxt;
 	size_t capacity;                         // slots per history plane
 	const unsigned long long* pathCount;     // batch size (nullptr at depth 0: w.paths)
@@ -177,11 +177,11 @@ __device__ __forceinline__ bool survives(const WaveParams& w, const ShadeIo& io,
 	return io.hitFlags[i] != 0;
 }
 
-// Records and rays are 40- and 24-byte structures; a lane reading or writing its own costs the load/store unit one
-// sector request per lane and word, and that -- not DRAM, not instruction issue -- is what bounds this kernel
-// (profiles/r02_analysis.md, "Path tracer"). The 32 paths of a step are consecutive and so are the slots of their
-// survivors, so both move through a per-warp shared-memory stage: whole 8-byte words, consecutive lanes, consecutive addresses.
-constexpr int kStageWords = 32 * 2 * 3 + 32 * 3;   // uint2 words per warp: 32 x 2 shadow rays + 32 bounce rays (the 32 x 5 words of the hit records fit inside)
+// A lane reading or writing its own 24- or 40-byte structure costs the load/store unit one sector request per lane and
+// word, and that -- not DRAM, not instruction issue -- is what bounds this kernel (profiles/r02_analysis.md, "Path tracer").
+// Hits therefore arrive as one 16-byte word per path (PathHitSink), and the survivors' rays, whose slots are consecutive,
+// leave through a per-warp shared-memory stage: whole 8-byte words, consecutive lanes, consecutive addresses.
+constexpr int kStageWords = 32 * 2 * 3 + 32 * 3;   // uint2 words per warp: 32 x 2 shadow rays + 32 bounce rays
 
 __device__ __forceinline__ void stageRay(uint2* __restrict__ stage, uint32_t index, float ox, float oy, float oz, float dx, float dy, float dz)
 {
@@ -239,14 +239,6 @@ shadeKernel(WaveParams w, ShadeIo io)
 		// ---- pass 2: light the previous depth, fold the paths that end here, shade and spawn the survivors
 		for (uint64_t base = begin; base < end; base += 32u) {
 			const uint64_t i = base + lane;
-			const uint32_t valid = (uint32_t)((end - base < 32u) ? (end - base) : 32u);
-			// the step's hit records: depth 0 shares the pixel's primary hit between its samples
-			const uint64_t firstRecord = (kDepth == 0) ? base % w.pixels : base;
-			const bool contiguous = (kDepth != 0) || (firstRecord + valid <= (uint64_t)w.pixels);
-			if (contiguous) {
-				const uint2* __restrict__ src = reinterpret_cast<const uint2*>(io.hits + firstRecord);
-				for (uint32_t t = lane; t < valid * 5u; t += 32u) stage[t] = src[t];
-			}
 			bool live = false, finished = false;
 			uint32_t pixel = 0, rng = 0;
 			float4 hst[kMaxDepth];       // only [0, kDepth) is touched
@@ -267,17 +259,19 @@ shadeKernel(WaveParams w, ShadeIo io)
 					hst[kDepth > 0 ? kDepth - 1 : 0].w = directLight<kDepth>(w, io, i, pixel, hst[kDepth > 0 ? kDepth - 1 : 0].w);   // D[kDepth - 1] is complete now
 				}
 			}
-			__syncwarp();
 			if (onImage) {
-				const uint2* hp = contiguous ? stage + lane * 5u : reinterpret_cast<const uint2*>(io.hits + i % w.pixels);
-				const uint2 a = hp[0], b = hp[1], c = hp[2], d = hp[3], e = hp[4];
-				h.hit = a.x; h.distance = __uint_as_float(a.y); h.material = b.x;
-				h.position[0] = __uint_as_float(b.y); h.position[1] = __uint_as_float(c.x); h.position[2] = __uint_as_float(c.y);
-				h.normal[0] = __uint_as_float(d.x); h.normal[1] = __uint_as_float(d.y); h.normal[2] = __uint_as_float(e.x);
+				// depth 0: every sample of a pixel shares the pixel's primary hit
+				const uint4 rec = io.hits[(kDepth == 0) ? (i % w.pixels) : i];
+				h.hit = (rec.w >> 14) & 1u; h.material = rec.w & 0xffu;
+				h.position[0] = __uint_as_float(rec.x); h.position[1] = __uint_as_float(rec.y); h.position[2] = __uint_as_float(rec.z);
+#pragma unroll
+				for (int a = 0; a < 3; a++) {     // two bits per component: non-zero, sign (-0.0f included)
+					const uint32_t two = (rec.w >> (8 + 2 * a)) & 3u;
+					h.normal[a] = __uint_as_float(((two & 1u) ? 0x3f800000u : 0u) | ((two & 2u) ? 0x80000000u : 0u));
+				}
 				live = h.hit != 0;
 				finished = !live;
 			}
-			__syncwarp();                                        // the stage turns from input to output
 			const unsigned liveMask = __ballot_sync(kFullMask, live);
 			const uint32_t rank = (uint32_t)__popc(liveMask & below), survivors = (uint32_t)__popc(liveMask);
 			const uint64_t j = slot + rank;
@@ -531,7 +525,7 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 			// ---- surface rays of this depth
 			TraceArgs t;
 			memset(&t, 0, sizeof(t));
-			t.volume = a.volume; t.hits = b.hits; t.flags = b.hitFlags; t.maxFootprint = p.max_footprint; t.abandoned = a.abandoned;
+			t.volume = a.volume; t.pathHits = b.hits; t.flags = b.hitFlags; t.maxFootprint = p.max_footprint; t.abandoned = a.abandoned;
 			if (nextQueue(user, stream, &t.queue) != 0) return cudaErrorUnknown;
 			if (d == 0) {
 				// one primary ray per PIXEL: the samples of the group share it
