@@ -49,11 +49,16 @@ else:
         ctx.primary_rays_tiled_device(cam, W, H, rays.data_ptr() + f * W * H * 24, None, stream)
 hits = torch.zeros(n * (2 if args.compact else 10), dtype=torch.int32, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+times = []
 for _ in range(args.launches):
     flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     if args.compact:
         ctx.trace_compact_device(rays.data_ptr(), n, hits.data_ptr(), True, args.lod, stream)
     else:
         ctx.trace_device(rays.data_ptr(), n, hits.data_ptr(), True, args.lod, stream)
-torch.cuda.synchronize()
-print("done")
+    e1.record()
+    torch.cuda.synchronize()
+    times.append(e0.elapsed_time(e1))
+print("done: %d rays, ms per launch %s, last %.3f Grays/s" % (n, [round(t, 3) for t in times], n / times[-1] / 1e6))
