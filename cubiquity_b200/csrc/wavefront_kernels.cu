@@ -12,11 +12,11 @@
 // SAMPLE ORDER, so the result is bit-identical to tracing the samples one after another. Per depth d:
 //
 //   trace   surface rays of depth d  (d = 0: straight from the camera, 8x4-pixel tiles; d > 0: the
-//           compacted bounce-ray buffer)                         tracePersistent<surface>  -> 40-byte hits
+//           compacted bounce-ray buffer)                         tracePersistent<surface, PathHitSink> -> 16-byte hits + hit/miss bytes
 //   shade   one thread per path: first D[d-1] from the shadow flags of the previous depth (gatherLighting's sum);
 //           miss -> fold the path's radiance into its slot; hit -> c[d] = surfaceColour, draw the sky and bounce
-//           directions from the path's RNG stream, COMPACT the survivors with a warp ballot + one atomicAdd
-//           per warp, and emit for each survivor its shadow rays and its bounce ray
+//           directions from the path's RNG stream, COMPACT the survivors (slots reserved with one atomicAdd per run of
+//           512 paths, ranks by warp ballot), and emit for each survivor its shadow rays and its bounce ray
 //   trace   the shadow rays, flag-only results                   tracePersistent<!surface, FlagSink>
 // and after the last depth one `lightKernel` folds the paths that are still alive.
 //
