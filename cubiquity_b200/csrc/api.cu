@@ -797,7 +797,7 @@ int buildDenseBricked(cbq_context* ctx, const uint8_t* dVoxels, uint32_t k, cons
 	CBQ_BRICK(poolAlloc(ctx, &dTree, (size_t)treeNodes * 32));
 	CBQ_BRICK(poolAlloc(ctx, &dScratch, scratchBytes + 256));
 	CBQ_BRICK(poolAlloc(ctx, &dMerged, (size_t)treeNodes * 32));
-	unsigned long long* dResults = reinterpret_cast<unsigned long long*>(dScratch + scratchBytes);   // [0..3] launchBake's, [4] the brick's own node
+	unsigned long long* dResults = reinterpret_cast<unsigned long long*>(dScratch + scratchBytes);   // launchBake's four
 	uint64_t capacity = std::max<uint64_t>(treeNodes, 1u << 22), count = cbq::kMaterialCount;      // [0, 256) of a merge input is never read
 	CBQ_BRICK(poolAlloc(ctx, &dAll, (size_t)capacity * 32));
 
@@ -814,16 +814,18 @@ int buildDenseBricked(cbq_context* ctx, const uint8_t* dVoxels, uint32_t k, cons
 		const int32_t brickOrigin[3] = { (int32_t)(origin[0] + (int64_t)(bx * brickSide)), (int32_t)(origin[1] + (int64_t)(by * brickSide)), (int32_t)(origin[2] + (int64_t)(bz * brickSide)) };
 		uint32_t root = 0;
 		uint64_t n = treeNodes;
-		CBQ_BRICK(cbq::launchBuildDense(dBrick, brickLog2, brickOrigin, reinterpret_cast<uint32_t*>(dTree), &root, &n, ctx->cfg.smCount, s, &ctx->launches));
-		CBQ_BRICK(cbq::launchBake(reinterpret_cast<const uint32_t*>(dTree), n, root, dScratch, slots, reinterpret_cast<uint32_t*>(dMerged), dResults, ctx->cfg.smCount, s, &ctx->launches));
-		CBQ_BRICK(cbq::launchBrickTop(reinterpret_cast<const uint32_t*>(dMerged), dResults, brickOrigin, brickLog2, reinterpret_cast<uint32_t*>(dResults + 4), s));
-		unsigned long long host[5];
+		// No chain to the height-32 root per brick (its place in the volume is the top's business, below): the tree is
+		// brickLog2 levels tall, its root IS the brick, and the merge needs that many passes instead of 33.
+		CBQ_BRICK(cbq::launchBuildDense(dBrick, brickLog2, brickOrigin, reinterpret_cast<uint32_t*>(dTree), &root, &n, ctx->cfg.smCount, s, &ctx->launches, false));
+		CBQ_BRICK(cbq::launchBake(reinterpret_cast<const uint32_t*>(dTree), n, root, dScratch, slots, reinterpret_cast<uint32_t*>(dMerged), dResults, ctx->cfg.smCount, s, &ctx->launches,
+			brickLog2 + 2));
+		unsigned long long host[4];
 		CBQ_BRICK(cudaMemcpyAsync(host, dResults, sizeof(host), cudaMemcpyDeviceToHost, s));
 		CBQ_BRICK(cudaStreamSynchronize(s));
 		ctx->launches += 1; ctx->bytesD2H += sizeof(host);
 		if (host[0] != 0) { cleanup(); return fail(CBQ_ERROR_CORRUPT_VOLUME, "cbq_build_dense: brick (%u, %u, %u) did not merge", bx, by, bz); }
 		const uint64_t merged = host[1];
-		const uint32_t top = (uint32_t)host[4];
+		const uint32_t top = (uint32_t)host[2];      // the merged brick's root: a node, or a material if the brick is uniform
 		if (count + merged + 4096 > 0xffffffffull) { cleanup(); return fail(CBQ_ERROR_OUT_OF_MEMORY, "cbq_build_dense: more than 2^32 nodes before the last merge"); }
 		if (count + merged > capacity) {
 			const uint64_t bigger = std::max<uint64_t>(capacity * 2, count + merged);

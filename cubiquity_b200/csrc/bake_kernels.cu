@@ -514,7 +514,7 @@ uint32_t topTrie(uint32_t k, const int32_t origin[3], const uint32_t cubes[8], u
 // Levels 1 .. k-1 are written on the device; what is left are the eight height-(k-1) cubes the grid consists of.
 // Their ancestors up to the height-32 root are topTrie's.
 cudaError_t launchBuildDense(const uint8_t* voxels, uint32_t k, const int32_t origin[3], uint32_t* nodes, uint32_t* root, uint64_t* nodeCount,
-	int smCount, cudaStream_t stream, uint64_t* launches)
+	int smCount, cudaStream_t stream, uint64_t* launches, bool chain)
 {
 	// Material nodes are written by launchBake into ITS output; the input copy of them is never read (children < 256
 	// are ids, not indices), so [0, 256) of `nodes` stays untouched.
@@ -524,13 +524,21 @@ cudaError_t launchBuildDense(const uint8_t* voxels, uint32_t k, const int32_t or
 	uint64_t count = 1;
 	uint32_t childBase = base;
 	base += (uint32_t)leaves;
-	for (uint32_t j = 2; j + 1 <= k; j++) {
+	// chain == false (one brick of a larger grid, whose own position is dealt with by the caller): the levels go all the
+	// way up to the single node that is the whole grid, and that node is the root.
+	for (uint32_t j = 2; j + (chain ? 1u : 0u) <= k; j++) {
 		const uint32_t cellsLog2 = k - j;
 		const uint64_t cells = 1ull << (3 * cellsLog2);
 		denseInnerKernel<<<gridFor(cells, smCount), 256, 0, stream>>>(cellsLog2, base, childBase, nodes);
 		count++;
 		childBase = base;
 		base += (uint32_t)cells;
+	}
+	if (!chain) {
+		*root = childBase;                // the level of one cell written last (k >= 2)
+		*nodeCount = (uint64_t)base;
+		if (launches) *launches += count;
+		return cudaGetLastError();
 	}
 	// childBase .. childBase + 8: the height-(k-1) cubes, index (z * 2 + y) * 2 + x within the grid.
 	uint32_t cubes[8];
@@ -546,20 +554,7 @@ cudaError_t launchBuildDense(const uint8_t* voxels, uint32_t k, const int32_t or
 	return cudaGetLastError();
 }
 
-// Brick-wise dense build (cbq_build_dense past 1024^3): where does the merged DAG of ONE brick keep the brick itself?
-// Follow the position bits from the height-32 root (results[2]) down to height brickLog2; stops early at a material.
-__global__ void brickTopKernel(const uint32_t* __restrict__ nodes, const unsigned long long* __restrict__ results, uint32_t ux, uint32_t uy, uint32_t uz,
-	uint32_t brickLog2, uint32_t* top)
-{
-	uint32_t cur = (uint32_t)results[2];
-	for (int h = 32; h > (int)brickLog2 && cur >= kMaterialCount; h--) {
-		const int bit = h - 1;
-		const uint32_t slot = ((ux >> bit) & 1u) | (((uy >> bit) & 1u) << 1) | (((uz >> bit) & 1u) << 2);
-		cur = nodes[(size_t)cur * 8 + slot];
-	}
-	*top = cur;
-}
-
+// Brick-wise dense build (cbq_build_dense past 1024^3).
 // Append a brick's merged nodes [256, 256 + count) to the collection: child indices move by `delta`, materials stay.
 __global__ void __launch_bounds__(256) appendNodesKernel(const uint32_t* __restrict__ src, uint64_t words, uint32_t delta, uint32_t* __restrict__ dst)
 {
@@ -567,13 +562,6 @@ __global__ void __launch_bounds__(256) appendNodesKernel(const uint32_t* __restr
 		const uint32_t c = src[i];
 		dst[i] = (c >= kMaterialCount) ? c + delta : c;
 	}
-}
-
-cudaError_t launchBrickTop(const uint32_t* nodes, const unsigned long long* results, const int32_t brickOrigin[3], uint32_t brickLog2, uint32_t* top, cudaStream_t stream)
-{
-	brickTopKernel<<<1, 1, 0, stream>>>(nodes, results, (uint32_t)brickOrigin[0] + 0x80000000u, (uint32_t)brickOrigin[1] + 0x80000000u,
-		(uint32_t)brickOrigin[2] + 0x80000000u, brickLog2, top);
-	return cudaGetLastError();
 }
 
 cudaError_t launchAppendNodes(const uint32_t* src, uint64_t count, uint32_t delta, uint32_t* dst, int smCount, cudaStream_t stream)
@@ -616,8 +604,11 @@ cudaError_t launchSubdags(const uint32_t* nodes, uint32_t nodeCount, uint32_t ro
 // deeper than 32 levels), results[1] = distinct non-material nodes, results[2] = new root index,
 // results[3] = nodes reachable from the root before merging.
 cudaError_t launchBake(const uint32_t* nodes, uint64_t n64, uint32_t root, uint8_t* scratch, uint64_t tableSlots, uint32_t* out,
-	unsigned long long* results, int smCount, cudaStream_t stream, uint64_t* launches)
+	unsigned long long* results, int smCount, cudaStream_t stream, uint64_t* launches, uint32_t levels)
 {
+	// `levels`: an upper bound on the number of node levels below (and including) the root; 33 fits any volume. The
+	// brick-wise dense build knows its trees are 2^brickLog2 voxels tall and saves two thirds of the launches.
+	if (levels == 0 || levels > 33) levels = 33;
 	const uint32_t n = (uint32_t)n64;
 	const BakeScratch sc = carve(scratch, n64, tableSlots);
 	uint32_t* canon = sc.canon; uint32_t* newIndex = sc.newIndex; uint32_t* rep = sc.rep; uint32_t* flags = sc.flags;
@@ -631,14 +622,14 @@ cudaError_t launchBake(const uint32_t* nodes, uint64_t n64, uint32_t root, uint8
 	if ((e = cudaMemsetAsync(table, 0xff, tableSlots * 4, stream)) != cudaSuccess) return e;
 	const uint32_t chunks = (uint32_t)((n64 + kChunk - 1) / kChunk);
 	bakeInit<<<grid, 256, 0, stream>>>(n, root, mark, newIndex, rep, flags, sc.frontierA, sc.frontierB, sc.chunkRemaining, sc.chunkPending, chunks); count++;
-	for (uint32_t depth = 1; depth <= 33; depth++) {
+	for (uint32_t depth = 1; depth <= levels; depth++) {
 		uint8_t* cur = (depth & 1u) ? sc.frontierB : sc.frontierA;
 		uint8_t* next = (depth & 1u) ? sc.frontierA : sc.frontierB;
 		bakeReach<<<grid, 256, 0, stream>>>(nodes, n, depth, mark, cur, next, chunks); count++;
 	}
 	if ((e = cudaMemsetAsync(results, 0, 4 * sizeof(unsigned long long), stream)) != cudaSuccess) return e;
 	bakeCountReached<<<grid, 256, 0, stream>>>(n, mark, sc.chunkRemaining, chunks, counters, results); count++;
-	for (int pass = 0; pass < 33; pass++) {
+	for (uint32_t pass = 0; pass < levels; pass++) {
 		bakeResolve<<<grid, 256, 0, stream>>>(nodes, n, mark, newIndex, canon, sc.chunkRemaining, sc.chunkPending, chunks, counters);
 		bakeInsert<<<grid, 256, 0, stream>>>(n, newIndex, canon, table, (uint32_t)(tableSlots - 1), rep, sc.chunkRemaining, sc.chunkPending, chunks, counters);
 		count += 2;

@@ -164,7 +164,7 @@ cudaError_t launchRenderWavefront(const RenderArgs& a, WavefrontBuffers& b, cons
 // Device-side bake (bake_kernels.cu).
 size_t bakeScratchBytes(uint64_t nodeCount, uint64_t* tableSlots);
 cudaError_t launchBake(const uint32_t* nodes, uint64_t nodeCount, uint32_t root, uint8_t* scratch, uint64_t tableSlots, uint32_t* out,
-	unsigned long long* results, int smCount, cudaStream_t stream, uint64_t* launches);
+	unsigned long long* results, int smCount, cudaStream_t stream, uint64_t* launches, uint32_t levels = 33);
 // findSubDAGs on a device array; root is read from *rootPtr when rootPtr != nullptr. *status |= 1 on a runaway chain.
 // *worst = max(*worst, largest child word of nodes [0, count)): the device-side half of the child-index check.
 cudaError_t launchMaxChild(const uint32_t* nodes, uint64_t count, uint32_t* worst, int smCount, cudaStream_t stream);
@@ -174,11 +174,10 @@ cudaError_t launchSubdags(const uint32_t* nodes, uint32_t nodeCount, uint32_t ro
 uint64_t denseNodeCount(uint32_t sizeLog2);   // upper bound: what to allocate
 // Host-built chains from a grid's eight half-side cubes up to the height-32 root (bake_kernels.cu).
 uint32_t topTrie(uint32_t sizeLog2, const int32_t origin[3], const uint32_t cubes[8], uint32_t base, std::vector<uint32_t>& words);
-// Brick-wise build: the brick's own node (or material) inside its merged DAG; re-indexed append of merged nodes.
-cudaError_t launchBrickTop(const uint32_t* nodes, const unsigned long long* results, const int32_t brickOrigin[3], uint32_t brickLog2, uint32_t* top, cudaStream_t stream);
+// Brick-wise build: re-indexed append of a brick's merged nodes to the collection.
 cudaError_t launchAppendNodes(const uint32_t* src, uint64_t count, uint32_t delta, uint32_t* dst, int smCount, cudaStream_t stream);
 cudaError_t launchBuildDense(const uint8_t* voxels, uint32_t sizeLog2, const int32_t origin[3], uint32_t* nodes, uint32_t* root, uint64_t* nodeCount,
-	int smCount, cudaStream_t stream, uint64_t* launches);
+	int smCount, cudaStream_t stream, uint64_t* launches, bool chain = true);
 
 // Mesh voxeliser (voxelize_kernels.cu; host helpers in voxelize_host.cpp). Leaf records are 16 bytes.
 cudaError_t launchShell(const void* tris, uint32_t count, uint8_t* voxels, uint32_t gridLog2, const int32_t origin[3], int mode, uint8_t background, int thin,
